@@ -1,0 +1,810 @@
+// batch_host.cu -- host side of the drop-in boundary: ZstdBatchManager, NvcompV5BatchManager and the
+// extern "C" entry points, all thin marshalling over the two batch kernels.
+//
+// Mirrors the reference's interface for this path (same names, argument meaning, error behaviour):
+//   ZstdBatchManager            src/cuda_zstd_manager.cu:5540-6037
+//   NvcompV5BatchManager        src/cuda_zstd_nvcomp.cpp:192-644
+//   nvcomp_zstd_*_v5            src/cuda_zstd_nvcomp.cpp:766-840
+//   cuda_zstd_*                 src/cuda_zstd_c_api.cpp:18-211
+//   Status/config helpers       src/cuda_zstd_types.cpp:36-261, 831-950
+// What is different by design: no per-item host loop, no CPU route (cpu_threshold is ignored), no
+// allocation and no hidden streams inside a call -- one persistent kernel per batch on the caller's
+// stream, with pointer/size tables staged in the caller's workspace.
+#include "../../include/cuda_zstd_batch_c.h"
+#include "../../include/cuda_zstd_nvcomp.h"
+#include "zstd_device_api.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace cuda_zstd {
+
+// ============================================================================================
+// Status strings and the global last-error slot (reference src/cuda_zstd_types.cpp:25-141)
+// ============================================================================================
+const char *status_to_string(Status s) {
+  switch (static_cast<u32>(s)) {
+  case 0: return "SUCCESS";
+  case 1: return "ERROR_GENERIC";
+  case 2: return "ERROR_INVALID_PARAMETER";
+  case 3: return "ERROR_OUT_OF_MEMORY";
+  case 4: return "ERROR_CUDA_ERROR";
+  case 5: return "ERROR_INVALID_MAGIC";
+  case 6: return "ERROR_CORRUPT_DATA";
+  case 7: return "ERROR_BUFFER_TOO_SMALL";
+  case 8: return "ERROR_UNSUPPORTED_VERSION";
+  case 9: return "ERROR_DICTIONARY_MISMATCH";
+  case 10: return "ERROR_CHECKSUM_FAILED";
+  case 11: return "ERROR_IO";
+  case 12: return "ERROR_COMPRESSION";
+  case 13: return "ERROR_DECOMPRESSION";
+  case 14: return "ERROR_WORKSPACE_INVALID";
+  case 15: return "ERROR_STREAM_ERROR";
+  case 16: return "ERROR_ALLOCATION_FAILED";
+  case 17: return "ERROR_HASH_TABLE_FULL";
+  case 18: return "ERROR_SEQUENCE_ERROR";
+  case 19: return "ERROR_NOT_INITIALIZED";
+  case 20: return "ERROR_ALREADY_INITIALIZED";
+  case 21: return "ERROR_INVALID_STATE";
+  case 22: return "ERROR_TIMEOUT";
+  case 23: return "ERROR_CANCELLED";
+  case 24: return "ERROR_NOT_IMPLEMENTED";
+  case 25: return "ERROR_INTERNAL";
+  case 26: return "ERROR_UNKNOWN";
+  case 27: return "ERROR_DICTIONARY_FAILED";
+  case 28: return "ERROR_UNSUPPORTED_FORMAT";
+  default: return "UNKNOWN_STATUS";
+  }
+}
+
+namespace {
+std::mutex g_err_mu;
+ErrorContext g_last_err;
+ErrorCallback g_err_cb = nullptr;
+
+Status fail(Status s, const char *fn, const char *msg, cudaError_t ce = cudaSuccess) {
+  ErrorContext c(s, __FILE__, 0, fn, msg);
+  c.cuda_error = ce;
+  log_error(c);
+  return s;
+}
+Status cuda_fail(cudaError_t e, const char *fn) { return fail(Status::ERROR_CUDA_ERROR, fn, cudaGetErrorString(e), e); }
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+} // namespace
+
+const char *get_detailed_error_message(const ErrorContext &ctx) { return ctx.message ? ctx.message : status_to_string(ctx.status); }
+void set_error_callback(ErrorCallback cb) { std::lock_guard<std::mutex> l(g_err_mu); g_err_cb = cb; }
+void log_error(const ErrorContext &ctx) {
+  ErrorCallback cb;
+  { std::lock_guard<std::mutex> l(g_err_mu); g_last_err = ctx; cb = g_err_cb; }
+  if (cb) cb(ctx);
+}
+ErrorContext get_last_error() { std::lock_guard<std::mutex> l(g_err_mu); return g_last_err; }
+void clear_last_error() { std::lock_guard<std::mutex> l(g_err_mu); g_last_err = ErrorContext(); }
+
+// ============================================================================================
+// CompressionConfig (reference src/cuda_zstd_types.cpp:147-261, 860-950): same level bands
+// ============================================================================================
+Strategy CompressionConfig::level_to_strategy(int level) {
+  static const int upper[] = {1, 3, 6, 12, 15, 18, 20};
+  for (int i = 0; i < 7; ++i) if (level <= upper[i]) return static_cast<Strategy>(i);
+  return Strategy::BTULTRA;
+}
+int CompressionConfig::strategy_to_default_level(Strategy s) {
+  static const int lv[] = {1, 3, 5, 9, 13, 16, 19, 22};
+  u32 i = static_cast<u32>(s);
+  return i < 8 ? lv[i] : 3;
+}
+CompressionConfig CompressionConfig::from_level(int level) {
+  CompressionConfig c;
+  c.compression_mode = CompressionMode::LEVEL_BASED;
+  c.level = level;
+  c.use_exact_level = true;
+  c.strategy = level_to_strategy(level);
+  // table-size fields are informational in this build (the kernels size their own SMEM tables);
+  // they keep the reference's band values so get_config() round-trips look the same
+  struct Band { int upto; u32 wlog, hlog, clog; };
+  static const Band bands[] = {{1, 18, 15, 15}, {3, 19, 17, 17}, {6, 20, 17, 17}, {9, 22, 18, 18}, {12, 23, 19, 19},
+                               {14, 23, 19, 19}, {15, 23, 20, 19}, {22, 23, 20, 20}};
+  for (const Band &b : bands) if (level <= b.upto) { c.window_log = b.wlog; c.hash_log = b.hlog; c.chain_log = b.clog; break; }
+  static const u32 depth[] = {1, 1, 1, 1, 2, 4, 8, 8, 16, 32, 64, 128, 256, 256, 256, 512, 512, 512, 999, 999, 999, 999, 999};
+  c.search_log = depth[std::min(std::max(level, 0), 22)];
+  return c;
+}
+CompressionConfig CompressionConfig::get_default() { return from_level(static_cast<int>(DEFAULT_COMPRESSION_LEVEL)); }
+CompressionConfig CompressionConfig::optimal(size_t) { return from_level(3); }
+Status CompressionConfig::validate() const {
+  if (level < static_cast<int>(MIN_COMPRESSION_LEVEL) || level > static_cast<int>(MAX_COMPRESSION_LEVEL)) return Status::ERROR_INVALID_PARAMETER;
+  if (window_log < MIN_WINDOW_LOG || window_log > MAX_WINDOW_LOG) return Status::ERROR_INVALID_PARAMETER;
+  if (block_size < 1024) return Status::ERROR_INVALID_PARAMETER;
+  return Status::SUCCESS;
+}
+Status validate_config(const CompressionConfig &c) { return c.validate(); }
+void apply_level_parameters(CompressionConfig &c) {
+  CompressionConfig t = CompressionConfig::from_level(c.level);
+  c.strategy = t.strategy; c.window_log = t.window_log; c.hash_log = t.hash_log; c.chain_log = t.chain_log; c.search_log = t.search_log;
+}
+u32 get_optimal_block_size(u32 input_size, u32) { return std::min<u32>(std::max<u32>(input_size, 1024u), 128u * 1024u); }
+
+size_t estimate_compressed_size(size_t n, int) {
+  size_t blocks = (n + (128 * 1024 - 1)) / (128 * 1024);
+  if (blocks == 0) blocks = 1;
+  return n + n / 255 + blocks * 3 + 512;
+}
+
+ZstdManager::ExecutionPath ZstdManager::select_execution_path(size_t size, int cpu_threshold) {
+  return (cpu_threshold > 0 && size < static_cast<size_t>(cpu_threshold)) ? ExecutionPath::CPU : ExecutionPath::GPU_BATCH;
+}
+
+// ============================================================================================
+// frame-header peek on a HOST copy of the first bytes (reference parse_frame_header,
+// src/cuda_zstd_manager.cu:4108-4225, but with the single-segment 1-byte FCS handled per RFC)
+// ============================================================================================
+namespace {
+struct HeaderInfo { bool ok = false; bool has_size = false; u64 content_size = 0; bool checksum = false; u32 dict_id = 0; u32 header_bytes = 0; };
+HeaderInfo peek_header(const unsigned char *p, size_t n) {
+  HeaderInfo h;
+  if (n < 5) return h;
+  u32 magic = p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24);
+  if (magic != ZSTD_MAGIC) return h;
+  const u32 fhd = p[4];
+  const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did_flag = fhd & 3;
+  const int did = did_flag == 3 ? 4 : did_flag, fcs = fcs_flag == 0 ? single : (1 << fcs_flag);
+  size_t pos = 5 + (single ? 0 : 1);
+  if (pos + did + fcs > n) return h;
+  for (int k = 0; k < did; ++k) h.dict_id |= (u32)p[pos + k] << (8 * k);
+  pos += did;
+  if (fcs) {
+    for (int k = 0; k < fcs; ++k) h.content_size |= (u64)p[pos + k] << (8 * k);
+    if (fcs == 2) h.content_size += 256;
+    h.has_size = true;
+    pos += fcs;
+  }
+  h.checksum = (fhd >> 2) & 1;
+  h.header_bytes = (u32)pos;
+  h.ok = true;
+  return h;
+}
+} // namespace
+
+Status get_decompressed_size(const void *data, size_t size, size_t *out) {
+  if (!data || !out) return Status::ERROR_INVALID_PARAMETER;
+  unsigned char head[18];
+  size_t n = std::min<size_t>(size, sizeof head);
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+    if (cudaMemcpy(head, data, n, cudaMemcpyDeviceToHost) != cudaSuccess) return Status::ERROR_CUDA_ERROR;
+  } else { (void)cudaGetLastError(); std::memcpy(head, data, n); }
+  HeaderInfo h = peek_header(head, n);
+  if (!h.ok) return Status::ERROR_INVALID_MAGIC;
+  if (!h.has_size) return Status::ERROR_CORRUPT_DATA;
+  *out = (size_t)h.content_size;
+  return Status::SUCCESS;
+}
+bool is_nvcomp_zstd_format(const void *data, size_t size) {
+  size_t s = 0;
+  Status st = get_decompressed_size(data, size, &s);
+  return st == Status::SUCCESS || st == Status::ERROR_CORRUPT_DATA;
+}
+Status extract_metadata(const void *data, size_t size, NvcompMetadata &m) {
+  size_t s = 0;
+  Status st = get_decompressed_size(data, size, &s);
+  if (st != Status::SUCCESS) return st;
+  m = NvcompMetadata();
+  m.format_version = get_format_version();
+  m.uncompressed_size = s;
+  m.num_chunks = 1;
+  m.chunk_size = (u32)std::min<size_t>(s, 0xFFFFFFFFu);
+  return Status::SUCCESS;
+}
+
+// ============================================================================================
+// ZstdBatchManager
+// ============================================================================================
+// Workspace layout (caller-owned device memory), identical for both directions:
+//   [0, 256)                         work-queue counter and padding
+//   [256, 256 + align256(40 n))      staged tables: in_ptrs | in_sizes | out_ptrs | out_sizes | statuses
+//   [.., .. + grid * per_cta)        per-CTA scratch (literal buffer for decode; parse scratch for encode)
+// grid = min(n, SMs * resident CTAs) -- scratch scales with the GPU, not with the batch.
+class ZstdBatchManager::Impl {
+public:
+  CompressionConfig cfg;
+  CompressionStats stats;
+  int sm_count = 0;
+  int dec_ctas_per_sm = 1;
+  int last_launches = 0;
+  std::mutex mu;   // one manager per thread is the contract; the lock keeps misuse safe (reference: api_mutex)
+
+  Impl() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) { (void)cudaGetLastError(); sm_count = 148; }     // size queries still work without a device
+    dec_ctas_per_sm = b200zstd::decode_ctas_per_sm();
+    (void)cudaGetLastError();
+  }
+  b200zstd::EncodeParams enc_params() const {
+    return b200zstd::encode_params_for_level(cfg.level, cfg.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY);
+  }
+  int dec_grid(size_t n) const { return (int)std::min<size_t>(n, (size_t)sm_count * dec_ctas_per_sm); }
+  int enc_grid(size_t n) const {
+    int per = b200zstd::encode_ctas_per_sm(enc_params());
+    (void)cudaGetLastError();
+    return (int)std::min<size_t>(n, (size_t)sm_count * per);
+  }
+  static size_t table_bytes(size_t n) { return align_up(n * 40, 256); }
+  size_t dec_temp(size_t n) const {
+    if (n == 0) return 0;
+    // sized for a full grid so that one workspace serves any batch of up to n chunks
+    return b200zstd::WS_HEADER_BYTES + table_bytes(n) + (size_t)dec_grid(n) * b200zstd::LIT_SCRATCH_BYTES;
+  }
+  size_t enc_temp(size_t n) const {
+    if (n == 0) return 0;
+    size_t e = b200zstd::WS_HEADER_BYTES + table_bytes(n) + (size_t)enc_grid(n) * b200zstd::encode_cta_scratch_bytes(enc_params());
+    return std::max(e, dec_temp(n));      // a compress workspace can always be reused for decompress
+  }
+
+  // Direction-agnostic batch driver.  tables_on_device: the five tables already live in device
+  // memory (no staging, and with sync == false no host synchronisation at all).
+  Status run(bool compress, const void *const *in_ptrs, const size_t *in_sizes, size_t n, void *const *out_ptrs,
+             size_t *out_sizes, u32 *statuses, bool tables_on_device, void *ws, size_t ws_bytes, cudaStream_t stream,
+             bool sync, std::vector<u32> *host_status, std::vector<size_t> *host_out_sizes) {
+    const char *fn = compress ? "compress_batch" : "decompress_batch";
+    last_launches = 0;
+    if (n == 0) return Status::SUCCESS;
+    if (!in_ptrs || !in_sizes || !out_ptrs || !out_sizes) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null pointer table");
+    if (n > 0xFFFFFFF0ull) return fail(Status::ERROR_INVALID_PARAMETER, fn, "too many chunks");
+    const size_t need = compress ? enc_temp(n) : dec_temp(n);
+    if (!ws) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null workspace");
+    if (ws_bytes < need) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    u32 *counter = reinterpret_cast<u32 *>(w);
+    unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
+    unsigned char *scratch = tab + table_bytes(n);
+    const void *const *d_in = in_ptrs;
+    const size_t *d_in_sz = in_sizes;
+    void *const *d_out = out_ptrs;
+    size_t *d_out_sz = out_sizes;
+    u32 *d_status = statuses;
+    cudaError_t e;
+    if (!tables_on_device) {
+      // stage the four host tables into the workspace (4 async copies, stream-ordered)
+      const size_t b = n * 8;
+      if ((e = cudaMemcpyAsync(tab, in_ptrs, b, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+      if ((e = cudaMemcpyAsync(tab + b, in_sizes, b, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+      if ((e = cudaMemcpyAsync(tab + 2 * b, out_ptrs, b, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+      if ((e = cudaMemcpyAsync(tab + 3 * b, out_sizes, b, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+      d_in = reinterpret_cast<const void *const *>(tab);
+      d_in_sz = reinterpret_cast<const size_t *>(tab + b);
+      d_out = reinterpret_cast<void *const *>(tab + 2 * b);
+      d_out_sz = reinterpret_cast<size_t *>(tab + 3 * b);
+    }
+    if (!d_status) d_status = reinterpret_cast<u32 *>(tab + 4 * n * 8);
+    if (compress) {
+      b200zstd::EncodeArgs a{};
+      a.in_ptrs = d_in; a.in_sizes = d_in_sz; a.out_ptrs = d_out; a.out_sizes = d_out_sz; a.statuses = d_status;
+      a.counter = counter; a.scratch = scratch; a.n = (uint32_t)n; a.prm = enc_params();
+      e = b200zstd::launch_encode_batch(a, enc_grid(n), stream);
+    } else {
+      b200zstd::DecodeArgs a{};
+      a.in_ptrs = d_in; a.in_sizes = d_in_sz; a.out_ptrs = d_out; a.out_sizes = d_out_sz; a.statuses = d_status;
+      a.counter = counter; a.lit_scratch = scratch; a.n = (uint32_t)n;
+      a.verify_checksum = cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY;   // reference gates on the manager's policy (manager.cu:3654)
+      e = b200zstd::launch_decode_batch(a, dec_grid(n), stream);
+    }
+    last_launches = 1;
+    if (e != cudaSuccess) return cuda_fail(e, fn);
+    if (!sync) return Status::SUCCESS;
+    // results back to the host: sizes (when the caller's table is host memory) and statuses
+    std::vector<u32> st_local;
+    std::vector<u32> &st = host_status ? *host_status : st_local;
+    st.resize(n);
+    if ((e = cudaMemcpyAsync(st.data(), d_status, n * sizeof(u32), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if (!tables_on_device) {
+      if ((e = cudaMemcpyAsync(out_sizes, d_out_sz, n * 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    } else if (host_out_sizes) {
+      host_out_sizes->resize(n);
+      if ((e = cudaMemcpyAsync(host_out_sizes->data(), d_out_sz, n * 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    }
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);
+    Status overall = Status::SUCCESS;
+    for (size_t i = 0; i < n; ++i)
+      if (st[i] != 0) { overall = Status::ERROR_GENERIC; break; }
+    if (overall != Status::SUCCESS) {
+      Status first = Status::ERROR_GENERIC;
+      for (size_t i = 0; i < n; ++i) if (st[i] != 0) { first = static_cast<Status>(st[i]); break; }
+      fail(first, fn, "one or more chunks failed; see per-item status");
+    }
+    return overall;
+  }
+};
+
+ZstdBatchManager::ZstdBatchManager() : pimpl_(new Impl) { pimpl_->cfg = CompressionConfig::get_default(); }
+ZstdBatchManager::ZstdBatchManager(const CompressionConfig &c) : pimpl_(new Impl) {
+  pimpl_->cfg = CompressionConfig::get_default();
+  configure(c);
+}
+ZstdBatchManager::~ZstdBatchManager() = default;
+
+Status ZstdBatchManager::configure(const CompressionConfig &c) {
+  Status s = c.validate();
+  if (s != Status::SUCCESS) return s;
+  pimpl_->cfg = c;
+  return Status::SUCCESS;
+}
+CompressionConfig ZstdBatchManager::get_config() const { return pimpl_->cfg; }
+size_t ZstdBatchManager::get_compress_temp_size(size_t) const { return pimpl_->enc_temp(1); }
+size_t ZstdBatchManager::get_decompress_temp_size(size_t) const { return pimpl_->dec_temp(1); }
+size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
+size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size()); }
+size_t ZstdBatchManager::get_batch_decompress_temp_size(const std::vector<size_t> &v) const { return pimpl_->dec_temp(v.size()); }
+Status ZstdBatchManager::set_dictionary(const dictionary::Dictionary &) { return Status::ERROR_NOT_IMPLEMENTED; }
+Status ZstdBatchManager::get_dictionary(dictionary::Dictionary &) const { return Status::ERROR_NOT_IMPLEMENTED; }
+Status ZstdBatchManager::clear_dictionary() { return Status::SUCCESS; }
+const CompressionStats &ZstdBatchManager::get_stats() const { return pimpl_->stats; }
+Status ZstdBatchManager::set_compression_level(int level) {
+  if (level < 1 || level > 22) return Status::ERROR_INVALID_PARAMETER;      // level left unchanged (manager.cu:1517-1522)
+  ChecksumPolicy ck = pimpl_->cfg.checksum;
+  u32 bs = pimpl_->cfg.block_size;
+  pimpl_->cfg = CompressionConfig::from_level(level);
+  pimpl_->cfg.checksum = ck;
+  pimpl_->cfg.block_size = bs;
+  return Status::SUCCESS;
+}
+int ZstdBatchManager::get_compression_level() const { return pimpl_->cfg.level; }
+void ZstdBatchManager::reset_stats() { pimpl_->stats = CompressionStats(); }
+
+namespace {
+Status run_items(ZstdBatchManager::Impl &I, bool compress, const std::vector<BatchItem> &items, void *ws, size_t ws_bytes,
+                 cudaStream_t stream) {
+  const size_t n = items.size();
+  if (n == 0) return Status::SUCCESS;
+  std::lock_guard<std::mutex> lock(I.mu);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<const void *> in(n);
+  std::vector<void *> out(n);
+  std::vector<size_t> in_sz(n), out_sz(n);
+  std::vector<u32> st;
+  bool bad = false;
+  for (size_t i = 0; i < n; ++i) {
+    in[i] = items[i].input_ptr; out[i] = items[i].output_ptr; in_sz[i] = items[i].input_size; out_sz[i] = items[i].output_size;
+    // null pointers are reported per item by the kernel as ERROR_INVALID_PARAMETER
+    if (compress && items[i].input_size == 0) bad = true;
+  }
+  (void)bad;
+  Status s = I.run(compress, in.data(), in_sz.data(), n, out.data(), out_sz.data(), nullptr, false, ws, ws_bytes, stream, true, &st, nullptr);
+  if (st.size() == n) {
+    BatchItem *mut = const_cast<BatchItem *>(items.data());      // the reference writes results the same way (manager.cu:5770-5795)
+    u64 in_total = 0, out_total = 0;
+    for (size_t i = 0; i < n; ++i) {
+      mut[i].status = static_cast<Status>(st[i]);
+      mut[i].output_size = st[i] == 0 ? out_sz[i] : 0;
+      if (st[i] == 0) { in_total += in_sz[i]; out_total += out_sz[i]; }
+    }
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (compress) {
+      I.stats.input_bytes += in_total; I.stats.output_bytes += out_total; I.stats.bytes_compressed += in_total;
+      I.stats.bytes_produced += out_total; I.stats.compression_time_ms += ms;
+    } else {
+      I.stats.bytes_decompressed += out_total; I.stats.decompression_time_ms += ms;
+    }
+    I.stats.blocks_processed += n; I.stats.num_blocks += n;
+  }
+  return s;
+}
+} // namespace
+
+Status ZstdBatchManager::compress_batch(const std::vector<BatchItem> &items, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  return run_items(*pimpl_, true, items, ws, ws_bytes, stream);
+}
+Status ZstdBatchManager::decompress_batch(const std::vector<BatchItem> &items, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  return run_items(*pimpl_, false, items, ws, ws_bytes, stream);
+}
+Status ZstdBatchManager::decompress_batch_preallocated(std::vector<BatchItem> &items, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  return run_items(*pimpl_, false, items, ws, ws_bytes, stream);
+}
+
+Status ZstdBatchManager::compress(const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes, const void *dict,
+                                  size_t dict_size, cudaStream_t stream, void *) {
+  if (!src || !dst || !dst_size || !ws) return fail(Status::ERROR_INVALID_PARAMETER, "compress", "null argument");   // manager.cu:1549-1552
+  if (n == 0) return fail(Status::ERROR_INVALID_PARAMETER, "compress", "zero-size input");                            // manager.cu:1554-1558
+  if (dict || dict_size) return fail(Status::ERROR_NOT_IMPLEMENTED, "compress", "dictionaries are out of scope");
+  std::vector<BatchItem> it(1);
+  it[0].input_ptr = const_cast<void *>(src); it[0].input_size = n; it[0].output_ptr = dst; it[0].output_size = *dst_size;
+  Status s = run_items(*pimpl_, true, it, ws, ws_bytes, stream);
+  if (s == Status::SUCCESS) { *dst_size = it[0].output_size; return s; }
+  return it[0].status != Status::SUCCESS ? it[0].status : s;
+}
+Status ZstdBatchManager::decompress(const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!src || !dst || !dst_size || !ws) return fail(Status::ERROR_INVALID_PARAMETER, "decompress", "null argument");
+  if (n < 4) return fail(Status::ERROR_INVALID_PARAMETER, "decompress", "input shorter than a magic number");         // manager.cu:3202-3206
+  if (*dst_size == 0) return fail(Status::ERROR_BUFFER_TOO_SMALL, "decompress", "zero output capacity");
+  std::vector<BatchItem> it(1);
+  it[0].input_ptr = const_cast<void *>(src); it[0].input_size = n; it[0].output_ptr = dst; it[0].output_size = *dst_size;
+  Status s = run_items(*pimpl_, false, it, ws, ws_bytes, stream);
+  if (s == Status::SUCCESS) { *dst_size = it[0].output_size; return s; }
+  return it[0].status != Status::SUCCESS ? it[0].status : s;
+}
+Status ZstdBatchManager::decompress_to_preallocated(const void *src, size_t n, void *out, size_t cap, size_t *actual, void *ws,
+                                                    size_t ws_bytes, cudaStream_t stream) {
+  if (!src || !out || !actual) return fail(Status::ERROR_INVALID_PARAMETER, "decompress_to_preallocated", "null argument");
+  if (cap == 0) return fail(Status::ERROR_BUFFER_TOO_SMALL, "decompress_to_preallocated", "zero output capacity");
+  size_t sz = cap;
+  Status s = decompress(src, n, out, &sz, ws, ws_bytes, stream);
+  if (s == Status::SUCCESS) *actual = sz;
+  return s;
+}
+Status ZstdBatchManager::decompress_async_no_sync(const void *src, size_t n, void *out, size_t cap, size_t *d_actual, void *ws,
+                                                  size_t ws_bytes, cudaStream_t stream) {
+  if (!src || !out || !d_actual || !ws) return fail(Status::ERROR_INVALID_PARAMETER, "decompress_async_no_sync", "null argument");
+  if (cap == 0) return fail(Status::ERROR_BUFFER_TOO_SMALL, "decompress_async_no_sync", "zero output capacity");
+  Impl &I = *pimpl_;
+  if (ws_bytes < I.dec_temp(1)) return fail(Status::ERROR_BUFFER_TOO_SMALL, "decompress_async_no_sync", "workspace too small");
+  // tables for a batch of one are built in the workspace by stream-ordered copies of by-value words
+  unsigned char *tab = static_cast<unsigned char *>(ws) + b200zstd::WS_HEADER_BYTES;
+  const void *hin = src; size_t hn = n; void *hout = out; size_t hcap = cap;
+  cudaError_t e;
+  // pageable -> device async copies are staged by the runtime before returning, so the stack words are safe
+  if ((e = cudaMemcpyAsync(tab, &hin, 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, "decompress_async_no_sync");
+  if ((e = cudaMemcpyAsync(tab + 8, &hn, 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, "decompress_async_no_sync");
+  if ((e = cudaMemcpyAsync(tab + 16, &hout, 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, "decompress_async_no_sync");
+  if ((e = cudaMemcpyAsync(d_actual, &hcap, 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, "decompress_async_no_sync");
+  b200zstd::DecodeArgs a{};
+  a.in_ptrs = reinterpret_cast<const void *const *>(tab); a.in_sizes = reinterpret_cast<const size_t *>(tab + 8);
+  a.out_ptrs = reinterpret_cast<void *const *>(tab + 16); a.out_sizes = d_actual; a.statuses = reinterpret_cast<u32 *>(tab + 32);
+  a.counter = reinterpret_cast<u32 *>(ws); a.lit_scratch = tab + Impl::table_bytes(1); a.n = 1;
+  a.verify_checksum = I.cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY;
+  e = b200zstd::launch_decode_batch(a, 1, stream);
+  return e == cudaSuccess ? Status::SUCCESS : cuda_fail(e, "decompress_async_no_sync");
+}
+size_t ZstdBatchManager::get_inference_workspace_size(size_t, size_t) const { return pimpl_->dec_temp(1); }
+Status ZstdBatchManager::allocate_inference_workspace(size_t mc, size_t mo, void **p, size_t *sz) {
+  if (!p || !sz) return Status::ERROR_INVALID_PARAMETER;
+  *sz = get_inference_workspace_size(mc, mo);
+  cudaError_t e = cudaMalloc(p, *sz);
+  return e == cudaSuccess ? Status::SUCCESS : fail(Status::ERROR_OUT_OF_MEMORY, "allocate_inference_workspace", cudaGetErrorString(e), e);
+}
+Status ZstdBatchManager::free_inference_workspace(void *p) {
+  if (!p) return Status::ERROR_INVALID_PARAMETER;
+  return cudaFree(p) == cudaSuccess ? Status::SUCCESS : Status::ERROR_CUDA_ERROR;
+}
+
+std::unique_ptr<ZstdManager> create_manager(int level) {
+  auto m = std::make_unique<ZstdBatchManager>();
+  m->set_compression_level(level);
+  return m;
+}
+std::unique_ptr<ZstdManager> create_manager(const CompressionConfig &c) { return std::make_unique<ZstdBatchManager>(c); }
+std::unique_ptr<ZstdBatchManager> create_batch_manager(int level) {
+  auto m = std::make_unique<ZstdBatchManager>();
+  m->set_compression_level(level);
+  return m;
+}
+
+namespace {
+Status simple(bool compress, const void *src, size_t n, void *dst, size_t *dst_size, int level, cudaStream_t stream) {
+  ZstdBatchManager m;
+  if (compress) m.set_compression_level(level);
+  size_t ws_bytes = compress ? m.get_compress_temp_size(n) : m.get_decompress_temp_size(n);
+  void *ws = nullptr;
+  if (cudaMalloc(&ws, ws_bytes) != cudaSuccess) return Status::ERROR_OUT_OF_MEMORY;
+  Status s = compress ? m.compress(src, n, dst, dst_size, ws, ws_bytes, nullptr, 0, stream) : m.decompress(src, n, dst, dst_size, ws, ws_bytes, stream);
+  cudaFree(ws);
+  return s;
+}
+} // namespace
+Status compress_simple(const void *src, size_t n, void *dst, size_t *dst_size, int level, cudaStream_t stream) {
+  return simple(true, src, n, dst, dst_size, level, stream);
+}
+Status decompress_simple(const void *src, size_t n, void *dst, size_t *dst_size, cudaStream_t stream) {
+  return simple(false, src, n, dst, dst_size, 3, stream);
+}
+
+// ============================================================================================
+// nvCOMP-v5 facade
+// ============================================================================================
+namespace nvcomp_v5 {
+
+bool is_compatible_with_nvcomp_v5(u32 v) { return (v >> 16) == 5; }
+NvcompV5Options to_nvcomp_v5_opts(const CompressionConfig &c) {
+  NvcompV5Options o;
+  o.level = c.level; o.chunk_size = c.block_size; o.enable_checksum = c.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
+  return o;
+}
+CompressionConfig from_nvcomp_v5_opts(const NvcompV5Options &o) {
+  CompressionConfig c = CompressionConfig::from_level(o.level);
+  c.block_size = o.chunk_size;
+  c.checksum = o.enable_checksum ? ChecksumPolicy::COMPUTE_AND_VERIFY : ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
+  return c;
+}
+std::unique_ptr<ZstdManager> create_nvcomp_v5_manager(const NvcompV5Options &o) { return create_manager(from_nvcomp_v5_opts(o)); }
+
+int status_to_nvcomp_error(Status s) {
+  switch (static_cast<u32>(s)) {
+  case 0: case 2: case 3: case 4: case 6: case 7: case 10: case 12: return static_cast<int>(s);
+  default: return 1;
+  }
+}
+Status nvcomp_error_to_status(int e) {
+  switch (e) {
+  case 0: case 2: case 3: case 4: case 6: case 7: case 10: case 12: return static_cast<Status>(e);
+  default: return Status::ERROR_GENERIC;
+  }
+}
+const char *get_nvcomp_v5_error_string(int e) { return status_to_string(nvcomp_error_to_status(e)); }
+
+class NvcompV5BatchManager::Impl {
+public:
+  ZstdBatchManager mgr;
+  explicit Impl(const NvcompV5Options &o) : mgr(sanitize(o)) {}
+  static CompressionConfig sanitize(const NvcompV5Options &o) {
+    NvcompV5Options t = o;
+    if (t.level < 1 || t.level > 22) t.level = 3;
+    if (t.chunk_size < 1024) t.chunk_size = 64 * 1024;
+    return from_nvcomp_v5_opts(t);
+  }
+};
+
+namespace {
+bool on_device(const void *p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+// Tables may be host or device memory, in any mix (reference src/cuda_zstd_nvcomp.cpp:319-437).
+// All-device -> used in place; otherwise everything is brought to host vectors and staged once.
+Status run_tables(ZstdBatchManager &m, bool compress, const void *const *in_ptrs, const size_t *in_sizes, size_t n,
+                  void *const *out_ptrs, size_t *out_sizes, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  if (n == 0) return Status::SUCCESS;
+  if (!in_ptrs || !in_sizes || !out_ptrs || !out_sizes) return fail(Status::ERROR_INVALID_PARAMETER, "batch", "null pointer table");
+  ZstdBatchManager::Impl &I = *m.impl();
+  std::lock_guard<std::mutex> lock(I.mu);
+  const bool d0 = on_device(in_ptrs), d1 = on_device(in_sizes), d2 = on_device(out_ptrs), d3 = on_device(out_sizes);
+  std::vector<u32> st;
+  std::vector<size_t> hs;
+  Status s;
+  if (d0 && d1 && d2 && d3) {
+    s = I.run(compress, in_ptrs, in_sizes, n, out_ptrs, out_sizes, nullptr, true, ws, ws_bytes, stream, true, &st, &hs);
+  } else {
+    std::vector<const void *> in(n);
+    std::vector<void *> out(n);
+    std::vector<size_t> isz(n), osz(n);
+    cudaError_t e = cudaSuccess;
+    if (d0 || d1 || d2 || d3) if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "batch");
+    auto fetch = [&](void *dst, const void *src, bool dev) {
+      if (dev) { cudaError_t r = cudaMemcpy(dst, src, n * 8, cudaMemcpyDeviceToHost); if (r != cudaSuccess) e = r; }
+      else std::memcpy(dst, src, n * 8);
+    };
+    fetch(in.data(), in_ptrs, d0); fetch(isz.data(), in_sizes, d1); fetch(out.data(), out_ptrs, d2); fetch(osz.data(), out_sizes, d3);
+    if (e != cudaSuccess) return cuda_fail(e, "batch");
+    s = I.run(compress, in.data(), isz.data(), n, out.data(), osz.data(), nullptr, false, ws, ws_bytes, stream, true, &st, nullptr);
+    if (st.size() == n) {
+      for (size_t i = 0; i < n; ++i) if (st[i] != 0) osz[i] = 0;
+      if (d3) { if ((e = cudaMemcpy(out_sizes, osz.data(), n * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "batch"); }
+      else std::memcpy(out_sizes, osz.data(), n * 8);
+      hs = osz;
+    }
+    if (st.size() == n) {
+      u64 it = 0, ot = 0;
+      for (size_t i = 0; i < n; ++i) if (st[i] == 0) { it += isz[i]; ot += osz[i]; }
+      if (compress) { I.stats.input_bytes += it; I.stats.output_bytes += ot; I.stats.bytes_compressed += it; I.stats.bytes_produced += ot; }
+      else I.stats.bytes_decompressed += ot;
+      I.stats.blocks_processed += n;
+    }
+  }
+  return s;
+}
+} // namespace
+
+NvcompV5BatchManager::NvcompV5BatchManager(const NvcompV5Options &o) : pimpl_(new Impl(o)) {}
+NvcompV5BatchManager::~NvcompV5BatchManager() = default;
+ZstdBatchManager &NvcompV5BatchManager::batch_manager() { return pimpl_->mgr; }
+size_t NvcompV5BatchManager::get_compress_temp_size(const size_t *, size_t n, cudaStream_t) const { return pimpl_->mgr.impl()->enc_temp(n); }
+size_t NvcompV5BatchManager::get_decompress_temp_size(const size_t *, size_t n, cudaStream_t) const { return pimpl_->mgr.impl()->dec_temp(n); }
+size_t NvcompV5BatchManager::get_max_compressed_chunk_size(size_t n) const { return pimpl_->mgr.get_max_compressed_size(n); }
+Status NvcompV5BatchManager::compress_async(const void *const *in, const size_t *in_sz, size_t n, void *const *out, size_t *out_sz,
+                                            void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  return run_tables(pimpl_->mgr, true, in, in_sz, n, out, out_sz, tmp, tmp_bytes, stream);
+}
+Status NvcompV5BatchManager::decompress_async(const void *const *in, const size_t *in_sz, size_t n, void *const *out, size_t *out_sz,
+                                              void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  return run_tables(pimpl_->mgr, false, in, in_sz, n, out, out_sz, tmp, tmp_bytes, stream);
+}
+const CompressionStats &NvcompV5BatchManager::get_stats() const { return pimpl_->mgr.get_stats(); }
+
+Status get_metadata_async(const void *d, size_t n, NvcompV5Metadata *m, cudaStream_t stream) {
+  if (!d || !m) return Status::ERROR_INVALID_PARAMETER;
+  if (n < 5) return Status::ERROR_INVALID_PARAMETER;
+  unsigned char head[18];
+  size_t k = std::min<size_t>(n, sizeof head);
+  if (on_device(d)) {
+    if (cudaMemcpyAsync(head, d, k, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return Status::ERROR_CUDA_ERROR;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return Status::ERROR_CUDA_ERROR;
+  } else std::memcpy(head, d, k);
+  HeaderInfo h = peek_header(head, k);
+  if (!h.ok) return Status::ERROR_INVALID_MAGIC;
+  *m = NvcompV5Metadata();
+  m->uncompressed_size = h.has_size ? h.content_size : 0;
+  m->compressed_size = n;
+  m->num_chunks = 1;
+  m->chunk_size = (u32)std::min<u64>(m->uncompressed_size, 0xFFFFFFFFu);
+  m->dictionary_id = h.dict_id;
+  m->has_dictionary = h.dict_id != 0;
+  m->checksum_policy = h.checksum ? ChecksumPolicy::COMPUTE_AND_VERIFY : ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
+  return Status::SUCCESS;
+}
+Status get_metadata(const void *d, size_t n, NvcompV5Metadata &m) { return get_metadata_async(d, n, &m, 0); }
+bool validate_metadata(const NvcompV5Metadata &m) { return is_compatible_with_nvcomp_v5(m.format_version) && m.num_chunks >= 1; }
+Status get_decompressed_size_async(const void *d, size_t n, size_t *out, cudaStream_t stream) {
+  NvcompV5Metadata m;
+  if (!out) return Status::ERROR_INVALID_PARAMETER;
+  Status s = get_metadata_async(d, n, &m, stream);
+  if (s == Status::SUCCESS) *out = (size_t)m.uncompressed_size;
+  return s;
+}
+Status get_num_chunks(const void *d, size_t n, size_t *out) {
+  if (!d || !out || n < 5) return Status::ERROR_INVALID_PARAMETER;
+  *out = 1;
+  return Status::SUCCESS;
+}
+Status get_chunk_sizes(const void *d, size_t n, size_t *sizes, size_t max_chunks) {
+  if (!sizes || max_chunks < 1) return Status::ERROR_INVALID_PARAMETER;
+  return get_decompressed_size_async(d, n, &sizes[0], 0);
+}
+
+NvcompV5BenchmarkResult benchmark_level(const void *d_input, size_t n, int level, int iterations, cudaStream_t stream) {
+  NvcompV5BenchmarkResult r{};
+  r.level = level;
+  if (!d_input || n == 0 || iterations < 1) return r;
+  ZstdBatchManager m;
+  m.set_compression_level(level);
+  const size_t cap = m.get_max_compressed_size(n), ws_bytes = m.get_compress_temp_size(n);
+  void *ws = nullptr, *comp = nullptr, *back = nullptr;
+  if (cudaMalloc(&ws, ws_bytes) != cudaSuccess || cudaMalloc(&comp, cap) != cudaSuccess || cudaMalloc(&back, n) != cudaSuccess) {
+    cudaFree(ws); cudaFree(comp); cudaFree(back);
+    return r;
+  }
+  size_t csz = cap, dsz = n;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iterations; ++i) { csz = cap; if (m.compress(d_input, n, comp, &csz, ws, ws_bytes, nullptr, 0, stream) != Status::SUCCESS) csz = 0; }
+  auto t1 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iterations && csz; ++i) { dsz = n; m.decompress(comp, csz, back, &dsz, ws, ws_bytes, stream); }
+  auto t2 = std::chrono::steady_clock::now();
+  r.compress_time_ms = std::chrono::duration<double, std::milli>(t1 - t0).count() / iterations;
+  r.decompress_time_ms = std::chrono::duration<double, std::milli>(t2 - t1).count() / iterations;
+  r.compress_throughput_mbps = r.compress_time_ms > 0 ? (n / 1e6) / (r.compress_time_ms / 1e3) : 0;
+  r.decompress_throughput_mbps = r.decompress_time_ms > 0 ? (n / 1e6) / (r.decompress_time_ms / 1e3) : 0;
+  r.compressed_size = csz;
+  r.compression_ratio = csz ? (float)n / (float)csz : 0.f;
+  cudaFree(ws); cudaFree(comp); cudaFree(back);
+  return r;
+}
+std::vector<NvcompV5BenchmarkResult> benchmark_all_levels(const void *d_input, size_t n, int iterations, cudaStream_t stream) {
+  std::vector<NvcompV5BenchmarkResult> v;
+  for (int l = 1; l <= 22; ++l) v.push_back(benchmark_level(d_input, n, l, iterations, stream));
+  return v;
+}
+
+} // namespace nvcomp_v5
+} // namespace cuda_zstd
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+using cuda_zstd::Status;
+using cuda_zstd::ZstdBatchManager;
+using cuda_zstd::nvcomp_v5::status_to_nvcomp_error;
+
+struct cuda_zstd_batch { cuda_zstd::nvcomp_v5::NvcompV5BatchManager *m; };
+
+extern "C" {
+
+// ---- nvcomp_zstd_*_v5 (reference src/cuda_zstd_nvcomp.cpp:766-840) ----
+nvcompZstdManagerHandle nvcomp_zstd_create_manager_v5(int level) {
+  try {
+    auto m = cuda_zstd::create_batch_manager((level < 1 || level > 22) ? 3 : level);
+    return static_cast<cuda_zstd::ZstdManager *>(m.release());
+  } catch (...) { return nullptr; }
+}
+void nvcomp_zstd_destroy_manager_v5(nvcompZstdManagerHandle h) { delete static_cast<cuda_zstd::ZstdManager *>(h); }
+int nvcomp_zstd_compress_async_v5(nvcompZstdManagerHandle h, const void *src, size_t n, void *dst, size_t *dst_size, void *tmp,
+                                  size_t tmp_bytes, cudaStream_t stream) {
+  if (!h) return status_to_nvcomp_error(Status::ERROR_INVALID_PARAMETER);
+  try { return status_to_nvcomp_error(static_cast<cuda_zstd::ZstdManager *>(h)->compress(src, n, dst, dst_size, tmp, tmp_bytes, nullptr, 0, stream)); }
+  catch (...) { return 1; }
+}
+int nvcomp_zstd_decompress_async_v5(nvcompZstdManagerHandle h, const void *src, size_t n, void *dst, size_t *dst_size, void *tmp,
+                                    size_t tmp_bytes, cudaStream_t stream) {
+  if (!h) return status_to_nvcomp_error(Status::ERROR_INVALID_PARAMETER);
+  try { return status_to_nvcomp_error(static_cast<cuda_zstd::ZstdManager *>(h)->decompress(src, n, dst, dst_size, tmp, tmp_bytes, stream)); }
+  catch (...) { return 1; }
+}
+size_t nvcomp_zstd_get_compress_temp_size_v5(nvcompZstdManagerHandle h, size_t n) {
+  return h ? static_cast<cuda_zstd::ZstdManager *>(h)->get_compress_temp_size(n) : 0;
+}
+size_t nvcomp_zstd_get_decompress_temp_size_v5(nvcompZstdManagerHandle h, size_t n) {
+  return h ? static_cast<cuda_zstd::ZstdManager *>(h)->get_decompress_temp_size(n) : 0;
+}
+int nvcomp_zstd_get_metadata_v5(const void *d, size_t n, cuda_zstd::nvcomp_v5::NvcompV5Metadata *m, cudaStream_t stream) {
+  return status_to_nvcomp_error(cuda_zstd::nvcomp_v5::get_metadata_async(d, n, m, stream));
+}
+
+// ---- cuda_zstd_* single-buffer C API (reference src/cuda_zstd_c_api.cpp:18-211) ----
+cuda_zstd_manager_t *cuda_zstd_create_manager(int level) {
+  return reinterpret_cast<cuda_zstd_manager_t *>(nvcomp_zstd_create_manager_v5(level));
+}
+void cuda_zstd_destroy_manager(cuda_zstd_manager_t *m) { nvcomp_zstd_destroy_manager_v5(m); }
+int cuda_zstd_compress(cuda_zstd_manager_t *m, const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes,
+                       cudaStream_t stream) {
+  if (!m) return static_cast<int>(Status::ERROR_INVALID_PARAMETER);
+  try { return static_cast<int>(reinterpret_cast<cuda_zstd::ZstdManager *>(m)->compress(src, n, dst, dst_size, ws, ws_bytes, nullptr, 0, stream)); }
+  catch (...) { return 1; }
+}
+int cuda_zstd_decompress(cuda_zstd_manager_t *m, const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes,
+                         cudaStream_t stream) {
+  if (!m) return static_cast<int>(Status::ERROR_INVALID_PARAMETER);
+  try { return static_cast<int>(reinterpret_cast<cuda_zstd::ZstdManager *>(m)->decompress(src, n, dst, dst_size, ws, ws_bytes, stream)); }
+  catch (...) { return 1; }
+}
+size_t cuda_zstd_get_compress_workspace_size(cuda_zstd_manager_t *m, size_t n) { return nvcomp_zstd_get_compress_temp_size_v5(m, n); }
+size_t cuda_zstd_get_decompress_workspace_size(cuda_zstd_manager_t *m, size_t n) { return nvcomp_zstd_get_decompress_temp_size_v5(m, n); }
+cuda_zstd_dict_t *cuda_zstd_train_dictionary(const void **, const size_t *, size_t, size_t) { return nullptr; }
+void cuda_zstd_destroy_dictionary(cuda_zstd_dict_t *) {}
+int cuda_zstd_set_dictionary(cuda_zstd_manager_t *, cuda_zstd_dict_t *) { return static_cast<int>(Status::ERROR_NOT_IMPLEMENTED); }
+const char *cuda_zstd_get_error_string(int code) { return cuda_zstd::status_to_string(static_cast<Status>(code)); }
+int cuda_zstd_is_error(int code) { return code != 0; }
+
+// ---- cuda_zstd_batch_* (additive batch ABI, include/cuda_zstd_batch_c.h) ----
+cuda_zstd_batch_t *cuda_zstd_batch_create(int level, int enable_checksum) {
+  try {
+    cuda_zstd::nvcomp_v5::NvcompV5Options o;
+    o.level = level; o.enable_checksum = enable_checksum != 0; o.chunk_size = 128 * 1024;
+    auto *b = new cuda_zstd_batch;
+    b->m = new cuda_zstd::nvcomp_v5::NvcompV5BatchManager(o);
+    return b;
+  } catch (...) { return nullptr; }
+}
+void cuda_zstd_batch_destroy(cuda_zstd_batch_t *b) { if (b) { delete b->m; delete b; } }
+size_t cuda_zstd_batch_get_max_compressed_size(cuda_zstd_batch_t *b, size_t n) { return b ? b->m->get_max_compressed_chunk_size(n) : 0; }
+size_t cuda_zstd_batch_get_compress_temp_size(cuda_zstd_batch_t *b, const size_t *sizes, size_t n) { return b ? b->m->get_compress_temp_size(sizes, n) : 0; }
+size_t cuda_zstd_batch_get_decompress_temp_size(cuda_zstd_batch_t *b, const size_t *sizes, size_t n) { return b ? b->m->get_decompress_temp_size(sizes, n) : 0; }
+int cuda_zstd_batch_compress(cuda_zstd_batch_t *b, const void *const *in, const size_t *in_sz, size_t n, void *const *out, size_t *out_sz,
+                             void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  if (!b) return 2;
+  try { return status_to_nvcomp_error(b->m->compress_async(in, in_sz, n, out, out_sz, tmp, tmp_bytes, stream)); } catch (...) { return 1; }
+}
+int cuda_zstd_batch_decompress(cuda_zstd_batch_t *b, const void *const *in, const size_t *in_sz, size_t n, void *const *out, size_t *out_sz,
+                               void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  if (!b) return 2;
+  try { return status_to_nvcomp_error(b->m->decompress_async(in, in_sz, n, out, out_sz, tmp, tmp_bytes, stream)); } catch (...) { return 1; }
+}
+int cuda_zstd_batch_compress_nosync(cuda_zstd_batch_t *b, const void *const *in, const size_t *in_sz, size_t n, void *const *out,
+                                    size_t *out_sz, uint32_t *st, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  if (!b) return 2;
+  try {
+    return status_to_nvcomp_error(b->m->batch_manager().impl()->run(true, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
+  } catch (...) { return 1; }
+}
+int cuda_zstd_batch_decompress_nosync(cuda_zstd_batch_t *b, const void *const *in, const size_t *in_sz, size_t n, void *const *out,
+                                      size_t *out_sz, uint32_t *st, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  if (!b) return 2;
+  try {
+    return status_to_nvcomp_error(b->m->batch_manager().impl()->run(false, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
+  } catch (...) { return 1; }
+}
+int cuda_zstd_batch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream) {
+  if (!d_sizes || !d_offsets) return 2;
+  return b200zstd::launch_scan_sizes(d_sizes, n, base, d_offsets, stream) == cudaSuccess ? 0 : 4;
+}
+int cuda_zstd_batch_pack(const void *const *d_ptrs, const size_t *d_sizes, const uint64_t *d_offsets, size_t n, void *d_packed,
+                         cudaStream_t stream) {
+  if (!d_ptrs || !d_sizes || !d_offsets || !d_packed) return 2;
+  return b200zstd::launch_pack(d_ptrs, d_sizes, d_offsets, n, d_packed, stream) == cudaSuccess ? 0 : 4;
+}
+int cuda_zstd_batch_last_launch_count(cuda_zstd_batch_t *b) { return b ? b->m->batch_manager().impl()->last_launches : 0; }
+const char *cuda_zstd_batch_error_string(int code) { return cuda_zstd::status_to_string(static_cast<Status>(code)); }
+
+} // extern "C"

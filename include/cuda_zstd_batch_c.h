@@ -1,0 +1,103 @@
+/* cuda_zstd_batch_c.h -- the C-ABI drop-in boundary of the B200-native batched Zstandard codec.
+ *
+ * Plain C: pointers, sizes and ints only; no C++ or torch types.  Every entry point names the
+ * reference interface it stands in for (file:line under /root/reference).  The reference's own C
+ * ABI is single-buffer only (include/cuda_zstd_manager.h:433-479, include/cuda_zstd_nvcomp.h:
+ * 272-336); the cuda_zstd_batch_* calls are the additive batch form BASELINE.json's north_star asks
+ * for, taking exactly the argument lists of NvcompV5BatchManager (include/cuda_zstd_nvcomp.h:
+ * 93-134) so that a binding written against either maps 1:1.
+ *
+ * Conventions (same as the reference):
+ *  - return value: 0 = success, else a cuda_zstd::Status value passed through the reference's lossy
+ *    map {0,2,3,4,6,7,10,12 -> same; everything else -> 1} (src/cuda_zstd_nvcomp.cpp:75-96);
+ *  - `*_sizes` arrays are in = capacity, out = bytes written;
+ *  - data buffers and the workspace are DEVICE memory owned by the caller; pointer/size arrays may
+ *    live in host OR device memory (src/cuda_zstd_nvcomp.cpp:319-437 accepts both);
+ *  - calls enqueue on `stream` and, unless the name says `_nosync`, return after the results are
+ *    visible to the host (the reference synchronises too: src/cuda_zstd_nvcomp.cpp:458,610);
+ *  - no allocation happens inside a call; no CPU codec is ever used; a missing GPU is an error.
+ */
+#ifndef CUDA_ZSTD_BATCH_C_H
+#define CUDA_ZSTD_BATCH_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+typedef struct cuda_zstd_batch cuda_zstd_batch_t;
+
+/* NvcompV5BatchManager(const NvcompV5Options&) (include/cuda_zstd_nvcomp.h:95, options :41-51) /
+ * create_batch_manager(level) (include/cuda_zstd_manager.h:361).  level 1..22; checksum != 0 writes
+ * and verifies the XXH64 content checksum (ChecksumPolicy::COMPUTE_AND_VERIFY).  NULL on failure. */
+cuda_zstd_batch_t *cuda_zstd_batch_create(int level, int enable_checksum);
+void cuda_zstd_batch_destroy(cuda_zstd_batch_t *mgr);
+
+/* NvcompV5BatchManager::get_max_compressed_chunk_size (src/cuda_zstd_nvcomp.cpp:289-298) ->
+ * ZstdBatchManager::get_max_compressed_size -> estimate_compressed_size
+ * (src/cuda_zstd_types.cpp:831-853): n + n/255 + 3*ceil(n/128K) + 512.  0 on a null handle. */
+size_t cuda_zstd_batch_get_max_compressed_size(cuda_zstd_batch_t *mgr, size_t uncompressed_chunk_size);
+
+/* NvcompV5BatchManager::get_compress_temp_size / get_decompress_temp_size
+ * (src/cuda_zstd_nvcomp.cpp:207-287) -> ZstdBatchManager::get_batch_*_temp_size
+ * (src/cuda_zstd_manager.cu:5661-5712).  `sizes` is a HOST array.  0 on a null handle.
+ * decompress_temp <= compress_temp for the same batch, so one workspace serves both
+ * (tests/test_c_api.cpp:62-64 in the reference relies on that). */
+size_t cuda_zstd_batch_get_compress_temp_size(cuda_zstd_batch_t *mgr, const size_t *chunk_sizes, size_t num_chunks);
+size_t cuda_zstd_batch_get_decompress_temp_size(cuda_zstd_batch_t *mgr, const size_t *compressed_sizes, size_t num_chunks);
+
+/* NvcompV5BatchManager::compress_async (include/cuda_zstd_nvcomp.h:112-121,
+ * src/cuda_zstd_nvcomp.cpp:300-484) -> ZstdBatchManager::compress_batch
+ * (src/cuda_zstd_manager.cu:5715-5797).  Every output is one complete Zstandard frame that stock
+ * libzstd decodes.  Empty batch -> 0; null array -> 2; workspace too small -> 7. */
+int cuda_zstd_batch_compress(cuda_zstd_batch_t *mgr, const void *const *uncompressed_ptrs, const size_t *uncompressed_sizes,
+                             size_t num_chunks, void *const *compressed_ptrs, size_t *compressed_sizes, void *d_temp,
+                             size_t temp_bytes, cudaStream_t stream);
+
+/* NvcompV5BatchManager::decompress_async (include/cuda_zstd_nvcomp.h:124-133,
+ * src/cuda_zstd_nvcomp.cpp:486-644) -> ZstdBatchManager::decompress_batch
+ * (src/cuda_zstd_manager.cu:5799-5859). */
+int cuda_zstd_batch_decompress(cuda_zstd_batch_t *mgr, const void *const *compressed_ptrs, const size_t *compressed_sizes,
+                               size_t num_chunks, void *const *uncompressed_ptrs, size_t *uncompressed_sizes, void *d_temp,
+                               size_t temp_bytes, cudaStream_t stream);
+
+/* Fully device-resident, no host synchronisation: all five arrays are DEVICE memory, d_statuses
+ * (uint32 per chunk, cuda_zstd::Status values, may be NULL) is written by the kernel.  This is the
+ * "true no-sync" form of ZstdBatchManager::decompress_async_no_sync
+ * (include/cuda_zstd_manager.h:254-259; the reference's version still synchronises,
+ * src/cuda_zstd_manager.cu:5979) extended to batches, and what bench.py times for `value`. */
+int cuda_zstd_batch_compress_nosync(cuda_zstd_batch_t *mgr, const void *const *d_uncompressed_ptrs,
+                                    const size_t *d_uncompressed_sizes, size_t num_chunks, void *const *d_compressed_ptrs,
+                                    size_t *d_compressed_sizes, uint32_t *d_statuses, void *d_temp, size_t temp_bytes,
+                                    cudaStream_t stream);
+int cuda_zstd_batch_decompress_nosync(cuda_zstd_batch_t *mgr, const void *const *d_compressed_ptrs,
+                                      const size_t *d_compressed_sizes, size_t num_chunks, void *const *d_uncompressed_ptrs,
+                                      size_t *d_uncompressed_sizes, uint32_t *d_statuses, void *d_temp, size_t temp_bytes,
+                                      cudaStream_t stream);
+
+/* Device-side exclusive scan of per-chunk compressed sizes -> packed offsets, plus the grand total
+ * in d_offsets[num_chunks]; `base` is this GPU's starting offset in a multi-GPU job (SURVEY.md
+ * section 8e).  Replaces the reference's thrust::exclusive_scan wrapper
+ * (src/cuda_zstd_utils.cu:50-90).  d_offsets has num_chunks + 1 entries. */
+int cuda_zstd_batch_scan_sizes(const size_t *d_sizes, size_t num_chunks, uint64_t base, uint64_t *d_offsets, cudaStream_t stream);
+
+/* Gather frames written at `compressed_ptrs[i]` into one packed buffer at d_offsets[i]. */
+int cuda_zstd_batch_pack(const void *const *d_compressed_ptrs, const size_t *d_sizes, const uint64_t *d_offsets,
+                         size_t num_chunks, void *d_packed, cudaStream_t stream);
+
+/* launch statistics of the most recent call on this manager: number of kernel launches it made */
+int cuda_zstd_batch_last_launch_count(cuda_zstd_batch_t *mgr);
+
+/* cuda_zstd_get_error_string (include/cuda_zstd_manager.h:476). */
+const char *cuda_zstd_batch_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDA_ZSTD_BATCH_C_H */
