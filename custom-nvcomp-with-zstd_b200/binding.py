@@ -1,0 +1,279 @@
+"""ctypes binding of include/cuda_zstd_batch_c.h plus torch-tensor conveniences.
+
+Mirrors the reference's pointer-array batch interface (NvcompV5BatchManager,
+include/cuda_zstd_nvcomp.h:93-134 in the reference): same argument meaning (sizes are in = capacity,
+out = bytes written), same error codes (cuda_zstd::Status through status_to_nvcomp_error).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcuda_zstd_b200.so")
+_LIB: Optional[C.CDLL] = None
+
+
+class Status(enum.IntEnum):
+    SUCCESS = 0
+    ERROR_GENERIC = 1
+    ERROR_INVALID_PARAMETER = 2
+    ERROR_OUT_OF_MEMORY = 3
+    ERROR_CUDA_ERROR = 4
+    ERROR_INVALID_MAGIC = 5
+    ERROR_CORRUPT_DATA = 6
+    ERROR_BUFFER_TOO_SMALL = 7
+    ERROR_DICTIONARY_MISMATCH = 9
+    ERROR_CHECKSUM_FAILED = 10
+    ERROR_COMPRESSION = 12
+    ERROR_NOT_IMPLEMENTED = 24
+    ERROR_UNSUPPORTED_FORMAT = 28
+
+
+def status_to_nvcomp_error(status: int) -> int:
+    """The reference's lossy Status -> int map (src/cuda_zstd_nvcomp.cpp:75-96)."""
+    return status if status in (0, 2, 3, 4, 6, 7, 10, 12) else 1
+
+
+# every symbol include/*.h declares extern "C"
+EXPORTS = [
+    "cuda_zstd_batch_create", "cuda_zstd_batch_destroy", "cuda_zstd_batch_get_max_compressed_size",
+    "cuda_zstd_batch_get_compress_temp_size", "cuda_zstd_batch_get_decompress_temp_size", "cuda_zstd_batch_compress",
+    "cuda_zstd_batch_decompress", "cuda_zstd_batch_compress_nosync", "cuda_zstd_batch_decompress_nosync",
+    "cuda_zstd_batch_scan_sizes", "cuda_zstd_batch_pack", "cuda_zstd_batch_last_launch_count", "cuda_zstd_batch_error_string",
+    "cuda_zstd_create_manager", "cuda_zstd_destroy_manager", "cuda_zstd_compress", "cuda_zstd_decompress",
+    "cuda_zstd_get_compress_workspace_size", "cuda_zstd_get_decompress_workspace_size", "cuda_zstd_train_dictionary",
+    "cuda_zstd_destroy_dictionary", "cuda_zstd_set_dictionary", "cuda_zstd_get_error_string", "cuda_zstd_is_error",
+    "nvcomp_zstd_create_manager_v5", "nvcomp_zstd_destroy_manager_v5", "nvcomp_zstd_compress_async_v5",
+    "nvcomp_zstd_decompress_async_v5", "nvcomp_zstd_get_compress_temp_size_v5", "nvcomp_zstd_get_decompress_temp_size_v5",
+    "nvcomp_zstd_get_metadata_v5",
+]
+
+
+def load_library() -> C.CDLL:
+    """Loads the in-tree CUDA library.  Raises if it is missing: there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+    lib.cuda_zstd_batch_create.restype = vp
+    lib.cuda_zstd_batch_create.argtypes = [i32, i32]
+    lib.cuda_zstd_batch_destroy.argtypes = [vp]
+    lib.cuda_zstd_batch_get_max_compressed_size.restype = sz
+    lib.cuda_zstd_batch_get_max_compressed_size.argtypes = [vp, sz]
+    for f in (lib.cuda_zstd_batch_get_compress_temp_size, lib.cuda_zstd_batch_get_decompress_temp_size):
+        f.restype = sz
+        f.argtypes = [vp, vp, sz]
+    for f in (lib.cuda_zstd_batch_compress, lib.cuda_zstd_batch_decompress):
+        f.restype = i32
+        f.argtypes = [vp, vp, vp, sz, vp, vp, vp, sz, vp]
+    for f in (lib.cuda_zstd_batch_compress_nosync, lib.cuda_zstd_batch_decompress_nosync):
+        f.restype = i32
+        f.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.cuda_zstd_batch_scan_sizes.restype = i32
+    lib.cuda_zstd_batch_scan_sizes.argtypes = [vp, sz, u64, vp, vp]
+    lib.cuda_zstd_batch_pack.restype = i32
+    lib.cuda_zstd_batch_pack.argtypes = [vp, vp, vp, sz, vp, vp]
+    lib.cuda_zstd_batch_last_launch_count.restype = i32
+    lib.cuda_zstd_batch_last_launch_count.argtypes = [vp]
+    lib.cuda_zstd_batch_error_string.restype = C.c_char_p
+    lib.cuda_zstd_batch_error_string.argtypes = [i32]
+    # single-buffer C APIs
+    for name in ("cuda_zstd_create_manager", "nvcomp_zstd_create_manager_v5"):
+        getattr(lib, name).restype = vp
+        getattr(lib, name).argtypes = [i32]
+    for name in ("cuda_zstd_destroy_manager", "nvcomp_zstd_destroy_manager_v5"):
+        getattr(lib, name).argtypes = [vp]
+    for name in ("cuda_zstd_compress", "cuda_zstd_decompress", "nvcomp_zstd_compress_async_v5", "nvcomp_zstd_decompress_async_v5"):
+        getattr(lib, name).restype = i32
+        getattr(lib, name).argtypes = [vp, vp, sz, vp, C.POINTER(sz), vp, sz, vp]
+    for name in ("cuda_zstd_get_compress_workspace_size", "cuda_zstd_get_decompress_workspace_size",
+                 "nvcomp_zstd_get_compress_temp_size_v5", "nvcomp_zstd_get_decompress_temp_size_v5"):
+        getattr(lib, name).restype = sz
+        getattr(lib, name).argtypes = [vp, sz]
+    lib.cuda_zstd_get_error_string.restype = C.c_char_p
+    lib.cuda_zstd_get_error_string.argtypes = [i32]
+    lib.cuda_zstd_is_error.restype = i32
+    lib.cuda_zstd_is_error.argtypes = [i32]
+    lib.cuda_zstd_set_dictionary.restype = i32
+    lib.cuda_zstd_set_dictionary.argtypes = [vp, vp]
+    lib.cuda_zstd_train_dictionary.restype = vp
+    lib.cuda_zstd_train_dictionary.argtypes = [vp, vp, sz, sz]
+    _LIB = lib
+    return lib
+
+
+def _addr(x) -> Optional[int]:
+    """Address of a numpy array (host) or torch tensor (device or host); None passes NULL."""
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return int(x)
+
+
+def _stream_handle(stream) -> int:
+    if stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, torch.cuda.Stream):
+        return stream.cuda_stream
+    return int(stream)
+
+
+class ZstdBatchCodec:
+    """Host-side mirror of NvcompV5BatchManager over the C ABI (one per thread, like the reference)."""
+
+    def __init__(self, level: int = 3, checksum: bool = False):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("ZstdBatchCodec needs a CUDA device: the batch path has no CPU route")
+        self.level, self.checksum = level, checksum
+        self.h = self.lib.cuda_zstd_batch_create(level, int(checksum))
+        if not self.h:
+            raise RuntimeError("cuda_zstd_batch_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cuda_zstd_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- size queries -------------------------------------------------------------------------
+    def max_compressed_size(self, n: int) -> int:
+        return int(self.lib.cuda_zstd_batch_get_max_compressed_size(self.h, n))
+
+    def compress_temp_size(self, num_chunks: int) -> int:
+        sizes = np.zeros(max(num_chunks, 1), dtype=np.uint64)
+        return int(self.lib.cuda_zstd_batch_get_compress_temp_size(self.h, sizes.ctypes.data, num_chunks))
+
+    def decompress_temp_size(self, num_chunks: int) -> int:
+        sizes = np.zeros(max(num_chunks, 1), dtype=np.uint64)
+        return int(self.lib.cuda_zstd_batch_get_decompress_temp_size(self.h, sizes.ctypes.data, num_chunks))
+
+    # ---- raw pointer-table calls (tables: numpy uint64 on the host, or torch int64 on the device) ----
+    def compress_tables(self, in_ptrs, in_sizes, n, out_ptrs, out_sizes, workspace: Optional[torch.Tensor], stream=None) -> int:
+        return int(self.lib.cuda_zstd_batch_compress(self.h, _addr(in_ptrs), _addr(in_sizes), n, _addr(out_ptrs), _addr(out_sizes),
+                                                     _addr(workspace), workspace.numel() if workspace is not None else 0,
+                                                     _stream_handle(stream)))
+
+    def decompress_tables(self, in_ptrs, in_sizes, n, out_ptrs, out_sizes, workspace: Optional[torch.Tensor], stream=None) -> int:
+        return int(self.lib.cuda_zstd_batch_decompress(self.h, _addr(in_ptrs), _addr(in_sizes), n, _addr(out_ptrs), _addr(out_sizes),
+                                                       _addr(workspace), workspace.numel() if workspace is not None else 0,
+                                                       _stream_handle(stream)))
+
+    def compress_nosync(self, d_in_ptrs, d_in_sizes, n, d_out_ptrs, d_out_sizes, d_status, workspace, stream=None) -> int:
+        return int(self.lib.cuda_zstd_batch_compress_nosync(self.h, _addr(d_in_ptrs), _addr(d_in_sizes), n, _addr(d_out_ptrs),
+                                                            _addr(d_out_sizes), _addr(d_status), _addr(workspace), workspace.numel(),
+                                                            _stream_handle(stream)))
+
+    def decompress_nosync(self, d_in_ptrs, d_in_sizes, n, d_out_ptrs, d_out_sizes, d_status, workspace, stream=None) -> int:
+        return int(self.lib.cuda_zstd_batch_decompress_nosync(self.h, _addr(d_in_ptrs), _addr(d_in_sizes), n, _addr(d_out_ptrs),
+                                                              _addr(d_out_sizes), _addr(d_status), _addr(workspace), workspace.numel(),
+                                                              _stream_handle(stream)))
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.cuda_zstd_batch_last_launch_count(self.h))
+
+    # ---- tensor conveniences ----------------------------------------------------------------------
+    def compress_chunks(self, data: torch.Tensor, chunk: int, workspace: Optional[torch.Tensor] = None
+                        ) -> Tuple[torch.Tensor, np.ndarray, int]:
+        """Compress a contiguous uint8 device tensor in `chunk`-byte pieces.  Returns (out, sizes, stride):
+        frame i is out[i*stride : i*stride + sizes[i]].  Raises on any failure."""
+        assert data.is_cuda and data.dtype == torch.uint8 and data.is_contiguous()
+        total = data.numel()
+        n = (total + chunk - 1) // chunk
+        stride = (self.max_compressed_size(chunk) + 15) // 16 * 16
+        out = torch.empty(n * stride, dtype=torch.uint8, device=data.device)
+        idx = np.arange(n, dtype=np.uint64)
+        in_ptrs = data.data_ptr() + idx * np.uint64(chunk)
+        in_sizes = np.minimum(np.uint64(chunk), np.uint64(total) - idx * np.uint64(chunk)).astype(np.uint64)
+        out_ptrs = out.data_ptr() + idx * np.uint64(stride)
+        out_sizes = np.full(n, stride, dtype=np.uint64)
+        if workspace is None:
+            workspace = torch.empty(self.compress_temp_size(n), dtype=torch.uint8, device=data.device)
+        rc = self.compress_tables(in_ptrs, in_sizes, n, out_ptrs, out_sizes, workspace)
+        if rc != 0:
+            raise RuntimeError(f"batch compress failed: {self.lib.cuda_zstd_batch_error_string(rc).decode()}")
+        return out, out_sizes, stride
+
+    def decompress_chunks(self, comp: torch.Tensor, offsets: np.ndarray, sizes: np.ndarray, chunk: int,
+                          workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, np.ndarray]:
+        """Decompress frames comp[offsets[i] : offsets[i]+sizes[i]] into a contiguous tensor with stride `chunk`."""
+        assert comp.is_cuda and comp.dtype == torch.uint8
+        n = len(sizes)
+        out = torch.empty(n * chunk, dtype=torch.uint8, device=comp.device)
+        idx = np.arange(n, dtype=np.uint64)
+        in_ptrs = (comp.data_ptr() + np.asarray(offsets, dtype=np.uint64)).astype(np.uint64)
+        in_sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        out_ptrs = out.data_ptr() + idx * np.uint64(chunk)
+        out_sizes = np.full(n, chunk, dtype=np.uint64)
+        if workspace is None:
+            workspace = torch.empty(self.decompress_temp_size(n), dtype=torch.uint8, device=comp.device)
+        rc = self.decompress_tables(in_ptrs, in_sizes, n, out_ptrs, out_sizes, workspace)
+        if rc != 0:
+            raise RuntimeError(f"batch decompress failed: {self.lib.cuda_zstd_batch_error_string(rc).decode()}")
+        return out, out_sizes
+
+    def scan_sizes(self, d_sizes: torch.Tensor, base: int = 0, stream=None) -> torch.Tensor:
+        """Device-side exclusive scan: returns int64 offsets[n+1] (offsets[n] = base + total)."""
+        n = d_sizes.numel()
+        off = torch.empty(n + 1, dtype=torch.int64, device=d_sizes.device)
+        rc = self.lib.cuda_zstd_batch_scan_sizes(d_sizes.data_ptr(), n, base, off.data_ptr(), _stream_handle(stream))
+        if rc != 0:
+            raise RuntimeError("scan_sizes failed")
+        return off
+
+    def pack(self, d_ptrs: torch.Tensor, d_sizes: torch.Tensor, d_offsets: torch.Tensor, packed: torch.Tensor, stream=None):
+        rc = self.lib.cuda_zstd_batch_pack(d_ptrs.data_ptr(), d_sizes.data_ptr(), d_offsets.data_ptr(), d_sizes.numel(),
+                                           packed.data_ptr(), _stream_handle(stream))
+        if rc != 0:
+            raise RuntimeError("pack failed")
+
+
+class ZstdSingle:
+    """The reference's single-buffer C API (cuda_zstd_* / nvcomp_zstd_*_v5) over device tensors."""
+
+    def __init__(self, level: int = 3, flavor: str = "cuda_zstd"):
+        self.lib = load_library()
+        self.flavor = flavor
+        create = self.lib.cuda_zstd_create_manager if flavor == "cuda_zstd" else self.lib.nvcomp_zstd_create_manager_v5
+        self.h = create(level)
+        if not self.h:
+            raise RuntimeError("create_manager failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            (self.lib.cuda_zstd_destroy_manager if self.flavor == "cuda_zstd" else self.lib.nvcomp_zstd_destroy_manager_v5)(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def compress_workspace(self, n: int) -> int:
+        f = self.lib.cuda_zstd_get_compress_workspace_size if self.flavor == "cuda_zstd" else self.lib.nvcomp_zstd_get_compress_temp_size_v5
+        return int(f(self.h, n))
+
+    def decompress_workspace(self, n: int) -> int:
+        f = self.lib.cuda_zstd_get_decompress_workspace_size if self.flavor == "cuda_zstd" else self.lib.nvcomp_zstd_get_decompress_temp_size_v5
+        return int(f(self.h, n))
+
+    def compress(self, src, n, dst, cap, ws, ws_bytes, stream=None) -> Tuple[int, int]:
+        f = self.lib.cuda_zstd_compress if self.flavor == "cuda_zstd" else self.lib.nvcomp_zstd_compress_async_v5
+        size = C.c_size_t(cap)
+        rc = f(self.h, _addr(src), n, _addr(dst), C.byref(size), _addr(ws), ws_bytes, _stream_handle(stream))
+        return int(rc), int(size.value)
+
+    def decompress(self, src, n, dst, cap, ws, ws_bytes, stream=None) -> Tuple[int, int]:
+        f = self.lib.cuda_zstd_decompress if self.flavor == "cuda_zstd" else self.lib.nvcomp_zstd_decompress_async_v5
+        size = C.c_size_t(cap)
+        rc = f(self.h, _addr(src), n, _addr(dst), C.byref(size), _addr(ws), ws_bytes, _stream_handle(stream))
+        return int(rc), int(size.value)

@@ -1,0 +1,350 @@
+// zstd_encode.cu -- batched Zstandard compressor for sm_100a: one persistent warp-CTA per in-flight chunk.
+//
+// Replaces, for the batch path, ZstdBatchManager::compress_batch -> DefaultZstdManager::compress
+// (src/cuda_zstd_manager.cu:5715-5797, 1536-3112 in the reference): find_matches_kernel +
+// greedy_parse_kernel + build_sequences_gpu_kernel (src/lz77_parallel.cu:26-268), compress_literals
+// (manager.cu:4406-4484, raw only), compress_sequences (:4864-4974, predefined FSE only),
+// write_frame_header / write_block (:3998-4106, 4227-4286), compute_xxhash64
+// (src/cuda_zstd_xxhash.cu:238-249).  Differences by design (north_star): the hash tables live in
+// shared memory, the parse is deterministic, repeat offsets are used, literals are Huffman coded
+// and sequence tables are FSE-compressed when that is cheaper, and one launch handles the batch.
+//
+// Parse ("window" parse).  The warp looks at 32 consecutive positions at a time: every lane hashes
+// the bytes at its own position, fetches its candidate(s) (long table, short table or hash chain,
+// repeat offset) and measures them; a ballot picks the first lane that holds a match, optionally
+// displaced by one of the next lanes (lazy evaluation); the chosen match is extended cooperatively
+// (32 x 8 bytes per step), emitted, and the tables are updated for all positions it covers with
+// sequential semantics (match_any resolves equal hashes inside a stripe: the highest position
+// wins, chain links point to the previous equal-hash lane).  tests/model/enc_model.cpp restates the
+// same procedure lane by lane on the host; the two must agree byte for byte.
+#include "zstd_common.cuh"
+#include "zstd_device_api.h"
+#include "zstd_encode_core.cuh"
+
+namespace b200zstd {
+
+using namespace enc;
+
+constexpr int ENC_THREADS = 32;
+
+struct EncScratch {          // layout of one CTA's slice of the global workspace
+  static constexpr size_t lits_off = 0;
+  static constexpr size_t ll_off = BLOCK_BYTES + 64;
+  static constexpr size_t ml_off = ll_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
+  static constexpr size_t of_off = ml_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
+  static constexpr size_t chain_off = of_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
+  static constexpr size_t bytes_nochain = chain_off;
+  static constexpr size_t bytes_chain = chain_off + (size_t)BLOCK_BYTES * 2;
+};
+
+size_t encode_cta_scratch_bytes(const EncodeParams &p) {
+  size_t b = p.chain_depth > 0 ? EncScratch::bytes_chain : EncScratch::bytes_nochain;
+  return (b + 255) & ~(size_t)255;
+}
+static size_t encode_smem_bytes(const EncodeParams &p) {
+  size_t tabs = ((size_t)2 << p.hash_log) + (p.long_log ? ((size_t)2 << p.long_log) : 0);
+  size_t ent = sizeof(EntropyWs);
+  return (tabs > ent ? tabs : ent) + 16;
+}
+
+// ---- unaligned 8-byte read through aligned 32-bit loads, clamped to the chunk's last word ----------
+struct Src {
+  const uint32_t *w;      // 4-byte aligned base (<= chunk start)
+  uint32_t delta;         // chunk start - aligned base (0..3)
+  uint32_t last_word;     // index of the last word that holds chunk bytes
+  __device__ __forceinline__ uint64_t ld64(uint32_t pos) const {      // pos relative to chunk start
+    const uint32_t off = pos + delta, a = off >> 2, sh = (off & 3) * 8;
+    const uint32_t w0 = __ldg(w + min(a, last_word)), w1 = __ldg(w + min(a + 1, last_word)), w2 = __ldg(w + min(a + 2, last_word));
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    return ((uint64_t)hi << 32) | lo;
+  }
+};
+__device__ __forceinline__ uint32_t common8(uint64_t a, uint64_t b) {
+  const uint64_t x = a ^ b;
+  return x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+}
+
+struct ParseCtx {
+  Src src;
+  const uint8_t *chunk;
+  uint32_t blk_off, bn, ilimit;
+  uint16_t *tab1, *tab2, *chain;
+  EncodeParams P;
+};
+
+// forward length of the match (s, s - off) inside the block, given `have` (<= 8) verified bytes;
+// the whole warp compares 32 x 8 bytes per round.  Uniform arguments, uniform result.
+__device__ uint32_t extend_warp(const ParseCtx &C, uint32_t s, uint32_t off, uint32_t have, int lane) {
+  if (have < 8) return have;
+  uint32_t len = 8;
+  for (;;) {
+    const uint32_t p = s + len + 8u * (uint32_t)lane;
+    uint32_t c = 0;
+    if (p < C.bn) {
+      c = common8(C.src.ld64(C.blk_off + p), C.src.ld64(C.blk_off + p - off));
+      const uint32_t room = C.bn - p;
+      if (c > room) c = room;
+    }
+    const uint32_t stop = __ballot_sync(0xffffffffu, c < 8);
+    if (stop) {
+      const int j = __ffs(stop) - 1;
+      return len + 8u * (uint32_t)j + __shfl_sync(0xffffffffu, c, j);
+    }
+    len += 256;
+  }
+}
+
+// per-lane forward length capped at `cap` (chain levels)
+__device__ __forceinline__ uint32_t extend_lane(const ParseCtx &C, uint32_t pos, uint32_t off, uint32_t cap) {
+  uint32_t len = 8;
+  while (len < cap && pos + len < C.bn) {
+    uint32_t c = common8(C.src.ld64(C.blk_off + pos + len), C.src.ld64(C.blk_off + pos + len - off));
+    const uint32_t room = C.bn - pos - len;
+    if (c > room) c = room;
+    len += c;
+    if (c < 8) break;
+  }
+  return len < cap ? len : cap;
+}
+
+// table update for one stripe of up to 32 consecutive positions [p0, p0+cnt): sequential semantics
+__device__ __forceinline__ void insert_stripe(const ParseCtx &C, uint32_t p0, uint32_t cnt, int lane) {
+  const uint32_t pos = p0 + (uint32_t)lane;
+  const bool act = (uint32_t)lane < cnt && pos < C.ilimit;
+  uint64_t v = 0;
+  if (act) v = C.src.ld64(C.blk_off + pos);
+  // inactive lanes get unique keys above any real hash so they never group with active lanes
+  const uint32_t h1 = act ? hash_short(v, C.P.hash_bytes, C.P.hash_log) : 0x80000000u + (uint32_t)lane;
+  const uint32_t g1 = __match_any_sync(0xffffffffu, h1);
+  if (act) {
+    const uint32_t lower = g1 & lanemask_lt();
+    if (C.chain) {
+      const uint32_t prev = lower ? (p0 + (uint32_t)(31 - __clz(lower))) : (uint32_t)C.tab1[h1];
+      C.chain[pos] = (uint16_t)((pos - prev) & 0xFFFF);
+    }
+  }
+  __syncwarp();
+  if (act && (g1 >> lane) == 1u) C.tab1[h1] = (uint16_t)pos;
+  if (C.tab2) {
+    const uint32_t h2 = act ? hash_long(v, C.P.long_log) : 0x80000000u + (uint32_t)lane;
+    const uint32_t g2 = __match_any_sync(0xffffffffu, h2);
+    if (act && (g2 >> lane) == 1u) C.tab2[h2] = (uint16_t)pos;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint32_t s_chunk;
+  const int lane = threadIdx.x;
+  const EncodeParams P = A.prm;
+  uint8_t *const scratch = A.scratch + (size_t)blockIdx.x * cta_scratch;
+  uint8_t *const lits = scratch + EncScratch::lits_off;
+  uint32_t *const s_ll = (uint32_t *)(scratch + EncScratch::ll_off);
+  uint32_t *const s_ml = (uint32_t *)(scratch + EncScratch::ml_off);
+  uint32_t *const s_of = (uint32_t *)(scratch + EncScratch::of_off);
+  EntropyWs &W = *reinterpret_cast<EntropyWs *>(smem);
+
+  for (;;) {
+    if (lane == 0) s_chunk = atomicAdd(A.counter, 1u);
+    __syncwarp();
+    const uint32_t chunk_id = s_chunk;
+    __syncwarp();
+    if (chunk_id >= A.n) break;
+
+    const uint8_t *const chunk = (const uint8_t *)A.in_ptrs[chunk_id];
+    const size_t n = A.in_sizes[chunk_id];
+    uint8_t *const dst = (uint8_t *)A.out_ptrs[chunk_id];
+    const size_t cap = A.out_sizes[chunk_id];
+    uint32_t status = ST_OK;
+    size_t op = 0;
+    if (!chunk || !dst) status = ST_INVALID_PARAMETER;
+    else if (n == 0) status = ST_INVALID_PARAMETER;                       // reference: manager.cu:1554-1558
+    else if (n > 0xFFFF0000ull) status = ST_UNSUPPORTED;
+    const size_t nblocks = (n + BLOCK_BYTES - 1) / BLOCK_BYTES;
+    if (status == ST_OK && cap < (size_t)frame_header_size(n) + n + 3 * nblocks + (P.checksum ? 4 : 0)) status = ST_BUFFER_TOO_SMALL;
+
+    if (status == ST_OK) {
+      ParseCtx C;
+      C.P = P;
+      C.chunk = chunk;
+      C.src.w = (const uint32_t *)((uintptr_t)chunk & ~(uintptr_t)3);
+      C.src.delta = (uint32_t)((uintptr_t)chunk & 3);
+      C.src.last_word = (uint32_t)((n - 1 + C.src.delta) >> 2);
+      C.tab1 = (uint16_t *)smem;
+      C.tab2 = P.long_log ? (uint16_t *)(smem + ((size_t)2 << P.hash_log)) : nullptr;
+      C.chain = P.chain_depth > 0 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
+
+      if (lane == 0) op = write_frame_header(dst, n, P.checksum != 0);
+      op = __shfl_sync(0xffffffffu, (unsigned long long)op, 0);
+      uint32_t rep[3] = {1, 4, 8};
+      size_t ip_chunk = 0;
+      while (ip_chunk < n) {
+        const uint32_t bn = (uint32_t)min((size_t)BLOCK_BYTES, n - ip_chunk);
+        const bool last = ip_chunk + bn == n;
+        const uint32_t blk_off = (uint32_t)ip_chunk;
+        // ---- RLE block? ----
+        {
+          const uint8_t b0 = chunk[blk_off];
+          bool same = true;
+          for (uint32_t k = lane; k < bn && same; k += 32) same = chunk[blk_off + k] == b0;
+          if (__all_sync(0xffffffffu, same) && bn > 1) {
+            if (lane == 0) { write_block_header(dst + op, last, 1, bn); dst[op + 3] = b0; }
+            op += 4;
+            ip_chunk += bn;
+            continue;
+          }
+        }
+        // ---- parse ----
+        C.blk_off = blk_off; C.bn = bn; C.ilimit = bn > 8 ? bn - 8 : 0;
+        {
+          const uint32_t words = (((uint32_t)2 << P.hash_log) + (P.long_log ? ((uint32_t)2 << P.long_log) : 0)) >> 2;
+          uint32_t *z = (uint32_t *)smem;
+          for (uint32_t k = lane; k < words; k += 32) z[k] = 0;
+          // "ghost" candidates of never-written buckets are positions 0 and 65536: their chain links
+          // must read as end-of-chain until those positions are really inserted
+          if (C.chain && lane == 0) { C.chain[0] = 0; if (bn > 65536) C.chain[65536] = 0; }
+        }
+        __syncwarp();
+        const uint32_t rep_save0 = rep[0], rep_save1 = rep[1], rep_save2 = rep[2];
+        uint32_t ip = 0, anchor = 0, nseq = 0, nlit = 0;
+        while (ip < C.ilimit && nseq < MAX_SEQ_PER_BLOCK) {
+          const uint32_t pos = ip + (uint32_t)lane;
+          uint32_t best = 0, bo = 0;
+          bool has = false;
+          if (pos < C.ilimit) {
+            const uint64_t v = C.src.ld64(blk_off + pos);
+            if (C.tab2) {
+              int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab2[hash_long(v, P.long_log)]);
+              if (c >= (int64_t)pos) c -= 0x10000;
+              if (c >= 0 && common8(v, C.src.ld64(blk_off + (uint32_t)c)) == 8) { best = 8; bo = pos - (uint32_t)c; }
+            }
+            {
+              int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab1[hash_short(v, P.hash_bytes, P.hash_log)]);
+              if (c >= (int64_t)pos) c -= 0x10000;
+              int depth = P.chain_depth > 0 ? P.chain_depth : 1;
+              while (depth-- > 0 && c >= 0) {
+                uint32_t l = common8(v, C.src.ld64(blk_off + (uint32_t)c));
+                if (C.chain && l == 8) l = extend_lane(C, pos, pos - (uint32_t)c, P.lane_cap);
+                if (l >= (uint32_t)P.min_match && l > best) { best = l; bo = pos - (uint32_t)c; }
+                if (!C.chain) break;
+                const uint32_t d = C.chain[(uint32_t)c];
+                if (d == 0) break;
+                c -= d;
+              }
+            }
+            if (blk_off + pos >= rep[0]) {
+              uint32_t l = common8(v, C.src.ld64(blk_off + pos - rep[0]));
+              if (C.chain && l == 8) l = extend_lane(C, pos, rep[0], P.lane_cap);
+              if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
+            }
+            has = best >= (uint32_t)P.min_match || (bo == rep[0] && best >= 4);
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, has);
+          if (mask == 0) {
+            insert_stripe(C, ip, 32, lane);
+            ip += 32;
+            continue;
+          }
+          const int f = __ffs(mask) - 1;
+          uint32_t s = ip + (uint32_t)f;
+          uint32_t off = __shfl_sync(0xffffffffu, bo, f);
+          const uint32_t bl_f = __shfl_sync(0xffffffffu, best, f);
+          uint32_t len = extend_warp(C, s, off, bl_f < 8 ? bl_f : 8, lane);
+          for (int step = 1; step <= P.lazy; step++) {
+            const int g = f + step;
+            if (g >= 32 || !((mask >> g) & 1)) continue;
+            const uint32_t bl_g = __shfl_sync(0xffffffffu, best, g), off2 = __shfl_sync(0xffffffffu, bo, g);
+            if (bl_g < 8 && bl_g <= len) continue;
+            const uint32_t s2 = ip + (uint32_t)g;
+            const uint32_t len2 = extend_warp(C, s2, off2, bl_g < 8 ? bl_g : 8, lane);
+            const int gain1 = (int)len * 4 - hb32(off + 1) + 3 * step + (off == rep[0] ? hb32(off + 1) : 0);
+            const int gain2 = (int)len2 * 4 - hb32(off2 + 1) + (off2 == rep[0] ? hb32(off2 + 1) : 0);
+            if (gain2 > gain1) { s = s2; off = off2; len = len2; }
+          }
+          // backward extension into the pending literals
+          for (;;) {
+            const uint32_t k = (uint32_t)lane;
+            bool m = false;
+            if (k < s - anchor && (uint64_t)k + off < (uint64_t)blk_off + s)
+              m = chunk[blk_off + s - 1 - k] == chunk[blk_off + s - 1 - k - off];
+            const uint32_t bal = __ballot_sync(0xffffffffu, m);
+            const uint32_t ext = (bal == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~bal) - 1);
+            s -= ext; len += ext;
+            if (ext < 32) break;
+          }
+          // tables: window positions before the match ...
+          if (s > ip) insert_stripe(C, ip, min(s - ip, 32u), lane);
+          // ... emit ...
+          const uint32_t llen = s - anchor;
+          for (uint32_t k = lane; k < llen; k += 32) lits[nlit + k] = chunk[blk_off + anchor + k];
+          const uint32_t code = offset_to_code(off, llen, rep);
+          if (lane == 0) { s_ll[nseq] = llen; s_ml[nseq] = len; s_of[nseq] = code; }
+          nlit += llen; nseq++;
+          // ... and the positions the match covers
+          {
+            const uint32_t from = s > ip ? s : ip, end = s + len;
+            if (P.insert_all) { for (uint32_t p = from; p < end; p += 32) insert_stripe(C, p, min(end - p, 32u), lane); }
+            else { insert_stripe(C, from, 1, lane); if (end >= 2) insert_stripe(C, end - 2, 1, lane); }
+          }
+          ip = anchor = s + len;
+        }
+        {
+          const uint32_t rest = bn - anchor;
+          for (uint32_t k = lane; k < rest; k += 32) lits[nlit + k] = chunk[blk_off + anchor + k];
+          nlit += rest;
+        }
+        __syncwarp();
+        __threadfence_block();
+        // ---- entropy stage (the hash tables are dead: the same shared memory now holds EntropyWs) ----
+        uint32_t payload = 0;
+        if (lane == 0 && nseq < MAX_SEQ_PER_BLOCK)
+          payload = encode_block_payload(W, lits, nlit, s_ll, s_ml, s_of, nseq, dst + op + 3, bn - 1);
+        payload = __shfl_sync(0xffffffffu, payload, 0);
+        if (payload == 0 || payload >= bn) {
+          rep[0] = rep_save0; rep[1] = rep_save1; rep[2] = rep_save2;
+          if (lane == 0) write_block_header(dst + op, last, 0, bn);
+          for (uint32_t k = lane; k < bn; k += 32) dst[op + 3 + k] = chunk[blk_off + k];
+          op += 3 + (size_t)bn;
+        } else {
+          if (lane == 0) write_block_header(dst + op, last, 2, payload);
+          op += 3 + (size_t)payload;
+        }
+        __syncwarp();
+        ip_chunk += bn;
+      }
+      if (P.checksum) {
+        // hash in <= 1 GiB pieces is not needed: chunks are far below 4 GiB (checked above)
+        const uint64_t h = xxh64_warp(chunk, (uint32_t)n, lane);
+        if (lane == 0) { dst[op] = (uint8_t)h; dst[op + 1] = (uint8_t)(h >> 8); dst[op + 2] = (uint8_t)(h >> 16); dst[op + 3] = (uint8_t)(h >> 24); }
+        op += 4;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      A.out_sizes[chunk_id] = status == ST_OK ? op : 0;
+      if (A.statuses) A.statuses[chunk_id] = status;
+    }
+  }
+}
+
+cudaError_t launch_encode_batch(const EncodeArgs &args, int grid, cudaStream_t stream) {
+  if (args.n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(args.counter, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  const size_t smem = encode_smem_bytes(args.prm);
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(zstd_encode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  zstd_encode_batch_kernel<<<grid, ENC_THREADS, smem, stream>>>(args, encode_cta_scratch_bytes(args.prm));
+  return cudaGetLastError();
+}
+
+int encode_ctas_per_sm(const EncodeParams &prm) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel, ENC_THREADS, encode_smem_bytes(prm)) != cudaSuccess || n < 1) n = 8;
+  return n;
+}
+
+} // namespace b200zstd

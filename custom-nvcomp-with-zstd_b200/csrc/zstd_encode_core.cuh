@@ -60,15 +60,16 @@ ZHD uint32_t ml_code(uint32_t ml) {   // ml >= 3
 
 struct SymTT { int32_t delta_nb; int32_t delta_state; };
 
-// bases/bits for the three alphabets, host+device copies
-#define ZLLB {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536}
-#define ZLLX {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16}
-#define ZMLB {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539}
-#define ZMLX {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16}
-ZHD uint32_t ll_base(uint32_t c) { const uint32_t t[36] = ZLLB; return t[c]; }
-ZHD uint32_t ll_xbits(uint32_t c) { const uint8_t t[36] = ZLLX; return t[c]; }
-ZHD uint32_t ml_base(uint32_t c) { const uint32_t t[53] = ZMLB; return t[c]; }
-ZHD uint32_t ml_xbits(uint32_t c) { const uint8_t t[53] = ZMLX; return t[c]; }
+// base value and number of extra bits of a length code, computed (no table lookups in the hot loops)
+ZHD uint32_t ll_xbits(uint32_t c) { return c < 16 ? 0u : c < 20 ? 1u : c < 22 ? 2u : c < 24 ? 3u : c == 24 ? 4u : c - 19; }
+ZHD uint32_t ll_base(uint32_t c) {
+  return c < 16 ? c : c < 20 ? 16 + 2 * (c - 16) : c < 22 ? 24 + 4 * (c - 20) : c < 24 ? 32 + 8 * (c - 22) : c == 24 ? 48u : 1u << (c - 19);
+}
+ZHD uint32_t ml_xbits(uint32_t c) { return c < 32 ? 0u : c < 36 ? 1u : c < 38 ? 2u : c < 40 ? 3u : c < 42 ? 4u : c == 42 ? 5u : c - 36; }
+ZHD uint32_t ml_base(uint32_t c) {
+  return c < 32 ? c + 3 : c < 36 ? 35 + 2 * (c - 32) : c < 38 ? 43 + 4 * (c - 36) : c < 40 ? 51 + 8 * (c - 38)
+                                                   : c < 42 ? 67 + 16 * (c - 40) : c == 42 ? 99u : (1u << (c - 36)) + 3;
+}
 
 ZHD void default_norm(int kind, int16_t *norm, int *max_sym, int *log) {
   const int16_t ll[36] = {4, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 1, 1, -1, -1, -1, -1};
@@ -598,6 +599,102 @@ ZHD uint32_t offset_to_code(uint32_t offset, uint32_t ll, uint32_t *rep) {
   rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = offset;
   return code;
 }
+
+// ---- entropy stage of one block: literals section + sequences section --------------------------------
+// Returns the block payload size, 0 = does not fit / not worth it (caller stores the block raw).
+ZHDN uint32_t encode_block_payload(EntropyWs &W, const uint8_t *lits, uint32_t nlit, const uint32_t *sll, const uint32_t *sml,
+                                   const uint32_t *sofv, uint32_t nseq, uint8_t *dst, uint32_t cap) {
+  uint32_t op = 0;
+  // ---- literals ----
+  bool done = false;
+  if (nlit >= 64) {
+    for (int i = 0; i < 256; i++) W.count[i] = 0;
+    for (uint32_t i = 0; i < nlit; i++) W.count[lits[i]]++;
+    int max_sym = 255;
+    while (max_sym > 0 && !W.count[max_sym]) max_sym--;
+    uint32_t maxc = 0;
+    for (int s = 0; s <= max_sym; s++) if (W.count[s] > maxc) maxc = W.count[s];
+    if (maxc == nlit) {                                    // RLE literals
+      if (cap < 4) return 0;
+      op = write_lit_header_raw_rle(dst, 1, nlit);
+      dst[op++] = lits[0];
+      done = true;
+    } else if (maxc <= (nlit >> 7) + 4) {
+      // nearly flat histogram: not worth a Huffman table (libzstd applies the same early exit)
+    } else {
+      int tl = huf_build_lengths(W.count, max_sym, 11, W.huflen, W.order, W.ncount, W.parent);
+      if (tl > 0) {
+        uint16_t *codes = W.order;                           // free again after the length build
+        huf_assign_codes(W.huflen, max_sym, tl, codes);
+        for (int s = 0; s <= max_sym; s++) W.hufc[s] = W.huflen[s] ? ((uint32_t)codes[s] | ((uint32_t)W.huflen[s] << 16)) : 0u;
+        const uint32_t hs = lit_header_size_compressed(nlit);
+        const bool single = nlit < 256;
+        uint32_t budget = nlit - ((nlit >> 6) + 2);       // must beat raw by libzstd's minimum gain
+        if (budget + hs > cap) budget = cap > hs ? cap - hs : 0;
+        uint8_t *body = dst + hs;
+        uint32_t t = huf_write_table(W, max_sym, tl, body, budget);
+        bool ok = t != 0;
+        uint32_t used = t;
+        if (ok) {
+          if (single) {
+            uint32_t n = huf_encode_stream(lits, nlit, W.hufc, body + used, budget - used);
+            if (!n) ok = false; else used += n;
+          } else {
+            if (used + 6 > budget) ok = false;
+            else {
+              const uint32_t seg = (nlit + 3) / 4;
+              uint32_t jt = used;
+              used += 6;
+              for (int k = 0; k < 4 && ok; k++) {
+                const uint32_t cnt = k < 3 ? seg : nlit - 3 * seg;
+                uint32_t n = huf_encode_stream(lits + k * seg, cnt, W.hufc, body + used, budget - used);
+                if (!n || n > 0xFFFF) { ok = false; break; }
+                if (k < 3) { body[jt + 2 * k] = (uint8_t)n; body[jt + 2 * k + 1] = (uint8_t)(n >> 8); }
+                used += n;
+              }
+            }
+          }
+        }
+        if (ok && used < budget) {
+          write_lit_header_compressed(dst, hs, single, nlit, used);
+          op = hs + used;
+          done = true;
+        }
+      }
+    }
+  }
+  if (!done) {                                             // raw literals
+    if (cap < nlit + 3) return 0;
+    op = write_lit_header_raw_rle(dst, 0, nlit);
+    for (uint32_t i = 0; i < nlit; i++) dst[op + i] = lits[i];
+    op += nlit;
+  }
+  // ---- sequences ----
+  if (op + 4 > cap) return 0;
+  op += seq_count_header(dst + op, nseq);
+  if (nseq == 0) return op;
+  uint8_t *modes = dst + op++;
+  int mode[3];
+  for (int kind = 0; kind < 3; kind++) {
+    for (int i = 0; i < 64; i++) W.count[i] = 0;
+    int maxc = 0;
+    for (uint32_t i = 0; i < nseq; i++) {
+      uint32_t c = kind == 0 ? ll_code(sll[i]) : kind == 1 ? (uint32_t)hb32(sofv[i]) : ml_code(sml[i]);
+      W.count[c]++;
+      if ((int)c > maxc) maxc = (int)c;
+    }
+    uint32_t desc = 0;
+    mode[kind] = seq_table_prepare(W, kind, W.count, maxc, nseq, dst + op, cap - op, &desc);
+    if (mode[kind] < 0) return 0;
+    op += desc;
+  }
+  *modes = (uint8_t)((mode[0] << 6) | (mode[1] << 4) | (mode[2] << 2));
+  SeqStore S{sll, sml, sofv};
+  uint32_t n = seq_encode_stream(W, S, nseq, dst + op, cap - op);
+  if (!n) return 0;
+  return op + n;
+}
+
 
 } // namespace enc
 } // namespace b200zstd

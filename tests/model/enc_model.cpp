@@ -169,103 +169,6 @@ void parse_block(const uint8_t *chunk, uint32_t blk_off, uint32_t bn, const Enco
   (void)ip;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Entropy stage + block assembly.  Returns block payload size (0 = store raw).
-// ------------------------------------------------------------------------------------------------
-uint32_t encode_block_payload(EntropyWs &W, const BlockOut &B, uint8_t *dst, uint32_t cap) {
-  uint32_t op = 0;
-  const uint32_t nlit = (uint32_t)B.lits.size();
-  // ---- literals ----
-  bool done = false;
-  if (nlit >= 64) {
-    for (int i = 0; i < 256; i++) W.count[i] = 0;
-    for (uint32_t i = 0; i < nlit; i++) W.count[B.lits[i]]++;
-    int max_sym = 255;
-    while (max_sym > 0 && !W.count[max_sym]) max_sym--;
-    uint32_t maxc = 0;
-    for (int s = 0; s <= max_sym; s++) if (W.count[s] > maxc) maxc = W.count[s];
-    if (maxc == nlit) {                                    // RLE literals
-      if (cap < 4) return 0;
-      op = write_lit_header_raw_rle(dst, 1, nlit);
-      dst[op++] = B.lits[0];
-      done = true;
-    } else if (maxc <= (nlit >> 7) + 4) {
-      // nearly flat histogram: not worth a Huffman table (libzstd applies the same early exit)
-    } else {
-      int tl = huf_build_lengths(W.count, max_sym, 11, W.huflen, W.order, W.ncount, W.parent);
-      if (tl > 0) {
-        uint16_t codes[256];
-        huf_assign_codes(W.huflen, max_sym, tl, codes);
-        for (int s = 0; s <= max_sym; s++) W.hufc[s] = (uint32_t)codes[s] | ((uint32_t)W.huflen[s] << 16);
-        const uint32_t hs = lit_header_size_compressed(nlit);
-        const bool single = nlit < 256;
-        uint32_t budget = nlit - ((nlit >> 6) + 2);       // must beat raw by libzstd's minimum gain
-        if (budget + hs > cap) budget = cap > hs ? cap - hs : 0;
-        uint8_t *body = dst + hs;
-        uint32_t t = huf_write_table(W, max_sym, tl, body, budget);
-        bool ok = t != 0;
-        uint32_t used = t;
-        if (ok) {
-          if (single) {
-            uint32_t n = huf_encode_stream(B.lits.data(), nlit, W.hufc, body + used, budget - used);
-            if (!n) ok = false; else used += n;
-          } else {
-            if (used + 6 > budget) ok = false;
-            else {
-              const uint32_t seg = (nlit + 3) / 4;
-              uint32_t jt = used;
-              used += 6;
-              for (int k = 0; k < 4 && ok; k++) {
-                const uint32_t cnt = k < 3 ? seg : nlit - 3 * seg;
-                uint32_t n = huf_encode_stream(B.lits.data() + k * seg, cnt, W.hufc, body + used, budget - used);
-                if (!n || n > 0xFFFF) { ok = false; break; }
-                if (k < 3) { body[jt + 2 * k] = (uint8_t)n; body[jt + 2 * k + 1] = (uint8_t)(n >> 8); }
-                used += n;
-              }
-            }
-          }
-        }
-        if (ok && used < budget) {
-          write_lit_header_compressed(dst, hs, single, nlit, used);
-          op = hs + used;
-          done = true;
-        }
-      }
-    }
-  }
-  if (!done) {                                             // raw literals
-    if (cap < nlit + 3) return 0;
-    op = write_lit_header_raw_rle(dst, 0, nlit);
-    memcpy(dst + op, B.lits.data(), nlit);
-    op += nlit;
-  }
-  // ---- sequences ----
-  const uint32_t nseq = (uint32_t)B.ll.size();
-  if (op + 4 > cap) return 0;
-  op += seq_count_header(dst + op, nseq);
-  if (nseq == 0) return op;
-  uint8_t *modes = dst + op++;
-  int mode[3];
-  for (int kind = 0; kind < 3; kind++) {
-    for (int i = 0; i < 64; i++) W.count[i] = 0;
-    int maxc = 0;
-    for (uint32_t i = 0; i < nseq; i++) {
-      uint32_t c = kind == 0 ? ll_code(B.ll[i]) : kind == 1 ? (uint32_t)hb32(B.ofv[i]) : ml_code(B.ml[i]);
-      W.count[c]++;
-      if ((int)c > maxc) maxc = (int)c;
-    }
-    uint32_t desc = 0;
-    mode[kind] = seq_table_prepare(W, kind, W.count, maxc, nseq, dst + op, cap - op, &desc);
-    if (mode[kind] < 0) return 0;
-    op += desc;
-  }
-  *modes = (uint8_t)((mode[0] << 6) | (mode[1] << 4) | (mode[2] << 2));
-  SeqStore S{B.ll.data(), B.ml.data(), B.ofv.data()};
-  uint32_t n = seq_encode_stream(W, S, nseq, dst + op, cap - op);
-  if (!n) return 0;
-  return op + n;
-}
-
 } // namespace
 
 extern "C" {
@@ -297,7 +200,7 @@ size_t model_compress(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, in
     BlockOut B;
     uint32_t rep_save[3] = {rep[0], rep[1], rep[2]};
     parse_block(src, (uint32_t)ip, bn, P, rep, B, MAX_SEQ_PER_BLOCK);
-    uint32_t payload = B.ll.size() >= MAX_SEQ_PER_BLOCK ? 0 : encode_block_payload(W, B, tmp.data(), bn - 1);
+    uint32_t payload = B.ll.size() >= MAX_SEQ_PER_BLOCK ? 0 : encode_block_payload(W, B.lits.data(), (uint32_t)B.lits.size(), B.ll.data(), B.ml.data(), B.ofv.data(), (uint32_t)B.ll.size(), tmp.data(), bn - 1);
     if (payload == 0 || payload >= bn) {
       rep[0] = rep_save[0]; rep[1] = rep_save[1]; rep[2] = rep_save[2];
       write_block_header(dst + op, last, 0, bn); op += 3;

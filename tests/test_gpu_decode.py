@@ -1,0 +1,181 @@
+"""GPU parity tests for the batch DECODER, called through the C ABI (ctypes) on torch device buffers.
+Oracle = oracle/zstd_oracle.c + the system libzstd (what the reference runs at these sizes)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CLASSES, golden_cases, golden_frame, golden_input
+
+pytestmark = pytest.mark.gpu
+
+
+def to_dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_decode(codec, blob, offs, sizes, chunk, caps=None):
+    """returns (rc, out ndarray with stride chunk, out_sizes)"""
+    n = len(sizes)
+    comp = to_dev(blob)
+    out = torch.zeros(n * chunk, dtype=torch.uint8, device="cuda")
+    idx = np.arange(n, dtype=np.uint64)
+    in_ptrs = (np.uint64(comp.data_ptr()) + np.asarray(offs, np.uint64)).astype(np.uint64)
+    out_ptrs = (np.uint64(out.data_ptr()) + idx * np.uint64(chunk)).astype(np.uint64)
+    out_sizes = np.full(n, chunk, np.uint64) if caps is None else np.asarray(caps, np.uint64).copy()
+    ws = torch.empty(codec.decompress_temp_size(n), dtype=torch.uint8, device="cuda")
+    rc = codec.decompress_tables(in_ptrs, np.asarray(sizes, np.uint64), n, out_ptrs, out_sizes, ws)
+    return rc, out.cpu().numpy(), out_sizes
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_golden_frames(oracle, gpu_codec_factory, case):
+    codec = gpu_codec_factory()
+    data, frame = golden_input(oracle, case), golden_frame(case)
+    rc, out, osz = gpu_decode(codec, frame, [0], [frame.size], data.size)
+    assert rc == 0 and int(osz[0]) == data.size and np.array_equal(out, data)
+
+
+@pytest.mark.parametrize("level", [1, 3, 5, 9, 19])
+@pytest.mark.parametrize("chunk", [65536, 131072, 4096])
+def test_libzstd_frames_all_classes(oracle, libzstd, gpu_codec_factory, level, chunk):
+    codec = gpu_codec_factory()
+    parts = [oracle.gen_batch(chunk, 6, kind, P, first_idx=11 * i) for i, (_, kind, P) in enumerate(CLASSES)]
+    d = np.concatenate(parts)
+    blob, offs, sizes = libzstd.compress_chunks(d, chunk, level, checksum=(level == 9))
+    rc, out, osz = gpu_decode(codec, blob, offs, sizes, chunk)
+    assert rc == 0 and (osz == chunk).all()
+    assert np.array_equal(out, d)
+    # and equal to the oracle's decode of the same frames
+    rc2, out2, _ = oracle.decompress_batch(blob, offs, sizes, chunk)
+    assert rc2 == 0 and np.array_equal(out, out2)
+
+
+def test_ragged_sizes_and_unaligned_frames(oracle, libzstd, gpu_codec_factory):
+    codec = gpu_codec_factory()
+    rng = np.random.default_rng(5)
+    sizes_in = [1, 2, 5, 17, 100, 255, 256, 300, 1023, 4097, 20000, 65535, 65536, 70001, 131072]
+    datas = [oracle.gen_batch(n, 1, 0, int(rng.integers(0, 60000)), first_idx=i) for i, n in enumerate(sizes_in)]
+    frames = [libzstd.compress(x, int(rng.integers(1, 10))) for x in datas]
+    # pack with odd gaps so that frames start at arbitrary alignments
+    blob, offs = [], []
+    pos = 0
+    for f in frames:
+        pad = int(rng.integers(0, 7))
+        blob.append(np.zeros(pad, np.uint8)); pos += pad
+        offs.append(pos); blob.append(f); pos += f.size
+    blob = np.concatenate(blob)
+    cap = 131072
+    rc, out, osz = gpu_decode(codec, blob, offs, [f.size for f in frames], cap)
+    assert rc == 0
+    for i, x in enumerate(datas):
+        assert int(osz[i]) == x.size and np.array_equal(out[i * cap: i * cap + x.size], x), i
+
+
+def test_multiblock_repeat_treeless_and_checksum(oracle, libzstd, pkg):
+    codec = pkg.ZstdBatchCodec(level=3, checksum=True)          # COMPUTE_AND_VERIFY: checksums are verified
+    big = [oracle.gen_batch(700000, 1, 0, 30000), oracle.gen_textlike(1 << 20), np.zeros(500000, np.uint8),
+           oracle.gen_batch(300000, 1, 1, 0)]
+    frames = [libzstd.compress(x, lvl, checksum=True) for x, lvl in zip(big, (1, 3, 7, 12))]
+    offs = np.cumsum([0] + [f.size for f in frames[:-1]])
+    cap = 1 << 20
+    rc, out, osz = gpu_decode(codec, np.concatenate(frames), offs, [f.size for f in frames], cap)
+    assert rc == 0
+    for i, x in enumerate(big):
+        assert int(osz[i]) == x.size and np.array_equal(out[i * cap: i * cap + x.size], x), i
+    # a flipped payload byte is caught by the XXH64 trailer or as corruption
+    bad = frames[0].copy(); bad[-2] ^= 0x40
+    rc, out, osz = gpu_decode(codec, bad, [0], [bad.size], cap)
+    assert rc != 0 and int(osz[0]) == 0
+
+
+def test_skippable_and_concatenated_frames(oracle, libzstd, gpu_codec_factory):
+    codec = gpu_codec_factory()
+    a, b = oracle.gen_batch(5000, 1, 0, 30000), oracle.gen_batch(7000, 1, 0, 10000, first_idx=3)
+    skip = np.frombuffer(bytes([0x53, 0x2A, 0x4D, 0x18, 5, 0, 0, 0, 1, 2, 3, 4, 5]), np.uint8)
+    blob = np.concatenate([skip, libzstd.compress(a, 3), skip, libzstd.compress(b, 5)])
+    rc, out, osz = gpu_decode(codec, blob, [0], [blob.size], 16384)
+    assert rc == 0 and int(osz[0]) == 12000 and np.array_equal(out[:12000], np.concatenate([a, b]))
+    assert np.array_equal(libzstd.decompress(blob, 16384), np.concatenate([a, b]))
+
+
+def test_error_statuses(oracle, libzstd, pkg, gpu_codec_factory):
+    codec = gpu_codec_factory()
+    d = oracle.gen_batch(65536, 1, 0, 32768)
+    f = libzstd.compress(d, 3)
+    n = 6
+    frames = [f.copy() for _ in range(n)]
+    frames[1][0] ^= 1                       # bad magic
+    frames[2] = frames[2][: f.size // 2]    # truncated
+    frames[3][20] ^= 0xFF                   # damaged payload
+    offs = np.cumsum([0] + [x.size for x in frames[:-1]])
+    caps = [65536, 65536, 65536, 65536, 1000, 65536]     # item 4: capacity too small
+    comp = to_dev(np.concatenate(frames))
+    out = torch.zeros(n * 65536, dtype=torch.uint8, device="cuda")
+    idx = np.arange(n, dtype=np.uint64)
+    in_ptrs = to_dev((np.uint64(comp.data_ptr()) + offs.astype(np.uint64)).astype(np.int64))
+    in_sizes = to_dev(np.array([x.size for x in frames], np.int64))
+    out_ptrs = to_dev((np.uint64(out.data_ptr()) + idx * np.uint64(65536)).astype(np.int64))
+    out_sizes = to_dev(np.array(caps, np.int64))
+    status = torch.full((n,), 77, dtype=torch.int32, device="cuda")
+    ws = torch.empty(codec.decompress_temp_size(n), dtype=torch.uint8, device="cuda")
+    rc = codec.decompress_nosync(in_ptrs, in_sizes, n, out_ptrs, out_sizes, status, ws)
+    torch.cuda.synchronize()
+    assert rc == 0
+    st = status.cpu().numpy().tolist()
+    assert st[0] == 0 and st[5] == 0
+    assert st[1] == pkg.Status.ERROR_INVALID_MAGIC
+    assert st[2] == pkg.Status.ERROR_CORRUPT_DATA
+    assert st[3] in (pkg.Status.ERROR_CORRUPT_DATA, 0)
+    assert st[4] == pkg.Status.ERROR_BUFFER_TOO_SMALL
+    osz = out_sizes.cpu().numpy()
+    assert osz[0] == 65536 and osz[1] == 0 and osz[2] == 0 and osz[4] == 0
+    assert np.array_equal(out.cpu().numpy()[:65536], d)
+    # synchronous call on the same batch: overall ERROR_GENERIC (1), workspace too small -> 7
+    caps_h = np.array(caps, np.uint64)
+    rc = codec.decompress_tables(in_ptrs.cpu().numpy().astype(np.uint64), in_sizes.cpu().numpy().astype(np.uint64), n,
+                                 out_ptrs.cpu().numpy().astype(np.uint64), caps_h, ws)
+    assert rc == 1
+    rc = codec.decompress_tables(in_ptrs.cpu().numpy().astype(np.uint64), in_sizes.cpu().numpy().astype(np.uint64), n,
+                                 out_ptrs.cpu().numpy().astype(np.uint64), caps_h, ws[:128])
+    assert rc == 7
+    # random single-byte damage: never a crash, never silent wrong output with checksum frames
+    codec_ck = pkg.ZstdBatchCodec(level=3, checksum=True)
+    fck = libzstd.compress(d, 3, checksum=True)
+    rng = np.random.default_rng(9)
+    m = 256
+    damaged = []
+    for _ in range(m):
+        x = fck.copy(); x[int(rng.integers(4, x.size))] ^= int(rng.integers(1, 256)); damaged.append(x)
+    offs = np.arange(m) * fck.size
+    rc, outd, osz = gpu_decode(codec_ck, np.concatenate(damaged), offs, [fck.size] * m, 65536)
+    for i in range(m):
+        if osz[i]:
+            assert np.array_equal(outd[i * 65536:(i + 1) * 65536], d), i
+
+
+def test_device_tables_and_single_buffer_apis(oracle, libzstd, pkg, gpu_codec_factory):
+    codec = gpu_codec_factory()
+    chunk, n = 32768, 4                                   # reference tests/test_nvcomp_interface.cu:195-369 uses 4 x 32 KB
+    d = oracle.gen_batch(chunk, n, 0, 32768)
+    blob, offs, sizes = libzstd.compress_chunks(d, chunk, 3)
+    comp = to_dev(blob)
+    out = torch.zeros(n * chunk, dtype=torch.uint8, device="cuda")
+    idx = np.arange(n, dtype=np.uint64)
+    d_in = to_dev((np.uint64(comp.data_ptr()) + offs).astype(np.int64))
+    d_out = to_dev((np.uint64(out.data_ptr()) + idx * np.uint64(chunk)).astype(np.int64))
+    d_osz = to_dev(np.full(n, chunk, np.int64))
+    ws = torch.empty(codec.compress_temp_size(n), dtype=torch.uint8, device="cuda")     # compress workspace reused for decompress
+    # mixed: device pointer tables, HOST sizes (tests/test_nvcomp_batch.cu:132-134 mixes them too)
+    rc = codec.decompress_tables(d_in, sizes.astype(np.uint64), n, d_out, d_osz, ws)
+    assert rc == 0 and (d_osz.cpu().numpy() == chunk).all() and np.array_equal(out.cpu().numpy(), d)
+    for flavor in ("cuda_zstd", "nvcomp"):
+        s = pkg.ZstdSingle(3, flavor)
+        one = torch.zeros(chunk, dtype=torch.uint8, device="cuda")
+        w1 = torch.empty(s.compress_workspace(chunk), dtype=torch.uint8, device="cuda")
+        rc, got = s.decompress(comp.data_ptr() + int(offs[1]), int(sizes[1]), one, chunk, w1, w1.numel())
+        assert rc == 0 and got == chunk and np.array_equal(one.cpu().numpy(), d[chunk:2 * chunk])
+        rc, _ = s.decompress(None, 10, one, chunk, w1, w1.numel())
+        assert rc == 2                                     # null input -> ERROR_INVALID_PARAMETER
+        rc, _ = s.decompress(comp.data_ptr(), int(sizes[0]), one, 0, w1, w1.numel())
+        assert rc == 7                                     # zero capacity -> ERROR_BUFFER_TOO_SMALL
+        s.close()
