@@ -286,7 +286,7 @@ def main():
     t_caps = torch.full((n,), CHUNK, dtype=torch.int64, device=dev)
     t_out_sizes = t_caps.clone()
     t_status = torch.zeros(n, dtype=torch.int32, device=dev)
-    ws = torch.empty(max(codec.compress_temp_size(n), codec.decompress_temp_size(n)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(codec.compress_temp_size(n), codec.decompress_temp_size(n, sizes)), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
     def dec_step():
@@ -312,7 +312,7 @@ def main():
     for k in range(args.steps):
         dec_step()
         ev[k + 1].record(stream)
-        launches += 1
+        launches += codec.last_launch_count()
     barrier()
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
@@ -348,7 +348,7 @@ def main():
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
         e2e_step()
-        launches += 1
+        launches += codec.last_launch_count()
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
@@ -389,7 +389,7 @@ def main():
         c0.record(stream)
         for _ in range(csteps):
             off_tab = cmp_step()
-            launches += 2
+            launches += codec.last_launch_count() + 1
         c1.record(stream)
         barrier()
         cms = c0.elapsed_time(c1)

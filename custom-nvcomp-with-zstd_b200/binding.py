@@ -152,13 +152,16 @@ class ZstdBatchCodec:
     def max_compressed_size(self, n: int) -> int:
         return int(self.lib.cuda_zstd_batch_get_max_compressed_size(self.h, n))
 
-    def compress_temp_size(self, num_chunks: int) -> int:
-        sizes = np.zeros(max(num_chunks, 1), dtype=np.uint64)
-        return int(self.lib.cuda_zstd_batch_get_compress_temp_size(self.h, sizes.ctypes.data, num_chunks))
+    def compress_temp_size(self, num_chunks: int, sizes: Optional[np.ndarray] = None) -> int:
+        """`sizes`: host array of uncompressed chunk sizes (optional)."""
+        p = np.ascontiguousarray(sizes, dtype=np.uint64).ctypes.data if sizes is not None else None
+        return int(self.lib.cuda_zstd_batch_get_compress_temp_size(self.h, p, num_chunks))
 
-    def decompress_temp_size(self, num_chunks: int) -> int:
-        sizes = np.zeros(max(num_chunks, 1), dtype=np.uint64)
-        return int(self.lib.cuda_zstd_batch_get_decompress_temp_size(self.h, sizes.ctypes.data, num_chunks))
+    def decompress_temp_size(self, num_chunks: int, sizes: Optional[np.ndarray] = None) -> int:
+        """`sizes`: host array of COMPRESSED sizes; it sizes the fast path's literal/sequence pools
+        (without it 16 KB frames are assumed; a small workspace only routes more chunks to the slower kernel)."""
+        p = np.ascontiguousarray(sizes, dtype=np.uint64).ctypes.data if sizes is not None else None
+        return int(self.lib.cuda_zstd_batch_get_decompress_temp_size(self.h, p, num_chunks))
 
     # ---- raw pointer-table calls (tables: numpy uint64 on the host, or torch int64 on the device) ----
     def compress_tables(self, in_ptrs, in_sizes, n, out_ptrs, out_sizes, workspace: Optional[torch.Tensor], stream=None) -> int:
@@ -218,7 +221,7 @@ class ZstdBatchCodec:
         out_ptrs = out.data_ptr() + idx * np.uint64(chunk)
         out_sizes = np.full(n, chunk, dtype=np.uint64)
         if workspace is None:
-            workspace = torch.empty(self.decompress_temp_size(n), dtype=torch.uint8, device=comp.device)
+            workspace = torch.empty(self.decompress_temp_size(n, in_sizes), dtype=torch.uint8, device=comp.device)
         rc = self.decompress_tables(in_ptrs, in_sizes, n, out_ptrs, out_sizes, workspace)
         if rc != 0:
             raise RuntimeError(f"batch decompress failed: {self.lib.cuda_zstd_batch_error_string(rc).decode()}")

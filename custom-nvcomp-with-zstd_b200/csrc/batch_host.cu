@@ -236,15 +236,41 @@ public:
     return (int)std::min<size_t>(n, (size_t)sm_count * per);
   }
   static size_t table_bytes(size_t n) { return align_up(n * 40, 256); }
-  size_t dec_temp(size_t n) const {
-    if (n == 0) return 0;
-    // sized for a full grid so that one workspace serves any batch of up to n chunks
-    return b200zstd::WS_HEADER_BYTES + table_bytes(n) + (size_t)dec_grid(n) * b200zstd::LIT_SCRATCH_BYTES;
+  // decode workspace: header | staged tables | slow list | general-kernel literal scratch | fast-path slots
+  static size_t wave_of(size_t n) { return std::min<size_t>(n, b200zstd::FAST_WAVE); }
+  static size_t slow_list_bytes(size_t n) { return align_up(wave_of(n) * 4, 256); }
+  size_t general_scratch_bytes(size_t n) const { return align_up((size_t)dec_grid(n) * b200zstd::LIT_SCRATCH_BYTES, 256); }
+  size_t dec_fixed(size_t n) const {
+    return b200zstd::WS_HEADER_BYTES + table_bytes(n) + slow_list_bytes(n) + general_scratch_bytes(n) +
+           wave_of(n) * b200zstd::FAST_SLOT_BYTES;
   }
-  size_t enc_temp(size_t n) const {
+  // pools for one wave, sized from the compressed bytes of the largest wave: literals regenerate to at
+  // most ~2x their coded size on compressible data, and a sequence costs >= ~2.7 coded bytes (16-byte
+  // records).  Too small a pool is not an error: the overflow chunks take the general kernel.
+  static void pool_split(size_t pool_bytes, size_t *lit, size_t *seq) {
+    *lit = (pool_bytes / 4) & ~(size_t)255;
+    *seq = (pool_bytes - *lit) & ~(size_t)255;
+  }
+  static size_t pool_share(size_t compressed) { return std::min<size_t>(8 * compressed, 192 * 1024) + 3072; }
+  size_t dec_temp(size_t n, const size_t *sizes = nullptr) const {
+    if (n == 0) return 0;
+    size_t worst = 0;
+    if (sizes) {
+      for (size_t w0 = 0; w0 < n; w0 += b200zstd::FAST_WAVE) {
+        size_t s = 0;
+        for (size_t i = w0; i < std::min<size_t>(n, w0 + b200zstd::FAST_WAVE); ++i) s += pool_share(sizes[i]);
+        worst = std::max(worst, s);
+      }
+    } else worst = wave_of(n) * pool_share(16 * 1024);      // no sizes given: assume 16 KB frames
+    return dec_fixed(n) + align_up(worst, 256);
+  }
+  size_t enc_temp(size_t n, const size_t *sizes = nullptr) const {
     if (n == 0) return 0;
     size_t e = b200zstd::WS_HEADER_BYTES + table_bytes(n) + (size_t)enc_grid(n) * b200zstd::encode_cta_scratch_bytes(enc_params());
-    return std::max(e, dec_temp(n));      // a compress workspace can always be reused for decompress
+    // a compress workspace can always be reused for decompress (reference tests/test_c_api.cpp:62-64):
+    // the decoder needs dec_fixed(); pool space beyond that only decides how many chunks take the fast path
+    (void)sizes;
+    return std::max(e, dec_fixed(n) + wave_of(n) * (size_t)(64 * 1024));
   }
 
   // Direction-agnostic batch driver.  tables_on_device: the five tables already live in device
@@ -257,7 +283,7 @@ public:
     if (n == 0) return Status::SUCCESS;
     if (!in_ptrs || !in_sizes || !out_ptrs || !out_sizes) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null pointer table");
     if (n > 0xFFFFFFF0ull) return fail(Status::ERROR_INVALID_PARAMETER, fn, "too many chunks");
-    const size_t need = compress ? enc_temp(n) : dec_temp(n);
+    const size_t need = compress ? enc_temp(n) : dec_fixed(n);             // decode pools use whatever lies beyond the fixed part
     if (!ws) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null workspace");
     if (ws_bytes < need) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
     unsigned char *w = static_cast<unsigned char *>(ws);
@@ -288,14 +314,37 @@ public:
       a.in_ptrs = d_in; a.in_sizes = d_in_sz; a.out_ptrs = d_out; a.out_sizes = d_out_sz; a.statuses = d_status;
       a.counter = counter; a.scratch = scratch; a.n = (uint32_t)n; a.prm = enc_params();
       e = b200zstd::launch_encode_batch(a, enc_grid(n), stream);
+      last_launches = 1;
     } else {
-      b200zstd::DecodeArgs a{};
-      a.in_ptrs = d_in; a.in_sizes = d_in_sz; a.out_ptrs = d_out; a.out_sizes = d_out_sz; a.statuses = d_status;
-      a.counter = counter; a.lit_scratch = scratch; a.n = (uint32_t)n;
-      a.verify_checksum = cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY;   // reference gates on the manager's policy (manager.cu:3654)
-      e = b200zstd::launch_decode_batch(a, dec_grid(n), stream);
+      // fast path in waves of FAST_WAVE chunks (bounds the scratch); each wave is 4 launches:
+      // prep, entropy, execute, and the general kernel for whatever the fast path declined
+      unsigned char *slow_list = scratch;
+      unsigned char *gen_scratch = slow_list + slow_list_bytes(n);
+      unsigned char *slots = gen_scratch + general_scratch_bytes(n);
+      unsigned char *pools = slots + wave_of(n) * b200zstd::FAST_SLOT_BYTES;
+      size_t lit_pool = 0, seq_pool = 0;
+      pool_split(ws_bytes - (size_t)(pools - w), &lit_pool, &seq_pool);
+      e = cudaSuccess;
+      for (size_t w0 = 0; w0 < n && e == cudaSuccess; w0 += b200zstd::FAST_WAVE) {
+        const size_t m = std::min<size_t>(b200zstd::FAST_WAVE, n - w0);
+        b200zstd::FastDecodeArgs f{};
+        f.base.in_ptrs = d_in + w0; f.base.in_sizes = d_in_sz + w0; f.base.out_ptrs = d_out + w0; f.base.out_sizes = d_out_sz + w0;
+        f.base.statuses = d_status + w0; f.base.counter = counter; f.base.lit_scratch = gen_scratch; f.base.n = (uint32_t)m;
+        f.base.verify_checksum = cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY;   // reference gates on the manager's policy (manager.cu:3654)
+        f.slots = slots;
+        f.lit_pool = pools; f.lit_pool_bytes = lit_pool;
+        f.seq_pool = pools + lit_pool; f.seq_pool_bytes = seq_pool;
+        f.pool_heads = reinterpret_cast<unsigned long long *>(w + 128);
+        f.slow_list = reinterpret_cast<u32 *>(slow_list);
+        f.slow_count = counter + 16;
+        f.group_counters = counter + 48;
+        f.sm_count = sm_count;
+        f.general_grid = dec_grid(m);
+        int k = 0;
+        e = b200zstd::launch_decode_fast(f, stream, &k);
+        last_launches += k;
+      }
     }
-    last_launches = 1;
     if (e != cudaSuccess) return cuda_fail(e, fn);
     if (!sync) return Status::SUCCESS;
     // results back to the host: sizes (when the caller's table is host memory) and statuses
@@ -336,11 +385,11 @@ Status ZstdBatchManager::configure(const CompressionConfig &c) {
   return Status::SUCCESS;
 }
 CompressionConfig ZstdBatchManager::get_config() const { return pimpl_->cfg; }
-size_t ZstdBatchManager::get_compress_temp_size(size_t) const { return pimpl_->enc_temp(1); }
-size_t ZstdBatchManager::get_decompress_temp_size(size_t) const { return pimpl_->dec_temp(1); }
+size_t ZstdBatchManager::get_compress_temp_size(size_t n) const { return pimpl_->enc_temp(1, &n); }
+size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const { return pimpl_->dec_temp(1, &n); }
 size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
-size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size()); }
-size_t ZstdBatchManager::get_batch_decompress_temp_size(const std::vector<size_t> &v) const { return pimpl_->dec_temp(v.size()); }
+size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size(), v.data()); }
+size_t ZstdBatchManager::get_batch_decompress_temp_size(const std::vector<size_t> &v) const { return pimpl_->dec_temp(v.size(), v.data()); }
 Status ZstdBatchManager::set_dictionary(const dictionary::Dictionary &) { return Status::ERROR_NOT_IMPLEMENTED; }
 Status ZstdBatchManager::get_dictionary(dictionary::Dictionary &) const { return Status::ERROR_NOT_IMPLEMENTED; }
 Status ZstdBatchManager::clear_dictionary() { return Status::SUCCESS; }
@@ -460,7 +509,7 @@ Status ZstdBatchManager::decompress_async_no_sync(const void *src, size_t n, voi
   e = b200zstd::launch_decode_batch(a, 1, stream);
   return e == cudaSuccess ? Status::SUCCESS : cuda_fail(e, "decompress_async_no_sync");
 }
-size_t ZstdBatchManager::get_inference_workspace_size(size_t, size_t) const { return pimpl_->dec_temp(1); }
+size_t ZstdBatchManager::get_inference_workspace_size(size_t mc, size_t) const { return pimpl_->dec_temp(1, &mc); }
 Status ZstdBatchManager::allocate_inference_workspace(size_t mc, size_t mo, void **p, size_t *sz) {
   if (!p || !sz) return Status::ERROR_INVALID_PARAMETER;
   *sz = get_inference_workspace_size(mc, mo);
@@ -602,8 +651,8 @@ Status run_tables(ZstdBatchManager &m, bool compress, const void *const *in_ptrs
 NvcompV5BatchManager::NvcompV5BatchManager(const NvcompV5Options &o) : pimpl_(new Impl(o)) {}
 NvcompV5BatchManager::~NvcompV5BatchManager() = default;
 ZstdBatchManager &NvcompV5BatchManager::batch_manager() { return pimpl_->mgr; }
-size_t NvcompV5BatchManager::get_compress_temp_size(const size_t *, size_t n, cudaStream_t) const { return pimpl_->mgr.impl()->enc_temp(n); }
-size_t NvcompV5BatchManager::get_decompress_temp_size(const size_t *, size_t n, cudaStream_t) const { return pimpl_->mgr.impl()->dec_temp(n); }
+size_t NvcompV5BatchManager::get_compress_temp_size(const size_t *s, size_t n, cudaStream_t) const { return pimpl_->mgr.impl()->enc_temp(n, s); }
+size_t NvcompV5BatchManager::get_decompress_temp_size(const size_t *s, size_t n, cudaStream_t) const { return pimpl_->mgr.impl()->dec_temp(n, s); }
 size_t NvcompV5BatchManager::get_max_compressed_chunk_size(size_t n) const { return pimpl_->mgr.get_max_compressed_size(n); }
 Status NvcompV5BatchManager::compress_async(const void *const *in, const size_t *in_sz, size_t n, void *const *out, size_t *out_sz,
                                             void *tmp, size_t tmp_bytes, cudaStream_t stream) {

@@ -63,9 +63,10 @@ __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
 // over-read (checked by the caller).
 // ---------------------------------------------------------------------------------------------
 struct BackBits {
-  const uint32_t *wp;     // next (lower) word to fetch
+  const uint32_t *wp;     // address of `nextw` (the next word to enter the window)
   const uint32_t *floor;  // lowest word that may be fetched
   uint64_t win;           // unread bits, MSB-aligned
+  uint32_t nextw;         // prefetched: loaded one refill ahead so its latency is off the critical path
   int avail;              // valid bits in win
   int left;               // payload bits not yet consumed
 
@@ -82,6 +83,7 @@ struct BackBits {
     int skip = 8 - highbit32(last);                    // zero padding + sentinel
     floor = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
     wp = wa - 1;
+    nextw = (wp >= floor) ? *wp : 0u;
     win = ((uint64_t)w << 32) << skip;
     avail = (int)(8 * vb) - skip;
     left = (int)(8 * n) - skip;
@@ -89,10 +91,10 @@ struct BackBits {
   }
   __device__ __forceinline__ void refill() {
     if (avail <= 32) {
-      uint32_t w = (wp >= floor) ? *wp : 0u;
-      wp--;
-      win |= (uint64_t)w << (32 - avail);
+      win |= (uint64_t)nextw << (32 - avail);
       avail += 32;
+      wp--;
+      nextw = (wp >= floor) ? *wp : 0u;
     }
   }
   __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)((win >> 1) >> (63 - n)); }   // n in [0,32]

@@ -1,0 +1,759 @@
+// zstd_decode_fast.cu -- batch fast path of the Zstandard decoder for sm_100a.
+//
+// The general decoder (zstd_decode.cu) keeps one chunk per CTA and is bound by the single lane that
+// walks the FSE sequence bitstream (ncu, profiles/r1_decode_general.md).  The serial parts of
+// Zstandard -- one Huffman stream, one interleaved FSE sequence stream -- cannot be split, but a batch
+// has tens of thousands of them.  The fast path therefore runs every serial stream of the WHOLE BATCH
+// as its own thread, and only the embarrassingly parallel parts per warp:
+//
+//   KA literals   persistent CTAs, 48 chunks at a time: one warp per chunk parses the frame / block /
+//                 section headers and builds the Huffman DTable in SHARED memory, then one THREAD per
+//                 Huffman stream (192 per CTA) decodes against those tables
+//   KB sequences  persistent CTAs, 20 chunks at a time: one warp per chunk reads the three FSE table
+//                 descriptions and builds the decode tables in SHARED memory, then one LANE per chunk
+//                 walks its interleaved sequence bitstream and emits 16-byte records
+//   (a first version kept the tables in global memory: every lookup missed L2 -- 7.8 GB of DRAM reads
+//   per GiB decoded, ncu profiles/r1_fast_entropy_global_tables.md -- hence shared memory)
+//   KC execute    one warp per chunk, one LANE per sequence: literal runs and every match whose source
+//               lies before the current group of 32 sequences are copied concurrently; the few
+//               matches that depend on the group itself are replayed in order by the whole warp
+//
+// It handles the batch case: a chunk that is exactly one frame with one block (what libzstd and this
+// library's compressor emit for <= 128 KB chunks).  Anything else (several blocks or frames, skippable
+// frames, more than FAST_SEQ_CAP sequences) is appended to a device-side list and decoded by the
+// general kernel in the same call.  Same reference functions replaced as zstd_decode.cu.
+#include "zstd_common.cuh"
+#include "zstd_decode_tables.cuh"
+#include "zstd_device_api.h"
+
+namespace b200zstd {
+
+struct __align__(16) FastDesc {
+  uint32_t state;        // 0 fast path continues, 1 finished in prep, 2 routed to the general kernel
+  uint32_t status;
+  uint32_t content;      // frame content size, 0xFFFFFFFF when the header has none
+  uint32_t cap;          // output capacity (clamped to 32 bits)
+  uint32_t lit_type;     // 0 raw, 1 rle, 2 huffman
+  uint32_t lit_size;
+  uint32_t lit_src;      // raw / rle literals: offset of the bytes inside the frame
+  uint32_t n_streams;    // huffman streams: 0, 1 or 4
+  uint32_t huf_log;
+  uint32_t seg;          // literals decoded by each of the first three streams
+  uint32_t st_off[4];
+  uint32_t st_len[4];
+  uint32_t nseq;
+  uint32_t bits_off, bits_len;
+  uint32_t ll_log, of_log, ml_log;
+  uint32_t ck_off;       // offset of the 4-byte content checksum, 0 = none
+  uint32_t tab_off;      // offset of the first FSE table description
+  uint32_t blk_end;      // offset one past the block
+  uint32_t modes;        // symbol compression modes byte
+  uint32_t seq_status, out_end, lit_end;      // written by the sequence thread
+  uint32_t lit_status[4];                     // written by the Huffman threads
+  uint32_t lit_slot, seq_slot;                // pool offsets in 16-byte units
+};
+static_assert(sizeof(FastDesc) <= FAST_DESC_BYTES, "descriptor slot too small");
+
+struct ChunkSlot {
+  uint8_t *base, *lit_pool, *seq_pool;
+  __device__ __forceinline__ FastDesc *desc() const { return reinterpret_cast<FastDesc *>(base); }
+  __device__ __forceinline__ uint16_t *huf() const { return reinterpret_cast<uint16_t *>(base + FAST_DESC_BYTES); }
+  __device__ __forceinline__ uint2 *ll() const { return reinterpret_cast<uint2 *>(base + FAST_DESC_BYTES + 4096); }
+  __device__ __forceinline__ uint2 *ml() const { return reinterpret_cast<uint2 *>(base + FAST_DESC_BYTES + 8192); }
+  __device__ __forceinline__ uint2 *of() const { return reinterpret_cast<uint2 *>(base + FAST_DESC_BYTES + 12288); }
+  __device__ __forceinline__ uint8_t *lits() const { return lit_pool + (size_t)desc()->lit_slot * 16; }
+  __device__ __forceinline__ uint4 *seqs() const { return reinterpret_cast<uint4 *>(seq_pool + (size_t)desc()->seq_slot * 16); }
+};
+__device__ __forceinline__ ChunkSlot slot_of(const FastDecodeArgs &F, uint32_t chunk) {
+  return ChunkSlot{F.slots + (size_t)chunk * FAST_SLOT_BYTES, F.lit_pool, F.seq_pool};
+}
+__device__ __forceinline__ uint32_t seg_padded(uint32_t seg) { return (seg + 15u) & ~15u; }
+
+// =================================================================================================
+// KA: headers + Huffman tables (one warp per chunk), then one thread per Huffman stream
+// =================================================================================================
+constexpr int KA_THREADS = 256, KA_WARPS = KA_THREADS / 32;
+constexpr int KA_GROUP = 48;                                   // chunks per CTA pass: 48 x 4 KB of tables
+struct __align__(16) HufScratch {                              // per-warp scratch of huf_read_table_warp
+  uint16_t *huf;                                               // -> this chunk's table in shared memory
+  uint8_t weights[256];
+  uint32_t huf_ft[64];
+  int16_t huf_norm[16];
+  uint32_t rank_cnt[16];
+  uint32_t rank_start[16];
+  int huf_log, huf_valid;
+};
+constexpr size_t KA_SMEM = (size_t)KA_GROUP * 4096 + KA_WARPS * sizeof(HufScratch) + 16;
+
+__device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
+                                                    uint32_t k, uint32_t *status_out);
+
+__global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArgs F) {
+  extern __shared__ __align__(16) uint8_t ka_smem[];
+  __shared__ uint32_t s_group;
+  uint16_t *const tables = reinterpret_cast<uint16_t *>(ka_smem);
+  HufScratch *const scratch = reinterpret_cast<HufScratch *>(ka_smem + (size_t)KA_GROUP * 4096);
+  const DecodeArgs &A = F.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  HufScratch &S = scratch[warp];
+  for (;;) {
+    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 0, 1u);
+    __syncthreads();
+    const uint32_t g0 = s_group * KA_GROUP;
+    if (g0 >= A.n) break;
+    // ---------------- phase 1: one warp per chunk ----------------
+   for (uint32_t c = warp; c < KA_GROUP && g0 + c < A.n; c += KA_WARPS) {
+    const uint32_t chunk = g0 + c;
+    if (lane == 0) S.huf = tables + (size_t)c * 2048;
+    __syncwarp();
+    const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
+    const size_t src_size = A.in_sizes[chunk];
+    uint8_t *const dst = (uint8_t *)A.out_ptrs[chunk];
+    const size_t dst_cap = A.out_sizes[chunk];
+    ChunkSlot slot = slot_of(F, chunk);
+    FastDesc D{};
+    uint32_t status = ST_OK;
+    bool route = false, finished = false;
+    uint32_t produced = 0;
+    __syncwarp();
+    do {
+      if (src == nullptr || (dst == nullptr && dst_cap != 0) || src_size < 4) { status = ST_INVALID_PARAMETER; break; }
+      const uint32_t magic = ld_le32(src);
+      if ((magic & 0xFFFFFFF0u) == ZSTD_SKIP_MAGIC) { route = true; break; }
+      if (magic != ZSTD_FRAME_MAGIC) { status = ST_INVALID_MAGIC; break; }
+      if (src_size > 0x7FFFFFFFull) { route = true; break; }
+      const uint32_t n = (uint32_t)src_size;
+      uint32_t h = 4;
+      if (h >= n) { status = ST_CORRUPT; break; }
+      const uint32_t fhd = src[h++];
+      const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_ck = (fhd >> 2) & 1, did_flag = fhd & 3;
+      if (fhd & 0x08) { status = ST_UNSUPPORTED; break; }
+      const uint32_t did_size = did_flag == 3 ? 4 : did_flag, fcs_size = fcs_flag == 0 ? single : (1u << fcs_flag);
+      if (h + (single ? 0 : 1) + did_size + fcs_size > n) { status = ST_CORRUPT; break; }
+      if (!single) { if ((src[h++] >> 3) > 21) { status = ST_UNSUPPORTED; break; } }
+      uint32_t dict_id = 0;
+      for (uint32_t k = 0; k < did_size; k++) dict_id |= (uint32_t)src[h + k] << (8 * k);
+      h += did_size;
+      uint64_t fcs = ~0ull;
+      if (fcs_size) {
+        fcs = 0;
+        for (uint32_t k = 0; k < fcs_size; k++) fcs |= (uint64_t)src[h + k] << (8 * k);
+        if (fcs_size == 2) fcs += 256;
+        h += fcs_size;
+      }
+      if (dict_id != 0) { status = ST_DICT_MISMATCH; break; }
+      if (fcs != ~0ull && fcs > dst_cap) { status = ST_BUFFER_TOO_SMALL; break; }
+      const uint32_t cap = dst_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)dst_cap;
+      // ---- the single block ----
+      if (n - h < 3) { status = ST_CORRUPT; break; }
+      const uint32_t bh = ld_le24(src + h);
+      h += 3;
+      const int last = bh & 1, btype = (bh >> 1) & 3;
+      const uint32_t bsize = bh >> 3;
+      if (btype == 3 || bsize > BLOCK_MAX) { status = ST_CORRUPT; break; }
+      const uint32_t body = (btype == 1) ? 1u : bsize;
+      if (body > n - h) { status = ST_CORRUPT; break; }
+      if (!last) { route = true; break; }
+      const uint32_t after = h + body;
+      if (has_ck && n - after < 4) { status = ST_CORRUPT; break; }
+      if (after + (has_ck ? 4u : 0u) != n) { route = true; break; }          // more frames follow
+      const uint32_t ck_off = has_ck ? after : 0;
+      if (btype == 0 || btype == 1) {
+        if (bsize > cap) { status = ST_BUFFER_TOO_SMALL; break; }
+        if (fcs != ~0ull && fcs != bsize) { status = ST_CORRUPT; break; }
+        if (btype == 0) for (uint32_t k = lane; k < bsize; k += 32) dst[k] = src[h + k];
+        else { const uint8_t v = src[h]; for (uint32_t k = lane; k < bsize; k += 32) dst[k] = v; }
+        __syncwarp();
+        if (has_ck && A.verify_checksum) {
+          const uint64_t hs = xxh64_warp(dst, bsize, lane);
+          if ((uint32_t)hs != ld_le32(src + ck_off)) { status = ST_CHECKSUM; break; }
+        }
+        produced = bsize;
+        finished = true;
+        break;
+      }
+      if (bsize < 2) { status = ST_CORRUPT; break; }
+      const uint8_t *const bp = src + h;
+      // -- literals section header --
+      const uint32_t b0 = bp[0];
+      const int ltype = b0 & 3, sf = (b0 >> 2) & 3;
+      uint32_t lit_size, lit_comp = 0, lhs, nstreams = 1;
+      if (ltype < 2) {
+        lhs = (sf == 1) ? 2 : (sf == 3) ? 3 : 1;
+        if (bsize < lhs) { status = ST_CORRUPT; break; }
+        lit_size = (lhs == 1) ? (b0 >> 3) : (lhs == 2) ? ((b0 >> 4) | ((uint32_t)bp[1] << 4))
+                                                       : ((b0 >> 4) | ((uint32_t)bp[1] << 4) | ((uint32_t)bp[2] << 12));
+        lit_comp = (ltype == 0) ? lit_size : 1;
+      } else {
+        lhs = (sf < 2) ? 3 : (sf == 2) ? 4 : 5;
+        nstreams = (sf == 0) ? 1 : 4;
+        if (bsize < lhs) { status = ST_CORRUPT; break; }
+        if (sf < 2) { lit_size = (b0 >> 4) | (((uint32_t)bp[1] & 0x3F) << 4); lit_comp = ((uint32_t)bp[1] >> 6) | ((uint32_t)bp[2] << 2); }
+        else if (sf == 2) { lit_size = (b0 >> 4) | ((uint32_t)bp[1] << 4) | (((uint32_t)bp[2] & 3) << 12); lit_comp = ((uint32_t)bp[2] >> 2) | ((uint32_t)bp[3] << 6); }
+        else { lit_size = (b0 >> 4) | ((uint32_t)bp[1] << 4) | (((uint32_t)bp[2] & 0x3F) << 12); lit_comp = ((uint32_t)bp[2] >> 6) | ((uint32_t)bp[3] << 2) | ((uint32_t)bp[4] << 10); }
+      }
+      if (lit_size > BLOCK_MAX || lhs + lit_comp > bsize) { status = ST_CORRUPT; break; }
+      // -- sequences section header --
+      uint32_t sp = lhs + lit_comp;
+      if (sp >= bsize) { status = ST_CORRUPT; break; }
+      uint32_t nseq;
+      {
+        const uint32_t s0 = bp[sp];
+        if (s0 < 128) { nseq = s0; sp += 1; }
+        else if (s0 < 255) { if (sp + 2 > bsize) { status = ST_CORRUPT; break; } nseq = ((s0 - 128) << 8) + bp[sp + 1]; sp += 2; }
+        else { if (sp + 3 > bsize) { status = ST_CORRUPT; break; } nseq = (uint32_t)bp[sp + 1] + ((uint32_t)bp[sp + 2] << 8) + 0x7F00; sp += 3; }
+      }
+      uint32_t modes = 0;
+      if (nseq) {
+        if (sp >= bsize) { status = ST_CORRUPT; break; }
+        modes = bp[sp++];
+        if (modes & 3) { status = ST_CORRUPT; break; }
+      } else if (sp != bsize) { status = ST_CORRUPT; break; }
+      if (nseq > FAST_SEQ_CAP) { route = true; break; }
+      D.content = fcs == ~0ull ? 0xFFFFFFFFu : (uint32_t)fcs;
+      D.cap = cap;
+      D.lit_type = ltype >= 2 ? 2u : (uint32_t)ltype;
+      D.lit_size = lit_size;
+      D.lit_src = h + lhs;
+      D.nseq = nseq;
+      D.ck_off = ck_off;
+      // -- Huffman table + stream layout --
+      if (ltype == 3) { status = ST_CORRUPT; break; }                         // treeless needs a previous block
+      if (ltype == 2) {
+        const uint8_t *hp = bp + lhs;
+        uint32_t rem = lit_comp;
+        const int used = huf_read_table_warp(S, hp, rem, lane);
+        if (used < 0) { status = ST_CORRUPT; break; }
+        hp += used; rem -= (uint32_t)used;
+        const uint32_t hoff = h + lhs + (uint32_t)used;
+        D.huf_log = (uint32_t)S.huf_log;
+        D.n_streams = nstreams;
+        if (nstreams == 1) { D.seg = lit_size; D.st_off[0] = hoff; D.st_len[0] = rem; }
+        else {
+          const uint32_t seg = (lit_size + 3) >> 2;
+          if (rem < 6 || seg * 3 > lit_size) { status = ST_CORRUPT; break; }
+          const uint32_t s1 = ld_le16(hp), s2 = ld_le16(hp + 2), s3 = ld_le16(hp + 4);
+          if (6 + s1 + s2 + s3 > rem) { status = ST_CORRUPT; break; }
+          D.seg = seg;
+          D.st_off[0] = hoff + 6; D.st_len[0] = s1;
+          D.st_off[1] = hoff + 6 + s1; D.st_len[1] = s2;
+          D.st_off[2] = hoff + 6 + s1 + s2; D.st_len[2] = s3;
+          D.st_off[3] = hoff + 6 + s1 + s2 + s3; D.st_len[3] = rem - 6 - s1 - s2 - s3;
+        }
+      }
+      // -- FSE tables are built by KB; remember where their descriptions start --
+      D.tab_off = h + sp; D.blk_end = h + bsize; D.modes = modes;
+    } while (false);
+    __syncwarp();
+    if (lane == 0 && !route && !finished && status == ST_OK) {
+      // bump-allocate this chunk's literal and sequence storage; pool exhaustion -> general kernel
+      const unsigned long long lit_need = D.lit_type == 2 ? (unsigned long long)4 * seg_padded(D.seg ? D.seg : 1) : 0ull;
+      const unsigned long long seq_need = (unsigned long long)(D.nseq + 1) * 16;
+      const unsigned long long lo = atomicAdd(&F.pool_heads[0], lit_need), so = atomicAdd(&F.pool_heads[1], seq_need);
+      if (lo + lit_need > F.lit_pool_bytes || so + seq_need > F.seq_pool_bytes) route = true;
+      D.lit_slot = (uint32_t)(lo >> 4); D.seq_slot = (uint32_t)(so >> 4);
+    }
+    route = __shfl_sync(0xffffffffu, route ? 1 : 0, 0) != 0;
+    if (lane == 0) {
+      if (route) {
+        D.state = 2;
+        F.slow_list[atomicAdd(F.slow_count, 1u)] = chunk;
+      } else if (status != ST_OK || finished) {
+        D.state = 1;
+        A.out_sizes[chunk] = status == ST_OK ? produced : 0;
+        if (A.statuses) A.statuses[chunk] = status;
+      } else D.state = 0;
+      D.status = status;
+      *slot.desc() = D;
+    }
+    __syncwarp();
+   }
+    __threadfence_block();
+    __syncthreads();
+    // ---------------- phase 2: one thread per Huffman stream ----------------
+    if (threadIdx.x < 4 * KA_GROUP) {
+      const uint32_t c = threadIdx.x >> 2, chunk = g0 + c;
+      if (chunk < A.n) {
+        ChunkSlot slot = slot_of(F, chunk);
+        FastDesc *D = slot.desc();
+        if (D->state == 0 && (threadIdx.x & 3) < D->n_streams)
+          fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, threadIdx.x & 3,
+                              &D->lit_status[threadIdx.x & 3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =================================================================================================
+// Huffman stream decode (one thread), table in shared memory
+// =================================================================================================
+__device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
+                                                    uint32_t k, uint32_t *status_out) {
+  const uint32_t seg = D->seg, lit_size = D->lit_size;
+  const uint32_t count = (D->n_streams == 1) ? lit_size : (k < 3 ? seg : lit_size - 3 * seg);
+  uint8_t *dst = lits + (size_t)k * seg_padded(seg);                          // 16-byte aligned segment
+  const int sh = 64 - (int)D->huf_log;
+  BackBits b;
+  bool ok = b.init(src + D->st_off[k], D->st_len[k]);
+  if (ok) {
+    uint32_t i = 0;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    for (; i + 4 <= count; i += 4) {                                          // 4 symbols -> one aligned 32-bit store
+      b.refill();
+      const uint32_t e0 = tab[b.win >> sh]; b.skip((int)(e0 >> 8));
+      const uint32_t e1 = tab[b.win >> sh]; b.skip((int)(e1 >> 8));
+      b.refill();
+      const uint32_t e2 = tab[b.win >> sh]; b.skip((int)(e2 >> 8));
+      const uint32_t e3 = tab[b.win >> sh]; b.skip((int)(e3 >> 8));
+      d32[i >> 2] = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | (e3 << 24);
+    }
+    for (; i < count; i++) {
+      b.refill();
+      const uint32_t e = tab[b.win >> sh];
+      b.skip((int)(e >> 8));
+      dst[i] = (uint8_t)e;
+    }
+    ok = b.left == 0;
+  }
+  *status_out = ok ? ST_OK : ST_CORRUPT;
+}
+
+// =================================================================================================
+// KB: FSE tables in shared memory (one warp per chunk), then one lane per sequence stream
+// =================================================================================================
+constexpr int KB_THREADS = 256, KB_WARPS = KB_THREADS / 32;
+constexpr int KB_GROUP = 40;                                   // chunks per CTA pass: 40 x 5 KB of packed tables
+constexpr int KB_DEC_WARPS = 2, KB_LANES = KB_GROUP / KB_DEC_WARPS;   // 2 decoding warps x 20 lanes
+struct __align__(16) SeqScratch {                              // per-warp scratch for the table build
+  int16_t norm[3][64];
+  uint8_t item_sym[512];
+  uint16_t sym_next[64];
+  int tab_log[3], tab_max[3], tab_mode[3];
+  uint32_t bits_off, ok;
+};
+struct SeqInfo { uint32_t ready, ll_log, of_log, ml_log, bits_off, bits_len; };
+constexpr size_t KB_TAB_BYTES = 1280 * 4;                      // LL 512 | ML 512 | OF 256 packed 32-bit entries
+constexpr size_t KB_SMEM = (size_t)KB_GROUP * KB_TAB_BYTES + KB_WARPS * sizeof(SeqScratch) + KB_GROUP * sizeof(SeqInfo) + 96 * 4 + 16;
+
+// packed decode entry: nextStateBase[0:10) | nbBits[10:14) | extraBits[14:19) | symbol[19:25)
+// (the base VALUE of a length code is recomputed from the symbol: it only feeds the output record,
+// not the bit-position chain, and this halves the table so twice as many chunks fit in shared memory)
+__device__ __forceinline__ uint32_t pack_entry(int kind, uint32_t sym, uint32_t next_base, uint32_t nb) {
+  const uint32_t xb = kind == 0 ? c_ll_bits[sym] : kind == 1 ? sym : c_ml_bits[sym];
+  return next_base | (nb << 10) | (xb << 14) | (sym << 19);
+}
+// fse_build_warp (zstd_decode_tables.cuh) emitting packed entries in place
+__device__ inline void fse_build_warp_packed(uint32_t *tab, const int16_t *norm, int max_sym, int log, int kind, uint8_t *item_sym,
+                                             uint16_t *sym_next, int lane) {
+  const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+  int high = size - 1, acc = 0;
+  for (int s = 0; s <= max_sym; s++) {
+    const int c = norm[s];
+    if (c == -1) { if (lane == 0) { tab[high] = (uint32_t)s; sym_next[s] = 1; } high--; }
+    else {
+      if (lane == 0) sym_next[s] = (uint16_t)c;
+      for (int k = lane; k < c; k += 32) item_sym[acc + k] = (uint8_t)s;
+      acc += c;
+    }
+  }
+  __syncwarp();
+  int run = 0;
+  for (int j0 = 0; j0 < size; j0 += 32) {
+    const int pos = ((j0 + lane) * step) & mask;
+    const bool ok = pos <= high;
+    const uint32_t b = __ballot_sync(0xffffffffu, ok);
+    if (ok) tab[pos] = item_sym[run + __popc(b & lanemask_lt())];
+    run += __popc(b);
+  }
+  __syncwarp();
+  for (int u0 = 0; u0 < size; u0 += 32) {
+    const int u = u0 + lane;
+    const uint32_t s = tab[u];
+    const uint32_t m = __match_any_sync(0xffffffffu, s);
+    const uint32_t x = (uint32_t)sym_next[s] + __popc(m & lanemask_lt());
+    __syncwarp();
+    if ((m >> lane) == 1u) sym_next[s] = (uint16_t)((uint32_t)sym_next[s] + __popc(m));
+    __syncwarp();
+    const uint32_t nb = (uint32_t)(log - highbit32(x));
+    tab[u] = pack_entry(kind, s, (x << nb) - (uint32_t)size, nb);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ uint32_t ll_base_of(uint32_t c) {
+  return c < 16 ? c : c < 20 ? 16 + 2 * (c - 16) : c < 22 ? 24 + 4 * (c - 20) : c < 24 ? 32 + 8 * (c - 22) : c == 24 ? 48u : 1u << (c - 19);
+}
+__device__ __forceinline__ uint32_t ml_base_of(uint32_t c) {
+  return c < 32 ? c + 3 : c < 36 ? 35 + 2 * (c - 32) : c < 38 ? 43 + 4 * (c - 36) : c < 40 ? 51 + 8 * (c - 38)
+                                                   : c < 42 ? 67 + 16 * (c - 40) : c == 42 ? 99u : (1u << (c - 36)) + 3;
+}
+
+// One lane walks one interleaved sequence stream.  A single in-order warp runs this loop, so its cost
+// is (instructions on the path) x (issue latency): the body is written branch-free where it can be --
+// fields are cut out of the top 32 bits of the window with 32-bit shifts, base values come from a
+// 96-entry shared table, validation accumulates into one flag (a bad stream keeps decoding harmlessly;
+// KC never executes a chunk whose seq_status is set), and bit accounting happens once at the end.
+struct SeqBits {                       // backward reader specialised for the sequence loop (see BackBits)
+  const uint32_t *wp, *floor;
+  uint64_t win;
+  uint32_t nextw;
+  int avail;
+  __device__ __forceinline__ void refill() {
+    if (avail <= 32) {
+      win |= (uint64_t)nextw << (32 - avail);
+      avail += 32;
+      wp--;
+      nextw = (wp >= floor) ? *wp : 0u;
+    }
+  }
+};
+__device__ __forceinline__ uint32_t top_bits(uint32_t hi, int skip, int n) { return ((hi << skip) >> 1) >> (31 - n); }   // n in [0,31]
+
+__device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const uint32_t *llt, const uint32_t *oft,
+                                                      const uint32_t *mlt, const uint32_t *bases, const SeqInfo &I) {
+  const uint32_t nseq = D->nseq, cap = D->cap, lit_size = D->lit_size;
+  uint32_t out_pos = 0, lit_pos = 0, err = ST_OK;
+  BackBits b0;
+  if (!b0.init(src + I.bits_off, I.bits_len)) err = ST_CORRUPT;
+  else {
+    b0.refill();
+    uint32_t sl = b0.read((int)I.ll_log), so = b0.read((int)I.of_log);
+    b0.refill();
+    uint32_t sm = b0.read((int)I.ml_log);
+    SeqBits b{b0.wp, b0.floor, b0.win, b0.nextw, b0.avail};
+    const uint32_t *const wp0 = b0.wp;                                             // for the final bit accounting
+    const int avail0 = b0.avail;
+    uint32_t rep0 = 1, rep1 = 4, rep2 = 8, bad = 0, big = 0;
+    const uint32_t *line_mark = b.wp;
+    for (uint32_t i = 0; i < nseq; i++) {
+      const uint32_t eo = oft[so], em = mlt[sm], el = llt[sl];
+      // lanes of a warp stall together: pull the next cache line of this lane's bitstream long before its words are needed
+      if (b.wp <= line_mark) {
+        line_mark = b.wp - 32;
+        if (line_mark >= b.floor) asm volatile("prefetch.global.L1 [%0];" ::"l"(line_mark));
+      }
+      b.refill();
+      const int ob = (int)((eo >> 14) & 31), mb = (int)((em >> 14) & 31), lb = (int)((el >> 14) & 31);
+      const int xb = ob + mb + lb;
+      uint32_t ov, mx, lx;
+      if (xb <= 31) {                                   // the usual case: all extra bits are in the top word
+        const uint32_t hi = (uint32_t)(b.win >> 32);
+        ov = top_bits(hi, 0, ob); mx = top_bits(hi, ob, mb); lx = top_bits(hi, ob + mb, lb);
+        b.win <<= xb; b.avail -= xb;
+      } else {
+        ov = (uint32_t)((b.win >> 1) >> (63 - ob)); b.win <<= ob; b.avail -= ob;
+        b.refill();
+        const uint32_t hi = (uint32_t)(b.win >> 32);
+        mx = top_bits(hi, 0, mb); lx = top_bits(hi, mb, lb);
+        b.win <<= (mb + lb); b.avail -= mb + lb;
+      }
+      b.refill();
+      {
+        const int nl = (int)((el >> 10) & 15), nm = (int)((em >> 10) & 15), no = (int)((eo >> 10) & 15);   // <= 26 bits together
+        const uint32_t hi = (uint32_t)(b.win >> 32);
+        const uint32_t last = (i + 1 == nseq) ? 0u : ~0u;                                                     // no state update after the last sequence
+        sl = (el & 1023) + (top_bits(hi, 0, nl) & last);
+        sm = (em & 1023) + (top_bits(hi, nl, nm) & last);
+        so = (eo & 1023) + (top_bits(hi, nl + nm, no) & last);
+        const int ns = (nl + nm + no) & (int)last;
+        b.win <<= ns; b.avail -= ns;
+      }
+      // ---- off the chain: values, repeat offsets, positions ----
+      ov += 1u << ob;
+      const uint32_t ll = bases[el >> 19] + lx, ml = bases[40 + (em >> 19)] + mx;
+      uint32_t offset;
+      if (ov > 3) { offset = ov - 3; rep2 = rep1; rep1 = rep0; rep0 = offset; }
+      else {
+        const uint32_t idx = ov - 1 + (ll == 0);
+        const uint32_t cand = idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
+        if (idx != 0) { if (idx != 1) rep2 = rep1; rep1 = rep0; rep0 = cand; }
+        offset = cand;
+      }
+      bad |= (offset == 0) | (lit_pos + ll > lit_size) | (offset > out_pos + ll);
+      __stcs(out + i, make_uint4(out_pos, lit_pos, offset, ml));
+      out_pos += ll + ml; lit_pos += ll;
+      big |= out_pos > cap;
+      // positions stay bounded even on garbage: a set flag stops KC from using them, and they cannot wrap within 65536 sequences
+    }
+    // bit accounting: consumed = bits that entered the window - bits still in it
+    const int entered = avail0 + 32 * (int)(wp0 - b.wp);
+    if (entered - b.avail != b0.left) bad |= 1;          // the stream must end exactly (b0.left = payload bits after the initial states)
+    if (bad) err = ST_CORRUPT; else if (big) err = ST_BUFFER_TOO_SMALL;
+  }
+  out[nseq] = make_uint4(out_pos, lit_pos, 0, 0);           // sentinel: literal length of the last sequence, block totals
+  D->seq_status = err; D->out_end = out_pos; D->lit_end = lit_pos;
+}
+
+__global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArgs F) {
+  extern __shared__ __align__(16) uint8_t kb_smem[];
+  __shared__ uint32_t s_group;
+  uint32_t *const tables = reinterpret_cast<uint32_t *>(kb_smem);                            // [KB_GROUP][1280]: LL 512 | ML 512 | OF 256
+  SeqScratch *const scratch = reinterpret_cast<SeqScratch *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES);
+  SeqInfo *const info = reinterpret_cast<SeqInfo *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES + KB_WARPS * sizeof(SeqScratch));
+  uint32_t *const bases = reinterpret_cast<uint32_t *>(info + KB_GROUP);                      // [0,36) LL bases, [40,93) ML bases
+  const DecodeArgs &A = F.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SeqScratch &S = scratch[warp];
+  if (threadIdx.x < 36) bases[threadIdx.x] = c_ll_base[threadIdx.x];
+  if (threadIdx.x >= 40 && threadIdx.x < 93) bases[threadIdx.x] = c_ml_base[threadIdx.x - 40];
+  for (;;) {
+    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 1, 1u);
+    __syncthreads();
+    const uint32_t g0 = s_group * KB_GROUP;
+    if (g0 >= A.n) break;
+    // ---------------- phase 1: table descriptions -> decode tables in shared memory ----------------
+    for (uint32_t c = warp; c < KB_GROUP && g0 + c < A.n; c += KB_WARPS) {
+      const uint32_t chunk = g0 + c;
+      ChunkSlot slot = slot_of(F, chunk);
+      FastDesc *D = slot.desc();
+      uint32_t *llt = tables + (size_t)c * 1280, *mlt = llt + 512, *oft = llt + 1024;
+      if (lane == 0) info[c].ready = 0;
+      if (D->state != 0) continue;                                                            // uniform per warp
+      const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
+      const uint32_t nseq = D->nseq;
+      if (nseq == 0) {
+        if (lane == 0) { slot.seqs()[0] = make_uint4(0, 0, 0, 0); D->seq_status = ST_OK; D->out_end = 0; D->lit_end = 0; }
+        continue;
+      }
+      const uint8_t *const bp = src + D->tab_off;
+      const uint32_t room = D->blk_end - D->tab_off, modes = D->modes;
+      if (lane == 0) {
+        uint32_t p = 0;
+        bool ok = true;
+        for (int t = 0; t < 3 && ok; t++) {                                                   // stream order: LL, OF, ML
+          const int mode = (modes >> (6 - 2 * t)) & 3;
+          const int max_allowed = (t == 0) ? LL_MAX_SYM : (t == 1) ? OF_MAX_SYM : ML_MAX_SYM;
+          S.tab_mode[t] = mode;
+          if (mode == 0) {
+            const int16_t *def = (t == 0) ? c_ll_def : (t == 1) ? c_of_def : c_ml_def;
+            const int dmax = (t == 0) ? 35 : (t == 1) ? 28 : 52;
+            for (int i = 0; i <= dmax; i++) S.norm[t][i] = def[i];
+            S.tab_max[t] = dmax; S.tab_log[t] = (t == 1) ? OF_DEF_LOG : LL_DEF_LOG;
+          } else if (mode == 1) {
+            if (p >= room || bp[p] > max_allowed) { ok = false; break; }
+            S.tab_max[t] = bp[p]; S.tab_log[t] = 0;
+            p += 1;
+          } else if (mode == 2) {
+            int ms = 0, al = 0;
+            const int max_log = (t == 1) ? OF_MAX_LOG : LL_MAX_LOG;
+            const int used = (p < room) ? read_ncount(bp + p, room - p, S.norm[t], max_allowed, max_log, &ms, &al) : -1;
+            if (used < 0) { ok = false; break; }
+            S.tab_max[t] = ms; S.tab_log[t] = al;
+            p += (uint32_t)used;
+          } else ok = false;                                                                  // Repeat needs a previous block
+        }
+        if (p >= room) ok = false;
+        S.bits_off = p;
+        S.ok = ok ? 1u : 0u;
+      }
+      __syncwarp();
+      if (!S.ok) {
+        if (lane == 0) { slot.seqs()[nseq] = make_uint4(0, 0, 0, 0); D->seq_status = ST_CORRUPT; D->out_end = 0; D->lit_end = 0; }
+        continue;
+      }
+      for (int t = 0; t < 3; t++) {
+        uint32_t *tab = (t == 0) ? llt : (t == 1) ? oft : mlt;
+        if (S.tab_mode[t] == 1) { if (lane == 0) tab[0] = pack_entry(t, (uint32_t)S.tab_max[t], 0, 0); }
+        else fse_build_warp_packed(tab, S.norm[t], S.tab_max[t], S.tab_log[t], t, S.item_sym, S.sym_next, lane);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        info[c].ll_log = (uint32_t)S.tab_log[0]; info[c].of_log = (uint32_t)S.tab_log[1]; info[c].ml_log = (uint32_t)S.tab_log[2];
+        info[c].bits_off = D->tab_off + S.bits_off; info[c].bits_len = room - S.bits_off;
+        info[c].ready = 1;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---------------- phase 2: one lane per chunk, KB_DEC_WARPS warps ----------------
+    if (warp < KB_DEC_WARPS && lane < KB_LANES) {
+      const uint32_t c = (uint32_t)warp * KB_LANES + (uint32_t)lane, chunk = g0 + c;
+      if (chunk < A.n && info[c].ready) {
+        ChunkSlot slot = slot_of(F, chunk);
+        const uint32_t *llt = tables + (size_t)c * 1280;
+        fast_decode_sequences((const uint8_t *)A.in_ptrs[chunk], slot.desc(), slot.seqs(), llt, llt + 1024, llt + 512, bases, info[c]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =================================================================================================
+// KC: sequence execution, one warp per chunk, one lane per sequence
+// =================================================================================================
+constexpr int EXEC_WARPS = 4;
+
+struct LitSrc {
+  const uint8_t *base;
+  uint32_t seg, pad, mode;     // mode 0: contiguous, 1: rle (every index reads base[0]), 2: four padded segments
+  __device__ __forceinline__ const uint8_t *run(uint32_t p, uint32_t len, bool *contig) const {
+    if (mode == 0) { *contig = true; return base + p; }
+    if (mode == 1) { *contig = false; return base; }
+    const uint32_t s = (p >= seg) + (p >= 2 * seg) + (p >= 3 * seg);
+    *contig = s == 3 || p + len <= (s + 1) * seg;
+    return base + p + s * pad;
+  }
+  __device__ __forceinline__ uint8_t at(uint32_t p) const {
+    if (mode == 0) return base[p];
+    if (mode == 1) return base[0];
+    const uint32_t s = (p >= seg) + (p >= 2 * seg) + (p >= 3 * seg);
+    return base[p + s * pad];
+  }
+};
+
+constexpr uint32_t LANE_COPY_MAX = 48;      // longest run a single lane copies by itself
+
+// One lane copies n <= LANE_COPY_MAX bytes, source and destination do not overlap.  Loads are issued
+// eight at a time before the stores so that the copy pays one memory latency per 8 bytes, not per byte.
+__device__ __forceinline__ void lane_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n) {
+  uint32_t k = 0;
+  for (; k + 8 <= n; k += 8) {
+    uint8_t t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = src[k + u];
+#pragma unroll
+    for (int u = 0; u < 8; u++) dst[k + u] = t[u];
+  }
+  uint8_t t[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) if (k + u < n) t[u] = src[k + u];
+#pragma unroll
+  for (int u = 0; u < 8; u++) if (k + u < n) dst[k + u] = t[u];
+}
+
+// Whole-warp match copy (RFC 8878 3.1.2.5 semantics incl. overlap): 32 consecutive bytes per step,
+// four steps in flight when source and destination are disjoint.
+__device__ __forceinline__ void warp_copy_match(uint8_t *out, uint32_t d, uint32_t offset, uint32_t ml, int lane) {
+  const uint8_t *sp = out + d - offset;
+  uint8_t *dp = out + d;
+  if (offset >= ml) {
+    uint32_t k = lane;
+    for (; k + 96 < ml; k += 128) {
+      const uint8_t a = sp[k], b = sp[k + 32], c = sp[k + 64], e = sp[k + 96];
+      dp[k] = a; dp[k + 32] = b; dp[k + 64] = c; dp[k + 96] = e;
+    }
+    for (; k < ml; k += 32) dp[k] = sp[k];
+  } else if (offset >= 32) {
+    // every 32-byte step reads bytes that earlier steps wrote: keep the steps ordered
+    for (uint32_t k0 = 0; k0 < ml; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      if (k < ml) dp[k] = sp[k];
+      __syncwarp();
+    }
+  } else {
+    for (uint32_t k = lane; k < ml; k += 32) dp[k] = sp[k % offset];          // periodic extension of the last `offset` bytes
+  }
+}
+
+__global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDecodeArgs F) {
+  const DecodeArgs &A = F.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stride = gridDim.x * EXEC_WARPS;
+  for (uint32_t chunk = blockIdx.x * EXEC_WARPS + warp; chunk < A.n; chunk += stride) {
+    ChunkSlot slot = slot_of(F, chunk);
+    const FastDesc *D = slot.desc();
+    if (D->state != 0) continue;
+    const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
+    uint8_t *const out = (uint8_t *)A.out_ptrs[chunk];
+    uint32_t status = D->seq_status;
+    for (uint32_t k = 0; k < D->n_streams; k++) if (status == ST_OK) status = D->lit_status[k];
+    uint32_t total = 0;
+    if (status == ST_OK) {
+      const uint32_t nseq = D->nseq, lit_size = D->lit_size, cap = D->cap;
+      LitSrc L;
+      if (D->lit_type == 2) { L.base = slot.lits(); L.seg = D->seg; L.pad = seg_padded(D->seg) - D->seg; L.mode = D->n_streams == 4 ? 2u : 0u; }
+      else { L.base = src + D->lit_src; L.seg = 0; L.pad = 0; L.mode = D->lit_type; }
+      const uint4 *__restrict__ seqs = slot.seqs();
+      for (uint32_t g0 = 0; g0 < nseq; g0 += 32) {
+        const uint32_t i = g0 + (uint32_t)lane;
+        const bool valid = i < nseq;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (valid) r = __ldcs(seqs + i);
+        // literal length = next record's literal position - mine (lane 31 / the last sequence fetch it)
+        uint32_t next_lit = __shfl_down_sync(0xffffffffu, r.y, 1);
+        if (valid && (lane == 31 || i + 1 == nseq)) next_lit = __ldcs(seqs + i + 1).y;
+        const uint32_t ll = valid ? next_lit - r.y : 0;
+        const uint32_t group_start = __shfl_sync(0xffffffffu, r.x, 0);
+        const uint32_t d = r.x + ll;
+        // a lane copies its own literal run / match when it is short; long ones and matches that read
+        // this group's output are replayed cooperatively (coalesced) below
+        const bool lit_self = ll <= LANE_COPY_MAX;
+        const bool indep = valid && (d - r.z + r.w <= group_start);            // whole source precedes this group's output
+        const bool match_self = indep && r.w <= LANE_COPY_MAX;
+        if (ll && lit_self) {
+          bool contig;
+          const uint8_t *lp = L.run(r.y, ll, &contig);
+          if (contig) lane_copy(out + r.x, lp, ll);
+          else for (uint32_t k = 0; k < ll; k++) out[r.x + k] = L.at(r.y + k);
+        }
+        if (match_self) lane_copy(out + d, out + d - r.z, r.w);
+        // long literal runs: whole warp, 32 consecutive bytes per step
+        uint32_t biglit = __ballot_sync(0xffffffffu, valid && !lit_self);
+        while (biglit) {
+          const int j = __ffs(biglit) - 1;
+          biglit &= biglit - 1;
+          const uint32_t oj = __shfl_sync(0xffffffffu, r.x, j), pj = __shfl_sync(0xffffffffu, r.y, j), lj = __shfl_sync(0xffffffffu, ll, j);
+          for (uint32_t k = lane; k < lj; k += 32) out[oj + k] = L.at(pj + k);
+        }
+        __syncwarp();
+        // remaining matches in sequence order (sources may lie inside this group's output)
+        uint32_t dep = __ballot_sync(0xffffffffu, valid && !match_self);
+        while (dep) {
+          const int j = __ffs(dep) - 1;
+          dep &= dep - 1;
+          const uint32_t dj = __shfl_sync(0xffffffffu, d, j), oj = __shfl_sync(0xffffffffu, r.z, j), mj = __shfl_sync(0xffffffffu, r.w, j);
+          warp_copy_match(out, dj, oj, mj, lane);
+          __syncwarp();
+        }
+      }
+      // trailing literals
+      const uint32_t out_end = D->out_end, lit_end = D->lit_end, rest = lit_size - lit_end;
+      if (rest > cap - out_end) status = ST_BUFFER_TOO_SMALL;
+      else {
+        for (uint32_t k = lane; k < rest; k += 32) out[out_end + k] = L.at(lit_end + k);
+        total = out_end + rest;
+        if (D->content != 0xFFFFFFFFu && D->content != total) status = ST_CORRUPT;
+      }
+      __syncwarp();
+      if (status == ST_OK && D->ck_off && A.verify_checksum) {
+        const uint64_t hs = xxh64_warp(out, total, lane);
+        if ((uint32_t)hs != ld_le32(src + D->ck_off)) status = ST_CHECKSUM;
+      }
+    }
+    if (lane == 0) {
+      A.out_sizes[chunk] = status == ST_OK ? total : 0;
+      if (A.statuses) A.statuses[chunk] = status;
+    }
+  }
+}
+
+cudaError_t launch_decode_fast(const FastDecodeArgs &F, cudaStream_t stream, int *launches) {
+  const uint32_t n = F.base.n;
+  if (launches) *launches = 0;
+  if (n == 0) return cudaSuccess;
+  static bool attr_done = false;
+  cudaError_t e;
+  if (!attr_done) {
+    if ((e = cudaFuncSetAttribute(zstd_fast_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KA_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
+    attr_done = true;
+  }
+  // one memset zeroes every counter of the pipeline: general work queue, slow count, pool heads, group counters
+  if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
+  const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP, kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
+  const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
+  zstd_fast_lit_kernel<<<ka_groups < sms ? ka_groups : sms, KA_THREADS, KA_SMEM, stream>>>(F);
+  zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
+  const uint32_t exec_blocks = (n + EXEC_WARPS - 1) / EXEC_WARPS;
+  zstd_fast_exec_kernel<<<exec_blocks, EXEC_WARPS * 32, 0, stream>>>(F);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // whatever the fast path declined: the general kernel pulls it from the device-side list
+  DecodeArgs G = F.base;
+  G.list = F.slow_list;
+  G.list_count = F.slow_count;
+  e = launch_decode_batch_nomemset(G, F.general_grid, stream);
+  if (launches) *launches = 4;
+  return e;
+}
+
+} // namespace b200zstd

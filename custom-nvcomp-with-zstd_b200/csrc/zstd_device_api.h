@@ -22,9 +22,36 @@ struct DecodeArgs {
   uint8_t *lit_scratch;     // grid * LIT_SCRATCH_BYTES
   uint32_t n;
   int verify_checksum;
+  const uint32_t *list;        // optional: chunk indices to process (general kernel behind the fast path)
+  const uint32_t *list_count;  // number of valid entries in list (device memory)
 };
 cudaError_t launch_decode_batch(const DecodeArgs &args, int grid, cudaStream_t stream);
+cudaError_t launch_decode_batch_nomemset(const DecodeArgs &args, int grid, cudaStream_t stream);   // counter already zero
 int decode_ctas_per_sm();
+
+// ---- batch fast path: three kernels over the whole batch (zstd_decode_fast.cu) --------------------
+constexpr uint32_t FAST_WAVE = 16384;                         // chunks per fast-path wave (bounds the scratch)
+constexpr uint32_t FAST_SEQ_CAP = 65536;                      // sequences per chunk the fast path accepts
+constexpr size_t FAST_TABLE_BYTES = 4096 + 10240;             // Huffman DTable + LL/OF/ML decode tables
+constexpr size_t FAST_DESC_BYTES = 192;
+constexpr size_t FAST_SLOT_BYTES = FAST_DESC_BYTES + FAST_TABLE_BYTES;     // fixed per-chunk slot
+// Literals and sequence records come from two bump-allocated pools sized from the COMPRESSED sizes the
+// caller passes to the temp-size query; a chunk that does not fit takes the general kernel instead.
+struct FastDecodeArgs {
+  DecodeArgs base;          // tables, sizes, statuses; base.counter / lit_scratch serve the general kernel
+  uint8_t *slots;           // n * FAST_SLOT_BYTES
+  uint8_t *lit_pool;        // 16-byte aligned
+  uint8_t *seq_pool;
+  uint64_t lit_pool_bytes, seq_pool_bytes;
+  unsigned long long *pool_heads;   // [0] literals, [1] sequences; zeroed by the launcher
+  uint32_t *slow_list;      // n entries
+  uint32_t *slow_count;     // 1 entry, zeroed by the launcher
+  uint32_t *group_counters; // [0] literal kernel, [1] sequence kernel work queues; zeroed by the launcher
+  int general_grid;
+  int sm_count;
+};
+// returns the number of kernels launched through *launches
+cudaError_t launch_decode_fast(const FastDecodeArgs &args, cudaStream_t stream, int *launches);
 
 struct EncodeArgs {
   const void *const *in_ptrs;

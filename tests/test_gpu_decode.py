@@ -22,7 +22,7 @@ def gpu_decode(codec, blob, offs, sizes, chunk, caps=None):
     in_ptrs = (np.uint64(comp.data_ptr()) + np.asarray(offs, np.uint64)).astype(np.uint64)
     out_ptrs = (np.uint64(out.data_ptr()) + idx * np.uint64(chunk)).astype(np.uint64)
     out_sizes = np.full(n, chunk, np.uint64) if caps is None else np.asarray(caps, np.uint64).copy()
-    ws = torch.empty(codec.decompress_temp_size(n), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(codec.decompress_temp_size(n, np.asarray(sizes, np.uint64)), dtype=torch.uint8, device="cuda")
     rc = codec.decompress_tables(in_ptrs, np.asarray(sizes, np.uint64), n, out_ptrs, out_sizes, ws)
     return rc, out.cpu().numpy(), out_sizes
 
@@ -179,3 +179,19 @@ def test_device_tables_and_single_buffer_apis(oracle, libzstd, pkg, gpu_codec_fa
         rc, _ = s.decompress(comp.data_ptr(), int(sizes[0]), one, 0, w1, w1.numel())
         assert rc == 7                                     # zero capacity -> ERROR_BUFFER_TOO_SMALL
         s.close()
+
+
+def test_small_workspace_routes_to_general_kernel(oracle, libzstd, gpu_codec_factory):
+    # pools sized for zero-byte frames overflow at once: every chunk must still decode (general kernel)
+    codec = gpu_codec_factory()
+    chunk, n = 65536, 40
+    d = oracle.gen_batch(chunk, n, 2, 0)
+    blob, offs, sizes = libzstd.compress_chunks(d, chunk, 3)
+    comp = to_dev(blob)
+    out = torch.zeros(n * chunk, dtype=torch.uint8, device="cuda")
+    idx = np.arange(n, dtype=np.uint64)
+    ws = torch.empty(codec.decompress_temp_size(n, np.zeros(n, np.uint64)), dtype=torch.uint8, device="cuda")
+    osz = np.full(n, chunk, np.uint64)
+    rc = codec.decompress_tables((np.uint64(comp.data_ptr()) + offs).astype(np.uint64), sizes, n,
+                                 (np.uint64(out.data_ptr()) + idx * np.uint64(chunk)).astype(np.uint64), osz, ws)
+    assert rc == 0 and (osz == chunk).all() and np.array_equal(out.cpu().numpy(), d)
