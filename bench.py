@@ -326,38 +326,70 @@ def main():
     peak, peak_src = measured_peak_hbm()
     achieved = (U + Cb) / (kern_ms * 1e-3) / 1e9
 
-    # ---- e2e through the C-ABI call with HOST buffers ----
+    # ---- e2e through the C-ABI with HOST buffers: every step moves the frames and the pointer/size tables H2D
+    # from pinned memory, decodes through cuda_zstd_batch_decompress_nosync, and moves the decompressed bytes and the
+    # per-chunk sizes/statuses D2H.  The step is pipelined in waves over three streams (copy-in, decode, copy-out):
+    # that is how a user of an async batch API overlaps PCIe with the kernels; nothing is left out of the timed region.
+    E2E_WAVES = 4
+    wave_n = (n + E2E_WAVES - 1) // E2E_WAVES
     h_comp = torch.from_numpy(blob).pin_memory()
     h_out = torch.empty(U, dtype=torch.uint8).pin_memory()
-    in_ptrs_h = (np.uint64(d_comp.data_ptr()) + offs).astype(np.uint64)
-    out_ptrs_h = (np.uint64(d_out.data_ptr()) + idx * np.uint64(CHUNK)).astype(np.uint64)
+    tab_np = np.stack([(np.uint64(d_comp.data_ptr()) + offs).astype(np.int64), sizes.astype(np.int64),
+                       (np.uint64(d_out.data_ptr()) + idx * np.uint64(CHUNK)).astype(np.int64), np.full(n, CHUNK, np.int64)])
+    h_tab = torch.from_numpy(tab_np).pin_memory()
+    d_tab = torch.empty_like(h_tab, device=dev)
+    h_res = torch.empty((2, n), dtype=torch.int64).pin_memory()          # sizes, statuses back on the host
+    d_st64 = torch.zeros(n, dtype=torch.int64, device=dev)
+    s_in, s_dec, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    blob_off = np.concatenate([offs, [np.uint64(blob.size)]]).astype(np.int64)
+    e2e_launches = [0]
 
     def e2e_step():
-        d_comp.copy_(h_comp, non_blocking=True)                         # H2D: this step's frames
-        osz = np.full(n, CHUNK, np.uint64)
-        rc = codec.decompress_tables(in_ptrs_h, sizes, n, out_ptrs_h, osz, ws)     # public call: stages tables, syncs, returns sizes
-        assert rc == 0
-        h_out.copy_(d_out, non_blocking=True)                           # D2H: the decompressed result
-        torch.cuda.synchronize()
+        ev_in = [torch.cuda.Event() for _ in range(E2E_WAVES)]
+        ev_dec = [torch.cuda.Event() for _ in range(E2E_WAVES)]
+        for w in range(E2E_WAVES):
+            lo, hi = w * wave_n, min(n, (w + 1) * wave_n)
+            with torch.cuda.stream(s_in):
+                if w == 0:
+                    d_tab.copy_(h_tab, non_blocking=True)                                   # pointer/size tables
+                d_comp[blob_off[lo]:blob_off[hi]].copy_(h_comp[blob_off[lo]:blob_off[hi]], non_blocking=True)
+                ev_in[w].record(s_in)
+            s_dec.wait_event(ev_in[w])
+            with torch.cuda.stream(s_dec):
+                rc = codec.decompress_nosync(d_tab[0, lo:hi], d_tab[1, lo:hi], hi - lo, d_tab[2, lo:hi], d_tab[3, lo:hi],
+                                             t_status[lo:hi], ws, s_dec)
+                assert rc == 0
+                e2e_launches[0] += codec.last_launch_count()
+                ev_dec[w].record(s_dec)
+            s_out.wait_event(ev_dec[w])
+            with torch.cuda.stream(s_out):
+                h_out[lo * CHUNK:hi * CHUNK].copy_(d_out[lo * CHUNK:hi * CHUNK], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            d_st64.copy_(t_status)
+            h_res[0].copy_(d_tab[3], non_blocking=True)
+            h_res[1].copy_(d_st64, non_blocking=True)
+        s_out.synchronize()
+        assert int(h_res[1].max()) == 0 and int(h_res[0].min()) == CHUNK
 
+    torch.cuda.synchronize()
     e2e_step()
     barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-        launches += codec.last_launch_count()
-    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3              # wall clock: the region spans three streams and host work
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    launches += e2e_launches[0]
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_val = world * U * e2e_steps / (e2e_ms * 1e-3) / 1e9
-    assert np.array_equal(h_out.numpy()[:CHUNK * 4], data[:CHUNK * 4])
+    assert np.array_equal(h_out.numpy(), data), "e2e output differs from the input"
+    h2d_bytes = int(blob.size) + int(h_tab.numel() * 8)
+    d2h_bytes = U + int(h_res.numel() * 8)
 
     # ---- level-3 batch compress of the same chunks (config 3 shape), device resident ----
     compress = None
@@ -427,8 +459,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic("decode"), "peak_source": peak_src, "kernel": "zstd_decode_batch_kernel",
                          "algorithmic_bytes_per_launch": U + Cb, "kernel_ms": kern_ms},
-            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(blob.size), "d2h_bytes_per_step": U,
-                    "steps": e2e_steps, "call": "cuda_zstd_batch_decompress (host tables) + pinned H2D/D2H"},
+            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "call": "cuda_zstd_batch_decompress_nosync in 4 waves; frames+tables H2D and output+sizes+statuses D2H from/to pinned host memory, 3-stream pipeline"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if compress:
