@@ -664,6 +664,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
       if (D->lit_type == 2) { L.base = slot.lits(); L.seg = D->seg; L.pad = seg_padded(D->seg) - D->seg; L.mode = D->n_streams == 4 ? 2u : 0u; }
       else { L.base = src + D->lit_src; L.seg = 0; L.pad = 0; L.mode = D->lit_type; }
       const uint4 *__restrict__ seqs = slot.seqs();
+      const uintptr_t out_addr = (uintptr_t)out;
       for (uint32_t g0 = 0; g0 < nseq; g0 += 32) {
         const uint32_t i = g0 + (uint32_t)lane;
         const bool valid = i < nseq;
@@ -675,29 +676,71 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
         const uint32_t ll = valid ? next_lit - r.y : 0;
         const uint32_t group_start = __shfl_sync(0xffffffffu, r.x, 0);
         const uint32_t d = r.x + ll;
-        // a lane copies its own literal run / match when it is short; long ones and matches that read
-        // this group's output are replayed cooperatively (coalesced) below
-        const bool lit_self = ll <= LANE_COPY_MAX;
         const bool indep = valid && (d - r.z + r.w <= group_start);            // whole source precedes this group's output
-        const bool match_self = indep && r.w <= LANE_COPY_MAX;
-        if (ll && lit_self) {
-          bool contig;
-          const uint8_t *lp = L.run(r.y, ll, &contig);
-          if (contig) lane_copy(out + r.x, lp, ll);
-          else for (uint32_t k = 0; k < ll; k++) out[r.x + k] = L.at(r.y + k);
-        }
-        if (match_self) lane_copy(out + d, out + d - r.z, r.w);
-        // long literal runs: whole warp, 32 consecutive bytes per step
-        uint32_t biglit = __ballot_sync(0xffffffffu, valid && !lit_self);
-        while (biglit) {
-          const int j = __ffs(biglit) - 1;
-          biglit &= biglit - 1;
-          const uint32_t oj = __shfl_sync(0xffffffffu, r.x, j), pj = __shfl_sync(0xffffffffu, r.y, j), lj = __shfl_sync(0xffffffffu, ll, j);
-          for (uint32_t k = lane; k < lj; k += 32) out[oj + k] = L.at(pj + k);
+        // ---- piece-parallel phase: the literal run of every sequence and every independent match are cut into
+        // destination-aligned 16-byte pieces; pieces are dealt to lanes round-robin, so the work per lane is
+        // uniform whatever the length distribution, and each round costs one memory round trip ----
+        const uint32_t mlen = indep ? r.w : 0u;
+        const uint32_t ca = ll ? (uint32_t)(((out_addr + r.x + ll - 1) >> 4) - ((out_addr + r.x) >> 4)) + 1 : 0u;
+        const uint32_t cb = mlen ? (uint32_t)(((out_addr + d + mlen - 1) >> 4) - ((out_addr + d) >> 4)) + 1 : 0u;
+        uint32_t incl = ca + cb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const uint32_t excl = incl - (ca + cb), total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+          const uint32_t q = q0 + (uint32_t)lane;
+          // owner j = last lane whose exclusive prefix is <= q
+          uint32_t j = 0;
+#pragma unroll
+          for (int st = 16; st; st >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, excl, (j + st) & 31); if (j + st < 32 && pj <= q) j += st; }
+          const uint32_t jx = __shfl_sync(0xffffffffu, r.x, j), jy = __shfl_sync(0xffffffffu, r.y, j), jz = __shfl_sync(0xffffffffu, r.z, j);
+          const uint32_t jll = __shfl_sync(0xffffffffu, ll, j), jml = __shfl_sync(0xffffffffu, mlen, j);
+          const uint32_t jca = __shfl_sync(0xffffffffu, ca, j), jex = __shfl_sync(0xffffffffu, excl, j);
+          if (q < total) {
+            uint32_t k = q - jex;
+            const bool is_match = k >= jca;
+            if (is_match) k -= jca;
+            const uint32_t a = is_match ? jx + jll : jx, len = is_match ? jml : jll;       // run start (output offset), run length
+            const uintptr_t a0 = out_addr + a, blk = (a0 >> 4) + k;
+            const uintptr_t lo = a0 > (blk << 4) ? a0 : (blk << 4);
+            const uintptr_t hi = (a0 + len) < ((blk + 1) << 4) ? (a0 + len) : ((blk + 1) << 4);
+            const uint32_t nb = (uint32_t)(hi - lo), rel = (uint32_t)(lo - a0);
+            // 16 source bytes -> v[0..3]
+            uint32_t v0, v1, v2, v3;
+            const uint8_t *sp = nullptr;
+            if (is_match) sp = out + a - jz + rel;
+            else {
+              bool contig;
+              sp = L.run(jy + rel, nb, &contig);
+              if (!contig) sp = nullptr;
+            }
+            if (sp) {
+              const uintptr_t s = (uintptr_t)sp;
+              const uint32_t *wbase = reinterpret_cast<const uint32_t *>(s & ~(uintptr_t)3);
+              const uint32_t sh = (uint32_t)(s & 3) * 8, lastw = (uint32_t)(((s + nb - 1) >> 2) - (s >> 2));
+              const uint32_t w0 = wbase[0], w1 = wbase[min(1u, lastw)], w2 = wbase[min(2u, lastw)], w3 = wbase[min(3u, lastw)],
+                             w4 = wbase[min(4u, lastw)];
+              v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh); v2 = __funnelshift_r(w2, w3, sh); v3 = __funnelshift_r(w3, w4, sh);
+            } else {
+              // RLE literals or a piece straddling two Huffman segments: byte gather
+              uint32_t t[4] = {0, 0, 0, 0};
+              for (uint32_t u = 0; u < nb; u++) t[u >> 2] |= (uint32_t)L.at(jy + rel + u) << (8 * (u & 3));
+              v0 = t[0]; v1 = t[1]; v2 = t[2]; v3 = t[3];
+            }
+            uint8_t *dp = reinterpret_cast<uint8_t *>(lo);
+            if (nb == 16) *reinterpret_cast<uint4 *>(dp) = make_uint4(v0, v1, v2, v3);
+            else {
+#pragma unroll
+              for (int u = 0; u < 15; u++) {
+                const uint32_t word = u < 4 ? v0 : u < 8 ? v1 : u < 12 ? v2 : v3;
+                if ((uint32_t)u < nb) dp[u] = (uint8_t)(word >> (8 * (u & 3)));
+              }
+            }
+          }
         }
         __syncwarp();
-        // remaining matches in sequence order (sources may lie inside this group's output)
-        uint32_t dep = __ballot_sync(0xffffffffu, valid && !match_self);
+        // ---- matches that read this group's own output: in sequence order, the whole warp on each ----
+        uint32_t dep = __ballot_sync(0xffffffffu, valid && !indep);
         while (dep) {
           const int j = __ffs(dep) - 1;
           dep &= dep - 1;
