@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t seg_padded(uint32_t seg) { return (seg + 15u
 // KA: headers + Huffman tables (one warp per chunk), then one thread per Huffman stream
 // =================================================================================================
 constexpr int KA_THREADS = 256, KA_WARPS = KA_THREADS / 32;
-constexpr int KA_GROUP = 48;                                   // chunks per CTA pass: 48 x 4 KB of tables
+constexpr int KA_GROUP = 24;                                   // chunks per CTA pass: 24 x 4 KB of tables, two CTAs per SM
 struct __align__(16) HufScratch {                              // per-warp scratch of huf_read_table_warp
   uint16_t *huf;                                               // -> this chunk's table in shared memory
   uint8_t weights[256];
@@ -785,7 +785,7 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F, cudaStream_t stream, int
   if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
   const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP, kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
   const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
-  zstd_fast_lit_kernel<<<ka_groups < sms ? ka_groups : sms, KA_THREADS, KA_SMEM, stream>>>(F);
+  zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
   zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
   const uint32_t exec_blocks = (n + EXEC_WARPS - 1) / EXEC_WARPS;
   zstd_fast_exec_kernel<<<exec_blocks, EXEC_WARPS * 32, 0, stream>>>(F);
