@@ -690,7 +690,8 @@ ZHDN uint32_t encode_block_payload(EntropyWs &W, const uint8_t *lits, uint32_t n
   }
   *modes = (uint8_t)((mode[0] << 6) | (mode[1] << 4) | (mode[2] << 2));
   SeqStore S{sll, sml, sofv};
-  uint32_t n = seq_encode_stream(W, S, nseq, dst + op, cap - op);
+  // three spare bytes: the kernel assembles this stream with 32-bit word writes (zstd_encode.cu)
+  uint32_t n = seq_encode_stream(W, S, nseq, dst + op, cap - op >= 3 ? cap - op - 3 : 0);
   if (!n) return 0;
   return op + n;
 }
