@@ -94,6 +94,39 @@ __device__ uint32_t extend_warp(const ParseCtx &C, uint32_t s, uint32_t off, uin
   }
 }
 
+// two matches measured together: lanes 0-15 walk (s1, off1), lanes 16-31 walk (s2, off2), 16 x 8 bytes per round each
+__device__ void extend_pair(const ParseCtx &C, uint32_t s1, uint32_t off1, uint32_t have1, uint32_t s2, uint32_t off2, uint32_t have2,
+                            int lane, uint32_t *len1, uint32_t *len2) {
+  const bool second = lane >= 16;
+  const uint32_t s = second ? s2 : s1, off = second ? off2 : off1, l16 = (uint32_t)(lane & 15);
+  uint32_t la = have1, lb = have2;
+  bool run_a = have1 >= 8, run_b = have2 >= 8;
+  uint32_t base_a = 8, base_b = 8;
+  while (run_a || run_b) {
+    const uint32_t base = second ? base_b : base_a;
+    const bool act = second ? run_b : run_a;
+    const uint32_t p = s + base + 8u * l16;
+    uint32_t c = 0;
+    if (act && p < C.bn) {
+      c = common8(C.src.ld64(C.blk_off + p), C.src.ld64(C.blk_off + p - off));
+      const uint32_t room = C.bn - p;
+      if (c > room) c = room;
+    }
+    const uint32_t stop = __ballot_sync(0xffffffffu, c < 8);
+    if (run_a) {
+      const uint32_t sa = stop & 0xFFFFu;
+      if (sa) { const int j = __ffs(sa) - 1; la = base_a + 8u * (uint32_t)j + __shfl_sync(0xffffffffu, c, j); run_a = false; }
+      else base_a += 128;
+    }
+    if (run_b) {
+      const uint32_t sb = stop >> 16;
+      if (sb) { const int j = __ffs(sb) - 1; lb = base_b + 8u * (uint32_t)j + __shfl_sync(0xffffffffu, c, 16 + j); run_b = false; }
+      else base_b += 128;
+    }
+  }
+  *len1 = la; *len2 = lb;
+}
+
 // per-lane forward length capped at `cap` (chain levels)
 __device__ __forceinline__ uint32_t extend_lane(const ParseCtx &C, uint32_t pos, uint32_t off, uint32_t cap) {
   uint32_t len = 8;
@@ -467,32 +500,50 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
           bool has = false;
           if (pos < C.ilimit) {
             const uint64_t v = C.src.ld64(blk_off + pos);
-            if (C.tab2) {
-              int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab2[hash_long(v, P.long_log)]);
-              if (c >= (int64_t)pos) c -= 0x10000;
-              if (c >= 0 && common8(v, C.src.ld64(blk_off + (uint32_t)c)) == 8) { best = 8; bo = pos - (uint32_t)c; }
-            }
-            {
+            if (!C.chain) {
+              // table candidates and the repeat offset: positions first, then all loads in flight together
+              int64_t c2 = -1, c1;
+              if (C.tab2) {
+                c2 = (int64_t)((pos & ~0xFFFFu) | C.tab2[hash_long(v, P.long_log)]);
+                if (c2 >= (int64_t)pos) c2 -= 0x10000;
+              }
+              c1 = (int64_t)((pos & ~0xFFFFu) | C.tab1[hash_short(v, P.hash_bytes, P.hash_log)]);
+              if (c1 >= (int64_t)pos) c1 -= 0x10000;
+              const bool vr = blk_off + pos >= rep[0];
+              const uint64_t x2 = c2 >= 0 ? C.src.ld64(blk_off + (uint32_t)c2) : ~v;
+              const uint64_t x1 = c1 >= 0 ? C.src.ld64(blk_off + (uint32_t)c1) : ~v;
+              const uint64_t xr = vr ? C.src.ld64(blk_off + pos - rep[0]) : ~v;
+              if (c2 >= 0 && common8(v, x2) == 8) { best = 8; bo = pos - (uint32_t)c2; }
+              if (c1 >= 0) {
+                const uint32_t l = common8(v, x1);
+                if (l >= (uint32_t)P.min_match && l > best) { best = l; bo = pos - (uint32_t)c1; }
+              }
+              if (vr) {
+                const uint32_t l = common8(v, xr);
+                if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
+              }
+            } else {
               int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab1[hash_short(v, P.hash_bytes, P.hash_log)]);
               if (c >= (int64_t)pos) c -= 0x10000;
-              int depth = P.chain_depth > 0 ? P.chain_depth : 1;
+              int depth = P.chain_depth;
               while (depth-- > 0 && c >= 0) {
                 uint32_t l = common8(v, C.src.ld64(blk_off + (uint32_t)c));
-                if (C.chain && l == 8) l = extend_lane(C, pos, pos - (uint32_t)c, P.lane_cap);
+                if (l == 8) l = extend_lane(C, pos, pos - (uint32_t)c, P.lane_cap);
                 if (l >= (uint32_t)P.min_match && l > best) { best = l; bo = pos - (uint32_t)c; }
-                if (!C.chain) break;
                 const uint32_t d = C.chain[(uint32_t)c];
                 if (d == 0) break;
                 c -= d;
               }
-            }
-            if (blk_off + pos >= rep[0]) {
-              uint32_t l = common8(v, C.src.ld64(blk_off + pos - rep[0]));
-              if (C.chain && l == 8) l = extend_lane(C, pos, rep[0], P.lane_cap);
-              if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
+              if (blk_off + pos >= rep[0]) {
+                uint32_t l = common8(v, C.src.ld64(blk_off + pos - rep[0]));
+                if (l == 8) l = extend_lane(C, pos, rep[0], P.lane_cap);
+                if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
+              }
             }
             has = best >= (uint32_t)P.min_match || (bo == rep[0] && best >= 4);
           }
+          // the input is read once, front to back: keep the line four windows ahead on its way from HBM
+          if (lane == 0 && ip + 640 < bn) asm volatile("prefetch.global.L2 [%0];" ::"l"(chunk + blk_off + ip + 512));
           const uint32_t mask = __ballot_sync(0xffffffffu, has);
           if (mask == 0) {
             insert_stripe(C, ip, 32, lane);
@@ -503,14 +554,21 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
           uint32_t s = ip + (uint32_t)f;
           uint32_t off = __shfl_sync(0xffffffffu, bo, f);
           const uint32_t bl_f = __shfl_sync(0xffffffffu, best, f);
-          uint32_t len = extend_warp(C, s, off, bl_f < 8 ? bl_f : 8, lane);
+          uint32_t len;
+          uint32_t len_g1 = 0;
+          const bool g1 = P.lazy >= 1 && f + 1 < 32 && ((mask >> (f + 1)) & 1);
+          if (g1) {
+            // first match and its lazy rival measured in the same memory round trips: 16 lanes each
+            const uint32_t bl_g = __shfl_sync(0xffffffffu, best, f + 1), off_g = __shfl_sync(0xffffffffu, bo, f + 1);
+            extend_pair(C, s, off, bl_f < 8 ? bl_f : 8, s + 1, off_g, bl_g < 8 ? bl_g : 8, lane, &len, &len_g1);
+          } else len = extend_warp(C, s, off, bl_f < 8 ? bl_f : 8, lane);
           for (int step = 1; step <= P.lazy; step++) {
             const int g = f + step;
             if (g >= 32 || !((mask >> g) & 1)) continue;
             const uint32_t bl_g = __shfl_sync(0xffffffffu, best, g), off2 = __shfl_sync(0xffffffffu, bo, g);
             if (bl_g < 8 && bl_g <= len) continue;
             const uint32_t s2 = ip + (uint32_t)g;
-            const uint32_t len2 = extend_warp(C, s2, off2, bl_g < 8 ? bl_g : 8, lane);
+            const uint32_t len2 = (step == 1) ? len_g1 : extend_warp(C, s2, off2, bl_g < 8 ? bl_g : 8, lane);
             const int gain1 = (int)len * 4 - hb32(off + 1) + 3 * step + (off == rep[0] ? hb32(off + 1) : 0);
             const int gain2 = (int)len2 * 4 - hb32(off2 + 1) + (off2 == rep[0] ? hb32(off2 + 1) : 0);
             if (gain2 > gain1) { s = s2; off = off2; len = len2; }

@@ -51,7 +51,7 @@ ZP_HD EncodeParams encode_params_for_level(int level, int checksum) {
   if (level <= 2) {
     p.strategy = 0; p.hash_log = 13; p.hash_bytes = 5; p.long_log = 0; p.chain_depth = 0; p.min_match = 5; p.lazy = 0; p.insert_all = 1;
   } else if (level <= 4) {
-    p.strategy = 1; p.hash_log = 12; p.hash_bytes = 5; p.long_log = 13; p.chain_depth = 0; p.min_match = 5; p.lazy = 1; p.insert_all = 1;
+    p.strategy = 1; p.hash_log = 11; p.hash_bytes = 5; p.long_log = 13; p.chain_depth = 0; p.min_match = 5; p.lazy = 1; p.insert_all = 1;
   } else {
     // chain levels: libzstd's <=128 KB rows are greedy(5) lazy(6) lazy2(7..10) with 2^3..2^6 attempts
     static const int depth[] = {8, 8, 8, 16, 32, 64};
