@@ -218,6 +218,25 @@ public:
   int dec_ctas_per_sm = 1;
   int last_launches = 0;
   std::mutex mu;   // one manager per thread is the contract; the lock keeps misuse safe (reference: api_mutex)
+  b200zstd::FastOverlap overlap{};     // helper stream + events, created on first decode (no device memory)
+  bool overlap_ready = false;
+  ~Impl() {
+    if (overlap_ready) {
+      for (auto &e : overlap.ev) cudaEventDestroy(e);
+      cudaEventDestroy(overlap.done);
+      cudaStreamDestroy(overlap.side);
+    }
+  }
+  const b200zstd::FastOverlap *get_overlap() {
+    if (!overlap_ready) {
+      if (cudaStreamCreateWithFlags(&overlap.side, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+      bool ok = cudaEventCreateWithFlags(&overlap.done, cudaEventDisableTiming) == cudaSuccess;
+      for (auto &e : overlap.ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) { (void)cudaGetLastError(); return nullptr; }
+      overlap_ready = true;
+    }
+    return &overlap;
+  }
 
   Impl() {
     int dev = 0;
@@ -341,7 +360,7 @@ public:
         f.sm_count = sm_count;
         f.general_grid = dec_grid(m);
         int k = 0;
-        e = b200zstd::launch_decode_fast(f, stream, &k);
+        e = b200zstd::launch_decode_fast(f, stream, get_overlap(), &k);
         last_launches += k;
       }
     }

@@ -497,12 +497,12 @@ __global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArg
   if (threadIdx.x < 36) bases[threadIdx.x] = c_ll_base[threadIdx.x];
   if (threadIdx.x >= 40 && threadIdx.x < 93) bases[threadIdx.x] = c_ml_base[threadIdx.x - 40];
   for (;;) {
-    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 1, 1u);
+    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 1 + F.sub, 1u);
     __syncthreads();
-    const uint32_t g0 = s_group * KB_GROUP;
-    if (g0 >= A.n) break;
+    const uint32_t g0 = F.lo + s_group * KB_GROUP;
+    if (g0 >= F.hi) break;
     // ---------------- phase 1: table descriptions -> decode tables in shared memory ----------------
-    for (uint32_t c = warp; c < KB_GROUP && g0 + c < A.n; c += KB_WARPS) {
+    for (uint32_t c = warp; c < KB_GROUP && g0 + c < F.hi; c += KB_WARPS) {
       const uint32_t chunk = g0 + c;
       ChunkSlot slot = slot_of(F, chunk);
       FastDesc *D = slot.desc();
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArg
     // ---------------- phase 2: one lane per chunk, KB_DEC_WARPS warps ----------------
     if (warp < KB_DEC_WARPS && lane < KB_LANES) {
       const uint32_t c = (uint32_t)warp * KB_LANES + (uint32_t)lane, chunk = g0 + c;
-      if (chunk < A.n && info[c].ready) {
+      if (chunk < F.hi && info[c].ready) {
         ChunkSlot slot = slot_of(F, chunk);
         const uint32_t *llt = tables + (size_t)c * 1280;
         fast_decode_sequences((const uint8_t *)A.in_ptrs[chunk], slot.desc(), slot.seqs(), llt, llt + 1024, llt + 512, bases, info[c]);
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
   const DecodeArgs &A = F.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * EXEC_WARPS;
-  for (uint32_t chunk = blockIdx.x * EXEC_WARPS + warp; chunk < A.n; chunk += stride) {
+  for (uint32_t chunk = F.lo + blockIdx.x * EXEC_WARPS + warp; chunk < F.hi; chunk += stride) {
     ChunkSlot slot = slot_of(F, chunk);
     const FastDesc *D = slot.desc();
     if (D->state != 0) continue;
@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
   }
 }
 
-cudaError_t launch_decode_fast(const FastDecodeArgs &F, cudaStream_t stream, int *launches) {
-  const uint32_t n = F.base.n;
+cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, const FastOverlap *ov, int *launches) {
+  const uint32_t n = F0.base.n;
   if (launches) *launches = 0;
   if (n == 0) return cudaSuccess;
   static bool attr_done = false;
@@ -781,21 +781,44 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F, cudaStream_t stream, int
     if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
     attr_done = true;
   }
+  FastDecodeArgs F = F0;
+  F.lo = 0; F.hi = n; F.sub = 0;
   // one memset zeroes every counter of the pipeline: general work queue, slow count, pool heads, group counters
   if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
-  const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP, kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
   const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
+  const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
   zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
-  zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
-  const uint32_t exec_blocks = (n + EXEC_WARPS - 1) / EXEC_WARPS;
-  zstd_fast_exec_kernel<<<exec_blocks, EXEC_WARPS * 32, 0, stream>>>(F);
+  int count = 1;
+  // KB (SMEM-bound: one CTA and two busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
+  // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1
+  const uint32_t sub_chunks = sms * KB_GROUP;
+  const uint32_t nsub = ov ? (n + sub_chunks - 1) / sub_chunks : 1;
+  const bool overlap = ov && nsub > 1 && nsub <= (uint32_t)FastOverlap::MAX_SUB;
+  if (!overlap) {
+    const uint32_t kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
+    zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
+    zstd_fast_exec_kernel<<<(n + EXEC_WARPS - 1) / EXEC_WARPS, EXEC_WARPS * 32, 0, stream>>>(F);
+    count += 2;
+  } else {
+    for (uint32_t k = 0; k < nsub; k++) {
+      F.lo = k * sub_chunks; F.hi = F.lo + sub_chunks < n ? F.lo + sub_chunks : n; F.sub = k;
+      const uint32_t m = F.hi - F.lo, kb_groups = (m + KB_GROUP - 1) / KB_GROUP;
+      zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
+      if ((e = cudaEventRecord(ov->ev[k], stream)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(ov->side, ov->ev[k], 0)) != cudaSuccess) return e;
+      zstd_fast_exec_kernel<<<(m + EXEC_WARPS - 1) / EXEC_WARPS, EXEC_WARPS * 32, 0, ov->side>>>(F);
+      count += 2;
+    }
+    if ((e = cudaEventRecord(ov->done, ov->side)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(stream, ov->done, 0)) != cudaSuccess) return e;
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // whatever the fast path declined: the general kernel pulls it from the device-side list
   DecodeArgs G = F.base;
   G.list = F.slow_list;
   G.list_count = F.slow_count;
   e = launch_decode_batch_nomemset(G, F.general_grid, stream);
-  if (launches) *launches = 4;
+  if (launches) *launches = count + 1;
   return e;
 }
 

@@ -49,9 +49,17 @@ struct FastDecodeArgs {
   uint32_t *group_counters; // [0] literal kernel, [1] sequence kernel work queues; zeroed by the launcher
   int general_grid;
   int sm_count;
+  uint32_t lo, hi, sub;     // set by the launcher: chunk sub-range and work-queue index of a KB / KC launch
+};
+// optional helper stream + events (owned by the manager) that let KC overlap the next KB sub-wave
+struct FastOverlap {
+  static constexpr int MAX_SUB = 8;
+  cudaStream_t side;
+  cudaEvent_t ev[MAX_SUB];
+  cudaEvent_t done;
 };
 // returns the number of kernels launched through *launches
-cudaError_t launch_decode_fast(const FastDecodeArgs &args, cudaStream_t stream, int *launches);
+cudaError_t launch_decode_fast(const FastDecodeArgs &args, cudaStream_t stream, const FastOverlap *overlap, int *launches);
 
 struct EncodeArgs {
   const void *const *in_ptrs;
