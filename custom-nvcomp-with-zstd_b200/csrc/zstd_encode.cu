@@ -33,7 +33,7 @@ struct EncScratch {          // layout of one CTA's slice of the global workspac
   static constexpr size_t ml_off = ll_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
   static constexpr size_t of_off = ml_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
   static constexpr size_t chain_off = of_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
-  static constexpr size_t bytes_nochain = chain_off;
+  static constexpr size_t bytes_nochain = chain_off + (size_t)64 * 1024;     // room for the long-hash table (<= 2^15 u16) of DFAST
   static constexpr size_t bytes_chain = chain_off + (size_t)BLOCK_BYTES * 2;
 };
 
@@ -42,12 +42,15 @@ size_t encode_cta_scratch_bytes(const EncodeParams &p) {
   return (b + 255) & ~(size_t)255;
 }
 static size_t encode_smem_bytes(const EncodeParams &p) {
-  size_t tabs = ((size_t)2 << p.hash_log) + (p.long_log ? ((size_t)2 << p.long_log) : 0);
+  // only the short table lives in shared memory; the long table of DFAST sits in the CTA's L2-resident scratch
+  // (10 -> 19 resident warps per SM; the parse is latency-bound, so occupancy buys more than the slower lookup costs)
+  size_t tabs = ((size_t)2 << p.hash_log);
   size_t ent = sizeof(EntropyWs);
   return (tabs > ent ? tabs : ent) + 16;
 }
 
-// ---- unaligned 8-byte read through aligned 32-bit loads, clamped to the chunk's last word ----------
+// ---- unaligned 8-byte read through three aligned 32-bit loads and two funnel shifts, clamped to the chunk's last
+// word (bytes past the end are never used by the parser).  (Two 8-byte loads + 64-bit shifts measured 10 % slower.)
 struct Src {
   const uint32_t *w;      // 4-byte aligned base (<= chunk start)
   uint32_t delta;         // chunk start - aligned base (0..3)
@@ -60,8 +63,10 @@ struct Src {
   }
 };
 __device__ __forceinline__ uint32_t common8(uint64_t a, uint64_t b) {
-  const uint64_t x = a ^ b;
-  return x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+  const uint32_t xl = (uint32_t)a ^ (uint32_t)b, xh = (uint32_t)(a >> 32) ^ (uint32_t)(b >> 32);
+  if (xl) return (uint32_t)(__ffs((int)xl) - 1) >> 3;
+  if (xh) return 4u + ((uint32_t)(__ffs((int)xh) - 1) >> 3);
+  return 8u;
 }
 
 struct ParseCtx {
@@ -140,14 +145,12 @@ __device__ __forceinline__ uint32_t extend_lane(const ParseCtx &C, uint32_t pos,
   return len < cap ? len : cap;
 }
 
-// table update for one stripe of up to 32 consecutive positions [p0, p0+cnt): sequential semantics
-__device__ __forceinline__ void insert_stripe(const ParseCtx &C, uint32_t p0, uint32_t cnt, int lane) {
+// table update for one stripe of up to 32 consecutive positions [p0, p0+cnt): sequential semantics.
+// h1 / h2 are the lane's hashes of position p0+lane (only read where `act`).
+__device__ __forceinline__ void insert_hashed(const ParseCtx &C, uint32_t p0, bool act, uint32_t h1_in, uint32_t h2_in, int lane) {
   const uint32_t pos = p0 + (uint32_t)lane;
-  const bool act = (uint32_t)lane < cnt && pos < C.ilimit;
-  uint64_t v = 0;
-  if (act) v = C.src.ld64(C.blk_off + pos);
   // inactive lanes get unique keys above any real hash so they never group with active lanes
-  const uint32_t h1 = act ? hash_short(v, C.P.hash_bytes, C.P.hash_log) : 0x80000000u + (uint32_t)lane;
+  const uint32_t h1 = act ? h1_in : 0x80000000u + (uint32_t)lane;
   const uint32_t g1 = __match_any_sync(0xffffffffu, h1);
   if (act) {
     const uint32_t lower = g1 & lanemask_lt();
@@ -159,11 +162,22 @@ __device__ __forceinline__ void insert_stripe(const ParseCtx &C, uint32_t p0, ui
   __syncwarp();
   if (act && (g1 >> lane) == 1u) C.tab1[h1] = (uint16_t)pos;
   if (C.tab2) {
-    const uint32_t h2 = act ? hash_long(v, C.P.long_log) : 0x80000000u + (uint32_t)lane;
+    const uint32_t h2 = act ? h2_in : 0x80000000u + (uint32_t)lane;
     const uint32_t g2 = __match_any_sync(0xffffffffu, h2);
-    if (act && (g2 >> lane) == 1u) C.tab2[h2] = (uint16_t)pos;
+    if (act && (g2 >> lane) == 1u) __stcg(C.tab2 + h2, (uint16_t)pos);
   }
   __syncwarp();
+}
+__device__ __forceinline__ void insert_stripe(const ParseCtx &C, uint32_t p0, uint32_t cnt, int lane) {
+  const uint32_t pos = p0 + (uint32_t)lane;
+  const bool act = (uint32_t)lane < cnt && pos < C.ilimit;
+  uint32_t h1 = 0, h2 = 0;
+  if (act) {
+    const uint64_t v = C.src.ld64(C.blk_off + pos);
+    h1 = hash_short(v, C.P.hash_bytes, C.P.hash_log);
+    if (C.tab2) h2 = hash_long(v, C.P.long_log);
+  }
+  insert_hashed(C, p0, act, h1, h2, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -458,7 +472,7 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
       C.src.delta = (uint32_t)((uintptr_t)chunk & 3);
       C.src.last_word = (uint32_t)((n - 1 + C.src.delta) >> 2);
       C.tab1 = (uint16_t *)smem;
-      C.tab2 = P.long_log ? (uint16_t *)(smem + ((size_t)2 << P.hash_log)) : nullptr;
+      C.tab2 = P.long_log ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
       C.chain = P.chain_depth > 0 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
 
       if (lane == 0) op = write_frame_header(dst, n, P.checksum != 0);
@@ -484,9 +498,14 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
         // ---- parse ----
         C.blk_off = blk_off; C.bn = bn; C.ilimit = bn > 8 ? bn - 8 : 0;
         {
-          const uint32_t words = (((uint32_t)2 << P.hash_log) + (P.long_log ? ((uint32_t)2 << P.long_log) : 0)) >> 2;
+          const uint32_t words = ((uint32_t)2 << P.hash_log) >> 2;
           uint32_t *z = (uint32_t *)smem;
           for (uint32_t k = lane; k < words; k += 32) z[k] = 0;
+          if (C.tab2) {
+            uint4 *z2 = (uint4 *)C.tab2;
+            const uint32_t vecs = ((uint32_t)2 << P.long_log) >> 4;
+            for (uint32_t k = lane; k < vecs; k += 32) __stcg(z2 + k, make_uint4(0, 0, 0, 0));
+          }
           // "ghost" candidates of never-written buckets are positions 0 and 65536: their chain links
           // must read as end-of-chain until those positions are really inserted
           if (C.chain && lane == 0) { C.chain[0] = 0; if (bn > 65536) C.chain[65536] = 0; }
@@ -496,18 +515,20 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
         uint32_t ip = 0, anchor = 0, nseq = 0, nlit = 0;
         while (ip < C.ilimit && nseq < MAX_SEQ_PER_BLOCK) {
           const uint32_t pos = ip + (uint32_t)lane;
-          uint32_t best = 0, bo = 0;
+          uint32_t best = 0, bo = 0, wh1 = 0, wh2 = 0;        // wh*: this position's hashes, reused by the table update
           bool has = false;
           if (pos < C.ilimit) {
             const uint64_t v = C.src.ld64(blk_off + pos);
+            wh1 = hash_short(v, P.hash_bytes, P.hash_log);
+            if (C.tab2) wh2 = hash_long(v, P.long_log);
             if (!C.chain) {
               // table candidates and the repeat offset: positions first, then all loads in flight together
               int64_t c2 = -1, c1;
               if (C.tab2) {
-                c2 = (int64_t)((pos & ~0xFFFFu) | C.tab2[hash_long(v, P.long_log)]);
+                c2 = (int64_t)((pos & ~0xFFFFu) | __ldcg(C.tab2 + wh2));
                 if (c2 >= (int64_t)pos) c2 -= 0x10000;
               }
-              c1 = (int64_t)((pos & ~0xFFFFu) | C.tab1[hash_short(v, P.hash_bytes, P.hash_log)]);
+              c1 = (int64_t)((pos & ~0xFFFFu) | C.tab1[wh1]);
               if (c1 >= (int64_t)pos) c1 -= 0x10000;
               const bool vr = blk_off + pos >= rep[0];
               const uint64_t x2 = c2 >= 0 ? C.src.ld64(blk_off + (uint32_t)c2) : ~v;
@@ -523,7 +544,7 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
                 if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
               }
             } else {
-              int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab1[hash_short(v, P.hash_bytes, P.hash_log)]);
+              int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab1[wh1]);
               if (c >= (int64_t)pos) c -= 0x10000;
               int depth = P.chain_depth;
               while (depth-- > 0 && c >= 0) {
@@ -546,7 +567,7 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
           if (lane == 0 && ip + 640 < bn) asm volatile("prefetch.global.L2 [%0];" ::"l"(chunk + blk_off + ip + 512));
           const uint32_t mask = __ballot_sync(0xffffffffu, has);
           if (mask == 0) {
-            insert_stripe(C, ip, 32, lane);
+            insert_hashed(C, ip, pos < C.ilimit, wh1, wh2, lane);
             ip += 32;
             continue;
           }
@@ -585,7 +606,7 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
             if (ext < 32) break;
           }
           // tables: window positions before the match ...
-          if (s > ip) insert_stripe(C, ip, min(s - ip, 32u), lane);
+          if (s > ip) insert_hashed(C, ip, (uint32_t)lane < min(s - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
           // ... emit ...
           const uint32_t llen = s - anchor;
           for (uint32_t k = lane; k < llen; k += 32) lits[nlit + k] = chunk[blk_off + anchor + k];

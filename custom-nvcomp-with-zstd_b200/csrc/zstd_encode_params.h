@@ -64,12 +64,16 @@ ZP_HD EncodeParams encode_params_for_level(int level, int checksum) {
   return p;
 }
 
-// multiplicative hashes on the little-endian 8 bytes at a position
+// hashes of the little-endian 8 bytes at a position, built from 32-bit multiplies only (IMAD on the GPU)
 ZP_HD uint32_t hash_short(uint64_t v, int bytes, int log) {
-  if (bytes == 4) return ((uint32_t)v * 2654435761u) >> (32 - log);
-  if (bytes == 5) return (uint32_t)(((v << 24) * 889523592379ull) >> (64 - log));
-  return (uint32_t)(((v << 16) * 227718039650203ull) >> (64 - log));
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  if (bytes == 4) return (lo * 2654435761u) >> (32 - log);
+  if (bytes == 5) return ((lo * 2654435761u) ^ ((hi & 0xFFu) * 2246822519u)) >> (32 - log);
+  return ((lo * 2654435761u) ^ ((hi & 0xFFFFu) * 2246822519u)) >> (32 - log);
 }
-ZP_HD uint32_t hash_long(uint64_t v, int log) { return (uint32_t)((v * 0xCF1BBCDCB7A56463ull) >> (64 - log)); }
+ZP_HD uint32_t hash_long(uint64_t v, int log) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  return ((lo * 2654435761u) + (hi * 2246822519u) * 3266489917u) >> (32 - log);
+}
 
 } // namespace b200zstd
