@@ -770,6 +770,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
   }
 }
 
+// KC grid: a bounded number of resident CTAs per SM, each striding over chunks.  Fewer chunks in flight keep the
+// recently written output (the match sources) inside the 126 MB L2 instead of re-reading it from HBM.
+static int g_exec_ctas_per_sm = 16;
+extern "C" void cuda_zstd_b200_tune_exec_ctas(int v) { if (v > 0) g_exec_ctas_per_sm = v; }
+static uint32_t exec_grid(uint32_t chunks, uint32_t sms) {
+  const uint32_t blocks = (chunks + EXEC_WARPS - 1) / EXEC_WARPS, cap = sms * (uint32_t)g_exec_ctas_per_sm;
+  return blocks < cap ? blocks : cap;
+}
+
 cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, const FastOverlap *ov, int *launches) {
   const uint32_t n = F0.base.n;
   if (launches) *launches = 0;
@@ -797,7 +806,7 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   if (!overlap) {
     const uint32_t kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
     zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
-    zstd_fast_exec_kernel<<<(n + EXEC_WARPS - 1) / EXEC_WARPS, EXEC_WARPS * 32, 0, stream>>>(F);
+    zstd_fast_exec_kernel<<<exec_grid(n, sms), EXEC_WARPS * 32, 0, stream>>>(F);
     count += 2;
   } else {
     for (uint32_t k = 0; k < nsub; k++) {
@@ -806,7 +815,7 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
       zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
       if ((e = cudaEventRecord(ov->ev[k], stream)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(ov->side, ov->ev[k], 0)) != cudaSuccess) return e;
-      zstd_fast_exec_kernel<<<(m + EXEC_WARPS - 1) / EXEC_WARPS, EXEC_WARPS * 32, 0, ov->side>>>(F);
+      zstd_fast_exec_kernel<<<exec_grid(m, sms), EXEC_WARPS * 32, 0, ov->side>>>(F);
       count += 2;
     }
     if ((e = cudaEventRecord(ov->done, ov->side)) != cudaSuccess) return e;

@@ -26,6 +26,7 @@ namespace b200zstd {
 using namespace enc;
 
 constexpr int ENC_THREADS = 32;
+constexpr size_t ENC_SMEM_TABLE_MAX = 4096;             // a hash table larger than this costs more in occupancy than shared memory saves in latency
 
 struct EncScratch {          // layout of one CTA's slice of the global workspace
   static constexpr size_t lits_off = 0;
@@ -34,7 +35,8 @@ struct EncScratch {          // layout of one CTA's slice of the global workspac
   static constexpr size_t of_off = ml_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
   static constexpr size_t chain_off = of_off + (size_t)MAX_SEQ_PER_BLOCK * 4;
   static constexpr size_t bytes_nochain = chain_off + (size_t)64 * 1024;     // room for the long-hash table (<= 2^15 u16) of DFAST
-  static constexpr size_t bytes_chain = chain_off + (size_t)BLOCK_BYTES * 2;
+  static constexpr size_t bytes_chain = chain_off + (size_t)BLOCK_BYTES * 2 + (size_t)64 * 1024;   // chain + room for the primary table
+  static constexpr size_t chain_tab_off = chain_off + (size_t)BLOCK_BYTES * 2;
 };
 
 size_t encode_cta_scratch_bytes(const EncodeParams &p) {
@@ -45,6 +47,7 @@ static size_t encode_smem_bytes(const EncodeParams &p) {
   // only the short table lives in shared memory; the long table of DFAST sits in the CTA's L2-resident scratch
   // (10 -> 19 resident warps per SM; the parse is latency-bound, so occupancy buys more than the slower lookup costs)
   size_t tabs = ((size_t)2 << p.hash_log);
+  if (tabs > ENC_SMEM_TABLE_MAX) tabs = 0;               // big primary tables also live in the CTA's L2-resident scratch
   size_t ent = sizeof(EntropyWs);
   return (tabs > ent ? tabs : ent) + 16;
 }
@@ -74,6 +77,7 @@ struct ParseCtx {
   const uint8_t *chunk;
   uint32_t blk_off, bn, ilimit;
   uint16_t *tab1, *tab2, *chain;
+  bool t1_global;         // tab1 lives in global scratch: L2-only accesses
   EncodeParams P;
 };
 
@@ -155,12 +159,12 @@ __device__ __forceinline__ void insert_hashed(const ParseCtx &C, uint32_t p0, bo
   if (act) {
     const uint32_t lower = g1 & lanemask_lt();
     if (C.chain) {
-      const uint32_t prev = lower ? (p0 + (uint32_t)(31 - __clz(lower))) : (uint32_t)C.tab1[h1];
+      const uint32_t prev = lower ? (p0 + (uint32_t)(31 - __clz(lower))) : (uint32_t)(C.t1_global ? __ldcg(C.tab1 + h1) : C.tab1[h1]);
       C.chain[pos] = (uint16_t)((pos - prev) & 0xFFFF);
     }
   }
   __syncwarp();
-  if (act && (g1 >> lane) == 1u) C.tab1[h1] = (uint16_t)pos;
+  if (act && (g1 >> lane) == 1u) { if (C.t1_global) __stcg(C.tab1 + h1, (uint16_t)pos); else C.tab1[h1] = (uint16_t)pos; }
   if (C.tab2) {
     const uint32_t h2 = act ? h2_in : 0x80000000u + (uint32_t)lane;
     const uint32_t g2 = __match_any_sync(0xffffffffu, h2);
@@ -471,7 +475,11 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
       C.src.w = (const uint32_t *)((uintptr_t)chunk & ~(uintptr_t)3);
       C.src.delta = (uint32_t)((uintptr_t)chunk & 3);
       C.src.last_word = (uint32_t)((n - 1 + C.src.delta) >> 2);
-      C.tab1 = (uint16_t *)smem;
+      C.t1_global = ((size_t)2 << P.hash_log) > ENC_SMEM_TABLE_MAX;
+      // scratch homes: [chain_off, +64 KB) long table (DFAST) or primary table (FAST); chain levels keep the chain there
+      // and the primary table right behind it
+      C.tab1 = !C.t1_global ? (uint16_t *)smem
+                            : (uint16_t *)(scratch + (P.chain_depth > 0 ? EncScratch::chain_tab_off : EncScratch::chain_off + (P.long_log ? 32 * 1024 : 0)));
       C.tab2 = P.long_log ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
       C.chain = P.chain_depth > 0 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
 
@@ -498,9 +506,15 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
         // ---- parse ----
         C.blk_off = blk_off; C.bn = bn; C.ilimit = bn > 8 ? bn - 8 : 0;
         {
-          const uint32_t words = ((uint32_t)2 << P.hash_log) >> 2;
-          uint32_t *z = (uint32_t *)smem;
-          for (uint32_t k = lane; k < words; k += 32) z[k] = 0;
+          if (!C.t1_global) {
+            const uint32_t words = ((uint32_t)2 << P.hash_log) >> 2;
+            uint32_t *z = (uint32_t *)smem;
+            for (uint32_t k = lane; k < words; k += 32) z[k] = 0;
+          } else {
+            uint4 *z1 = (uint4 *)C.tab1;
+            const uint32_t vecs = ((uint32_t)2 << P.hash_log) >> 4;
+            for (uint32_t k = lane; k < vecs; k += 32) __stcg(z1 + k, make_uint4(0, 0, 0, 0));
+          }
           if (C.tab2) {
             uint4 *z2 = (uint4 *)C.tab2;
             const uint32_t vecs = ((uint32_t)2 << P.long_log) >> 4;
@@ -528,7 +542,7 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
                 c2 = (int64_t)((pos & ~0xFFFFu) | __ldcg(C.tab2 + wh2));
                 if (c2 >= (int64_t)pos) c2 -= 0x10000;
               }
-              c1 = (int64_t)((pos & ~0xFFFFu) | C.tab1[wh1]);
+              c1 = (int64_t)((pos & ~0xFFFFu) | (C.t1_global ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
               if (c1 >= (int64_t)pos) c1 -= 0x10000;
               const bool vr = blk_off + pos >= rep[0];
               const uint64_t x2 = c2 >= 0 ? C.src.ld64(blk_off + (uint32_t)c2) : ~v;
@@ -544,7 +558,7 @@ __global__ void __launch_bounds__(ENC_THREADS) zstd_encode_batch_kernel(EncodeAr
                 if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
               }
             } else {
-              int64_t c = (int64_t)((pos & ~0xFFFFu) | C.tab1[wh1]);
+              int64_t c = (int64_t)((pos & ~0xFFFFu) | (C.t1_global ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
               if (c >= (int64_t)pos) c -= 0x10000;
               int depth = P.chain_depth;
               while (depth-- > 0 && c >= 0) {
