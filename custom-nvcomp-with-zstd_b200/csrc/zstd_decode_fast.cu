@@ -323,8 +323,8 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
 // KB: FSE tables in shared memory (one warp per chunk), then one lane per sequence stream
 // =================================================================================================
 constexpr int KB_THREADS = 256, KB_WARPS = KB_THREADS / 32;
-constexpr int KB_GROUP = 40;                                   // chunks per CTA pass: 40 x 5 KB of packed tables
-constexpr int KB_DEC_WARPS = 2, KB_LANES = KB_GROUP / KB_DEC_WARPS;   // 2 decoding warps x 20 lanes
+constexpr int KB_GROUP = 56;                                   // chunks per CTA pass: 56 x 3.75 KB of packed tables
+constexpr int KB_DEC_WARPS = 2, KB_LANES = KB_GROUP / KB_DEC_WARPS;   // 2 decoding warps x 28 lanes
 struct __align__(16) SeqScratch {                              // per-warp scratch for the table build
   int16_t norm[3][64];
   uint8_t item_sym[512];
@@ -333,24 +333,28 @@ struct __align__(16) SeqScratch {                              // per-warp scrat
   uint32_t bits_off, ok;
 };
 struct SeqInfo { uint32_t ready, ll_log, of_log, ml_log, bits_off, bits_len; };
-constexpr size_t KB_TAB_BYTES = 1280 * 4;                      // LL 512 | ML 512 | OF 256 packed 32-bit entries
+constexpr size_t KB_TAB_BYTES = 1280 * 3;                      // LL 512 | ML 512 | OF 256 entries: a uint16 plane and a uint8 plane
 constexpr size_t KB_SMEM = (size_t)KB_GROUP * KB_TAB_BYTES + KB_WARPS * sizeof(SeqScratch) + KB_GROUP * sizeof(SeqInfo) + 96 * 4 + 16;
 
-// packed decode entry: nextStateBase[0:10) | nbBits[10:14) | extraBits[14:19) | symbol[19:25)
-// (the base VALUE of a length code is recomputed from the symbol: it only feeds the output record,
-// not the bit-position chain, and this halves the table so twice as many chunks fit in shared memory)
-__device__ __forceinline__ uint32_t pack_entry(int kind, uint32_t sym, uint32_t next_base, uint32_t nb) {
+// packed decode entry, 24 bits in two planes so that 56 chunks' tables fit in one SM's shared memory:
+//   t16[state] = nextStateBase[0:9) | nbBits[9:13) | extraBits[13:16) (low 3 bits)      t8[state] = extraBits high 2 bits | symbol << 2
+// (nextStateBase < table size <= 512; the base VALUE of a length code is looked up from the symbol in a shared
+// 96-entry table: it only feeds the output record, not the bit-position chain)
+struct SeqTab { uint16_t *t16; uint8_t *t8; };        // one chunk: t16 = [LL 512 | ML 512 | OF 256], t8 likewise
+__device__ __forceinline__ void pack_entry(const SeqTab &T, uint32_t idx, int kind, uint32_t sym, uint32_t next_base, uint32_t nb) {
   const uint32_t xb = kind == 0 ? c_ll_bits[sym] : kind == 1 ? sym : c_ml_bits[sym];
-  return next_base | (nb << 10) | (xb << 14) | (sym << 19);
+  T.t16[idx] = (uint16_t)(next_base | (nb << 9) | ((xb & 7) << 13));
+  T.t8[idx] = (uint8_t)((xb >> 3) | (sym << 2));
 }
-// fse_build_warp (zstd_decode_tables.cuh) emitting packed entries in place
-__device__ inline void fse_build_warp_packed(uint32_t *tab, const int16_t *norm, int max_sym, int log, int kind, uint8_t *item_sym,
-                                             uint16_t *sym_next, int lane) {
+// fse_build_warp (zstd_decode_tables.cuh) emitting packed entries in place; `off` = first entry of this table in the planes
+__device__ inline void fse_build_warp_packed(const SeqTab &T, uint32_t off, const int16_t *norm, int max_sym, int log, int kind,
+                                             uint8_t *item_sym, uint16_t *sym_next, int lane) {
   const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+  uint8_t *cell = T.t8 + off;                       // the byte plane doubles as the symbol-of-cell scratch
   int high = size - 1, acc = 0;
   for (int s = 0; s <= max_sym; s++) {
     const int c = norm[s];
-    if (c == -1) { if (lane == 0) { tab[high] = (uint32_t)s; sym_next[s] = 1; } high--; }
+    if (c == -1) { if (lane == 0) { cell[high] = (uint8_t)s; sym_next[s] = 1; } high--; }
     else {
       if (lane == 0) sym_next[s] = (uint16_t)c;
       for (int k = lane; k < c; k += 32) item_sym[acc + k] = (uint8_t)s;
@@ -363,20 +367,20 @@ __device__ inline void fse_build_warp_packed(uint32_t *tab, const int16_t *norm,
     const int pos = ((j0 + lane) * step) & mask;
     const bool ok = pos <= high;
     const uint32_t b = __ballot_sync(0xffffffffu, ok);
-    if (ok) tab[pos] = item_sym[run + __popc(b & lanemask_lt())];
+    if (ok) cell[pos] = item_sym[run + __popc(b & lanemask_lt())];
     run += __popc(b);
   }
   __syncwarp();
   for (int u0 = 0; u0 < size; u0 += 32) {
     const int u = u0 + lane;
-    const uint32_t s = tab[u];
+    const uint32_t s = cell[u];
     const uint32_t m = __match_any_sync(0xffffffffu, s);
     const uint32_t x = (uint32_t)sym_next[s] + __popc(m & lanemask_lt());
     __syncwarp();
     if ((m >> lane) == 1u) sym_next[s] = (uint16_t)((uint32_t)sym_next[s] + __popc(m));
     __syncwarp();
     const uint32_t nb = (uint32_t)(log - highbit32(x));
-    tab[u] = pack_entry(kind, s, (x << nb) - (uint32_t)size, nb);
+    pack_entry(T, off + (uint32_t)u, kind, s, (x << nb) - (uint32_t)size, nb);
   }
   __syncwarp();
 }
@@ -409,8 +413,10 @@ struct SeqBits {                       // backward reader specialised for the se
 };
 __device__ __forceinline__ uint32_t top_bits(uint32_t hi, int skip, int n) { return ((hi << skip) >> 1) >> (31 - n); }   // n in [0,31]
 
-__device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const uint32_t *llt, const uint32_t *oft,
-                                                      const uint32_t *mlt, const uint32_t *bases, const SeqInfo &I) {
+__device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
+                                                      const SeqInfo &I) {
+  const uint16_t *const ll16 = T.t16, *const ml16 = T.t16 + 512, *const of16 = T.t16 + 1024;
+  const uint8_t *const ll8 = T.t8, *const ml8 = T.t8 + 512, *const of8 = T.t8 + 1024;
   const uint32_t nseq = D->nseq, cap = D->cap, lit_size = D->lit_size;
   uint32_t out_pos = 0, lit_pos = 0, err = ST_OK;
   BackBits b0;
@@ -426,14 +432,15 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8, bad = 0, big = 0;
     const uint32_t *line_mark = b.wp;
     for (uint32_t i = 0; i < nseq; i++) {
-      const uint32_t eo = oft[so], em = mlt[sm], el = llt[sl];
+      const uint32_t eo = of16[so], em = ml16[sm], el = ll16[sl];
+      const uint32_t eo8 = of8[so], em8 = ml8[sm], el8 = ll8[sl];
       // lanes of a warp stall together: pull the next cache line of this lane's bitstream long before its words are needed
       if (b.wp <= line_mark) {
         line_mark = b.wp - 32;
         if (line_mark >= b.floor) asm volatile("prefetch.global.L1 [%0];" ::"l"(line_mark));
       }
       b.refill();
-      const int ob = (int)((eo >> 14) & 31), mb = (int)((em >> 14) & 31), lb = (int)((el >> 14) & 31);
+      const int ob = (int)((eo >> 13) | ((eo8 & 3) << 3)), mb = (int)((em >> 13) | ((em8 & 3) << 3)), lb = (int)((el >> 13) | ((el8 & 3) << 3));
       const int xb = ob + mb + lb;
       uint32_t ov, mx, lx;
       if (xb <= 31) {                                   // the usual case: all extra bits are in the top word
@@ -449,18 +456,18 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
       }
       b.refill();
       {
-        const int nl = (int)((el >> 10) & 15), nm = (int)((em >> 10) & 15), no = (int)((eo >> 10) & 15);   // <= 26 bits together
+        const int nl = (int)((el >> 9) & 15), nm = (int)((em >> 9) & 15), no = (int)((eo >> 9) & 15);   // <= 26 bits together
         const uint32_t hi = (uint32_t)(b.win >> 32);
         const uint32_t last = (i + 1 == nseq) ? 0u : ~0u;                                                     // no state update after the last sequence
-        sl = (el & 1023) + (top_bits(hi, 0, nl) & last);
-        sm = (em & 1023) + (top_bits(hi, nl, nm) & last);
-        so = (eo & 1023) + (top_bits(hi, nl + nm, no) & last);
+        sl = (el & 511) + (top_bits(hi, 0, nl) & last);
+        sm = (em & 511) + (top_bits(hi, nl, nm) & last);
+        so = (eo & 511) + (top_bits(hi, nl + nm, no) & last);
         const int ns = (nl + nm + no) & (int)last;
         b.win <<= ns; b.avail -= ns;
       }
       // ---- off the chain: values, repeat offsets, positions ----
       ov += 1u << ob;
-      const uint32_t ll = bases[el >> 19] + lx, ml = bases[40 + (em >> 19)] + mx;
+      const uint32_t ll = bases[el8 >> 2] + lx, ml = bases[40 + (em8 >> 2)] + mx;
       uint32_t offset;
       if (ov > 3) { offset = ov - 3; rep2 = rep1; rep1 = rep0; rep0 = offset; }
       else {
@@ -484,10 +491,11 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
   D->seq_status = err; D->out_end = out_pos; D->lit_end = lit_pos;
 }
 
-__global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArgs F) {
+__global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecodeArgs F) {
   extern __shared__ __align__(16) uint8_t kb_smem[];
   __shared__ uint32_t s_group;
-  uint32_t *const tables = reinterpret_cast<uint32_t *>(kb_smem);                            // [KB_GROUP][1280]: LL 512 | ML 512 | OF 256
+  uint16_t *const tab16 = reinterpret_cast<uint16_t *>(kb_smem);                             // [KB_GROUP][1280]: LL 512 | ML 512 | OF 256
+  uint8_t *const tab8 = kb_smem + (size_t)KB_GROUP * 1280 * 2;                               // [KB_GROUP][1280]
   SeqScratch *const scratch = reinterpret_cast<SeqScratch *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES);
   SeqInfo *const info = reinterpret_cast<SeqInfo *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES + KB_WARPS * sizeof(SeqScratch));
   uint32_t *const bases = reinterpret_cast<uint32_t *>(info + KB_GROUP);                      // [0,36) LL bases, [40,93) ML bases
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArg
       const uint32_t chunk = g0 + c;
       ChunkSlot slot = slot_of(F, chunk);
       FastDesc *D = slot.desc();
-      uint32_t *llt = tables + (size_t)c * 1280, *mlt = llt + 512, *oft = llt + 1024;
+      const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
       if (lane == 0) info[c].ready = 0;
       if (D->state != 0) continue;                                                            // uniform per warp
       const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
@@ -552,9 +560,9 @@ __global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArg
         continue;
       }
       for (int t = 0; t < 3; t++) {
-        uint32_t *tab = (t == 0) ? llt : (t == 1) ? oft : mlt;
-        if (S.tab_mode[t] == 1) { if (lane == 0) tab[0] = pack_entry(t, (uint32_t)S.tab_max[t], 0, 0); }
-        else fse_build_warp_packed(tab, S.norm[t], S.tab_max[t], S.tab_log[t], t, S.item_sym, S.sym_next, lane);
+        const uint32_t toff = (t == 0) ? 0u : (t == 1) ? 1024u : 512u;
+        if (S.tab_mode[t] == 1) { if (lane == 0) pack_entry(T, toff, t, (uint32_t)S.tab_max[t], 0, 0); }
+        else fse_build_warp_packed(T, toff, S.norm[t], S.tab_max[t], S.tab_log[t], t, S.item_sym, S.sym_next, lane);
         __syncwarp();
       }
       if (lane == 0) {
@@ -570,8 +578,8 @@ __global__ void __launch_bounds__(KB_THREADS) zstd_fast_seq_kernel(FastDecodeArg
       const uint32_t c = (uint32_t)warp * KB_LANES + (uint32_t)lane, chunk = g0 + c;
       if (chunk < F.hi && info[c].ready) {
         ChunkSlot slot = slot_of(F, chunk);
-        const uint32_t *llt = tables + (size_t)c * 1280;
-        fast_decode_sequences((const uint8_t *)A.in_ptrs[chunk], slot.desc(), slot.seqs(), llt, llt + 1024, llt + 512, bases, info[c]);
+        const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
+        fast_decode_sequences((const uint8_t *)A.in_ptrs[chunk], slot.desc(), slot.seqs(), T, bases, info[c]);
       }
     }
     __syncthreads();
