@@ -673,21 +673,28 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
       else { L.base = src + D->lit_src; L.seg = 0; L.pad = 0; L.mode = D->lit_type; }
       const uint4 *__restrict__ seqs = slot.seqs();
       const uintptr_t out_addr = (uintptr_t)out;
+      // records of the first group (the sentinel at index nseq is fetched like a record: it ends the last literal run)
+      uint4 r_nxt = make_uint4(0, 0, 0, 0);
+      if ((uint32_t)lane <= nseq) r_nxt = __ldcs(seqs + lane);
       for (uint32_t g0 = 0; g0 < nseq; g0 += 32) {
         const uint32_t i = g0 + (uint32_t)lane;
         const bool valid = i < nseq;
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (valid) r = __ldcs(seqs + i);
-        // literal length = next record's literal position - mine (lane 31 / the last sequence fetch it)
+        const uint4 r = r_nxt;
+        // next group's records are requested now and used one iteration later (hides one memory round trip per group)
+        r_nxt = make_uint4(0, 0, 0, 0);
+        if (i + 32 <= nseq) r_nxt = __ldcs(seqs + i + 32);
+        // literal length = next record's literal position - mine
         uint32_t next_lit = __shfl_down_sync(0xffffffffu, r.y, 1);
-        if (valid && (lane == 31 || i + 1 == nseq)) next_lit = __ldcs(seqs + i + 1).y;
+        const uint32_t nl0 = __shfl_sync(0xffffffffu, r_nxt.y, 0);
+        if (lane == 31) next_lit = nl0;
         const uint32_t ll = valid ? next_lit - r.y : 0;
         const uint32_t group_start = __shfl_sync(0xffffffffu, r.x, 0);
         const uint32_t d = r.x + ll;
         const bool indep = valid && (d - r.z + r.w <= group_start);            // whole source precedes this group's output
         // ---- piece-parallel phase: the literal run of every sequence and every independent match are cut into
         // destination-aligned 16-byte pieces; pieces are dealt to lanes round-robin, so the work per lane is
-        // uniform whatever the length distribution, and each round costs one memory round trip ----
+        // uniform whatever the length distribution.  Two pieces per lane are in flight per round: all loads of a
+        // round are issued before the first store, so a round costs one memory round trip ----
         const uint32_t mlen = indep ? r.w : 0u;
         const uint32_t ca = ll ? (uint32_t)(((out_addr + r.x + ll - 1) >> 4) - ((out_addr + r.x) >> 4)) + 1 : 0u;
         const uint32_t cb = mlen ? (uint32_t)(((out_addr + d + mlen - 1) >> 4) - ((out_addr + d) >> 4)) + 1 : 0u;
@@ -695,9 +702,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const uint32_t excl = incl - (ca + cb), total = __shfl_sync(0xffffffffu, incl, 31);
-        for (uint32_t q0 = 0; q0 < total; q0 += 32) {
-          const uint32_t q = q0 + (uint32_t)lane;
-          // owner j = last lane whose exclusive prefix is <= q
+        struct Piece { uint8_t *dp; uint32_t nb, sh, w0, w1, w2, w3, w4; };
+        // all 32 lanes call (shuffles inside); q >= total yields an empty piece
+        auto fetch = [&](uint32_t q) -> Piece {
+          Piece P{nullptr, 0, 0, 0, 0, 0, 0, 0};
           uint32_t j = 0;
 #pragma unroll
           for (int st = 16; st; st >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, excl, (j + st) & 31); if (j + st < 32 && pj <= q) j += st; }
@@ -713,8 +721,6 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
             const uintptr_t lo = a0 > (blk << 4) ? a0 : (blk << 4);
             const uintptr_t hi = (a0 + len) < ((blk + 1) << 4) ? (a0 + len) : ((blk + 1) << 4);
             const uint32_t nb = (uint32_t)(hi - lo), rel = (uint32_t)(lo - a0);
-            // 16 source bytes -> v[0..3]
-            uint32_t v0, v1, v2, v3;
             const uint8_t *sp = nullptr;
             if (is_match) sp = out + a - jz + rel;
             else {
@@ -722,29 +728,41 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
               sp = L.run(jy + rel, nb, &contig);
               if (!contig) sp = nullptr;
             }
+            P.dp = reinterpret_cast<uint8_t *>(lo);
+            P.nb = nb;
             if (sp) {
               const uintptr_t s = (uintptr_t)sp;
               const uint32_t *wbase = reinterpret_cast<const uint32_t *>(s & ~(uintptr_t)3);
-              const uint32_t sh = (uint32_t)(s & 3) * 8, lastw = (uint32_t)(((s + nb - 1) >> 2) - (s >> 2));
-              const uint32_t w0 = wbase[0], w1 = wbase[min(1u, lastw)], w2 = wbase[min(2u, lastw)], w3 = wbase[min(3u, lastw)],
-                             w4 = wbase[min(4u, lastw)];
-              v0 = __funnelshift_r(w0, w1, sh); v1 = __funnelshift_r(w1, w2, sh); v2 = __funnelshift_r(w2, w3, sh); v3 = __funnelshift_r(w3, w4, sh);
+              const uint32_t lastw = (uint32_t)(((s + nb - 1) >> 2) - (s >> 2));
+              P.sh = (uint32_t)(s & 3) * 8;
+              P.w0 = wbase[0]; P.w1 = wbase[min(1u, lastw)]; P.w2 = wbase[min(2u, lastw)]; P.w3 = wbase[min(3u, lastw)]; P.w4 = wbase[min(4u, lastw)];
             } else {
-              // RLE literals or a piece straddling two Huffman segments: byte gather
+              // RLE literals or a piece straddling two Huffman segments: byte gather (already shifted into place)
               uint32_t t[4] = {0, 0, 0, 0};
               for (uint32_t u = 0; u < nb; u++) t[u >> 2] |= (uint32_t)L.at(jy + rel + u) << (8 * (u & 3));
-              v0 = t[0]; v1 = t[1]; v2 = t[2]; v3 = t[3];
-            }
-            uint8_t *dp = reinterpret_cast<uint8_t *>(lo);
-            if (nb == 16) *reinterpret_cast<uint4 *>(dp) = make_uint4(v0, v1, v2, v3);
-            else {
-#pragma unroll
-              for (int u = 0; u < 15; u++) {
-                const uint32_t word = u < 4 ? v0 : u < 8 ? v1 : u < 12 ? v2 : v3;
-                if ((uint32_t)u < nb) dp[u] = (uint8_t)(word >> (8 * (u & 3)));
-              }
+              P.sh = 0; P.w0 = t[0]; P.w1 = t[1]; P.w2 = t[2]; P.w3 = t[3]; P.w4 = 0;
             }
           }
+          return P;
+        };
+        auto store = [&](const Piece &P) {
+          if (P.nb == 0) return;
+          const uint32_t v0 = __funnelshift_r(P.w0, P.w1, P.sh), v1 = __funnelshift_r(P.w1, P.w2, P.sh), v2 = __funnelshift_r(P.w2, P.w3, P.sh),
+                         v3 = __funnelshift_r(P.w3, P.w4, P.sh);
+          if (P.nb == 16) *reinterpret_cast<uint4 *>(P.dp) = make_uint4(v0, v1, v2, v3);
+          else {
+#pragma unroll
+            for (int u = 0; u < 15; u++) {
+              const uint32_t word = u < 4 ? v0 : u < 8 ? v1 : u < 12 ? v2 : v3;
+              if ((uint32_t)u < P.nb) P.dp[u] = (uint8_t)(word >> (8 * (u & 3)));
+            }
+          }
+        };
+        for (uint32_t q0 = 0; q0 < total; q0 += 64) {
+          const Piece pa = fetch(q0 + (uint32_t)lane);
+          const Piece pb = fetch(q0 + 32 + (uint32_t)lane);
+          store(pa);
+          store(pb);
         }
         __syncwarp();
         // ---- matches that read this group's own output: in sequence order, the whole warp on each ----
