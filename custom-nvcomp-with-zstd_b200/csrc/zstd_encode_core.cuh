@@ -347,12 +347,13 @@ ZHDN void huf_assign_codes(const uint8_t *len, int max_sym, int table_log, uint1
 struct EntropyWs {
   uint32_t count[256];        // literal histogram, then per-alphabet sequence histograms
   uint32_t hufc[256];         // Huffman code | length << 16
-  uint32_t ncount[512];
-  uint16_t parent[512];
+  union {                     // the Huffman tree builder's node arrays are dead before any FSE table is built
+    struct { uint32_t ncount[512]; uint16_t parent[512]; };
+    uint16_t state_tab[3][512];   // LL, OF, ML compression state tables ([0] also serves the Huffman-weight FSE)
+  };
   uint16_t order[256];
   uint8_t huflen[256];
   uint8_t weights[256];
-  uint16_t state_tab[3][512]; // LL, OF, ML compression state tables
   SymTT tt[3][64];
   int16_t norm[64];
   uint16_t cumul[64];
