@@ -335,7 +335,7 @@ __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits, uint32
   if (lane < 3) {
     const int t = lane;
     const int log = W.tab_log[t];
-    const uint16_t *st = W.state_tab[t];
+    const uint16_t *st = W.state_tab(t);
     const SymTT *tt = W.tt[t];
     uint32_t *arr = t == 0 ? sll : t == 1 ? sofv : sml;
     uint32_t state = 0;
@@ -437,7 +437,7 @@ __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits, uint32
   return op + nbytes;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
+__global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_chunk;
   const int lane = threadIdx.x;
@@ -685,10 +685,13 @@ cudaError_t launch_encode_batch(const EncodeArgs &args, int grid, cudaStream_t s
   return cudaGetLastError();
 }
 
+static int g_enc_ctas_cap = 0;                      // 0 = whatever fits; tools/tune_enc.py sweeps it
 int encode_ctas_per_sm(const EncodeParams &prm) {
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel, ENC_THREADS, encode_smem_bytes(prm)) != cudaSuccess || n < 1) n = 8;
+  if (g_enc_ctas_cap > 0 && n > g_enc_ctas_cap) n = g_enc_ctas_cap;
   return n;
 }
 
 } // namespace b200zstd
+extern "C" void cuda_zstd_b200_tune_enc_ctas(int v) { b200zstd::g_enc_ctas_cap = v; }

@@ -345,21 +345,27 @@ ZHDN void huf_assign_codes(const uint8_t *len, int max_sym, int table_log, uint1
 
 // ---- entropy-stage workspace (lives in shared memory in the kernel) --------------------------------
 struct EntropyWs {
+  // 6.0 KB, laid out by lifetime so that 32 one-warp CTAs fit an SM.  Three phases share the storage:
+  //   tree build   : count, ncount, parent, order -> huflen
+  //   table write  : huflen, weights, hufc + the FSE set of the weights (st_ll, tt[0], cell, norm, cumul)
+  //   sequences    : count[0..63], st_ll/st_of/st_ml, tt, cell, norm, cumul
   uint32_t count[256];        // literal histogram, then per-alphabet sequence histograms
-  uint32_t hufc[256];         // Huffman code | length << 16
-  union {                     // the Huffman tree builder's node arrays are dead before any FSE table is built
-    struct { uint32_t ncount[512]; uint16_t parent[512]; };
-    uint16_t state_tab[3][512];   // LL, OF, ML compression state tables ([0] also serves the Huffman-weight FSE)
+  union {
+    struct { uint32_t ncount[512]; uint16_t parent[512]; };            // tree-build node arrays
+    struct { uint16_t st_ll[512]; SymTT tt[3][64]; uint8_t cell[512]; };
   };
-  uint16_t order[256];
-  uint8_t huflen[256];
-  uint8_t weights[256];
-  SymTT tt[3][64];
-  int16_t norm[64];
-  uint16_t cumul[64];
-  uint8_t cell[512];
+  union {
+    struct { uint32_t hufc[256];                                       // Huffman code | length << 16
+             uint8_t huflen[256]; uint8_t weights[256];
+             uint16_t order[256]; };                                   // dead before the table is written
+    struct { uint16_t st_ml[512];
+             uint16_t st_of[256];                                      // offset tables never exceed 2^8 states
+             int16_t norm[64]; uint16_t cumul[64]; };
+  };
   int tab_log[3];
+  ZHD uint16_t *state_tab(int kind) { return kind == 0 ? st_ll : kind == 1 ? st_of : st_ml; }   // LL, OF, ML
 };
+static_assert(sizeof(EntropyWs) <= 6160, "EntropyWs must stay small enough for 32 CTAs per SM");
 
 // Huffman tree description (RFC 8878 4.2.1): FSE-compressed weights when that is smaller, else
 // direct 4-bit weights.  Returns bytes written, 0 when the table cannot be represented.
@@ -388,7 +394,7 @@ ZHDN uint32_t huf_write_table(EntropyWs &W, int max_sym, int table_log, uint8_t 
         const uint32_t body_cap = cap - 1 < 127 ? cap - 1 : 127;
         uint32_t h = fse_write_ncount(body, body_cap, norm, max_w, log);
         if (h) {
-          uint16_t *st = W.state_tab[0];
+          uint16_t *st = W.state_tab(0);
           SymTT *tt = W.tt[0];
           fse_build_ctable(norm, max_w, log, st, tt, W.cell, W.cumul);
           BitW bw;
@@ -477,7 +483,7 @@ ZHDN int seq_table_prepare(EntropyWs &W, int kind, const uint32_t *count, int ma
     dst[0] = (uint8_t)only;
     *desc_bytes = 1;
     W.tab_log[kind] = 0;
-    W.state_tab[kind][0] = 0; W.state_tab[kind][1] = 0;
+    W.state_tab(kind)[0] = 0; W.state_tab(kind)[1] = 0;
     for (int s = 0; s < 64; s++) { W.tt[kind][s].delta_nb = 0; W.tt[kind][s].delta_state = 0; }
     return 1;
   }
@@ -507,13 +513,13 @@ ZHDN int seq_table_prepare(EntropyWs &W, int kind, const uint32_t *count, int ma
     }
   }
   if (cmp_ok && (!def_ok || cmp_cost < def_cost)) {
-    fse_build_ctable(W.norm, max_code_present, log, W.state_tab[kind], W.tt[kind], W.cell, W.cumul);
+    fse_build_ctable(W.norm, max_code_present, log, W.state_tab(kind), W.tt[kind], W.cell, W.cumul);
     W.tab_log[kind] = log;
     *desc_bytes = hdr;
     return 2;
   }
   if (!def_ok) return -1;
-  fse_build_ctable(dnorm, dmax, dlog, W.state_tab[kind], W.tt[kind], W.cell, W.cumul);
+  fse_build_ctable(dnorm, dmax, dlog, W.state_tab(kind), W.tt[kind], W.cell, W.cumul);
   W.tab_log[kind] = dlog;
   return 0;
 }
@@ -534,7 +540,7 @@ ZHD uint32_t seq_count_header(uint8_t *dst, uint32_t nseq) {
 ZHDN uint32_t seq_encode_stream(const EntropyWs &W, const SeqStore &S, uint32_t nseq, uint8_t *dst, uint32_t cap) {
   BitW bw;
   bw.init(dst, dst + cap);
-  const uint16_t *st_ll = W.state_tab[0], *st_of = W.state_tab[1], *st_ml = W.state_tab[2];
+  const uint16_t *st_ll = W.st_ll, *st_of = W.st_of, *st_ml = W.st_ml;
   const SymTT *tt_ll = W.tt[0], *tt_of = W.tt[1], *tt_ml = W.tt[2];
   uint32_t i = nseq - 1;
   uint32_t llc = ll_code(S.ll[i]), mlc = ml_code(S.ml[i]), ofc = (uint32_t)hb32(S.ofv[i]);
