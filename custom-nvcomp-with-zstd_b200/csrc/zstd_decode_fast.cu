@@ -397,21 +397,17 @@ __device__ __forceinline__ uint32_t ml_base_of(uint32_t c) {
 // fields are cut out of the top 32 bits of the window with 32-bit shifts, base values come from a
 // 96-entry shared table, validation accumulates into one flag (a bad stream keeps decoding harmlessly;
 // KC never executes a chunk whose seq_status is set), and bit accounting happens once at the end.
-struct SeqBits {                       // backward reader specialised for the sequence loop (see BackBits)
-  const uint32_t *wp, *floor;
-  uint64_t win;
-  uint32_t nextw;
-  int avail;
-  __device__ __forceinline__ void refill() {
-    if (avail <= 32) {
-      win |= (uint64_t)nextw << (32 - avail);
-      avail += 32;
-      wp--;
-      nextw = (wp >= floor) ? *wp : 0u;
-    }
-  }
-};
+// ---- sequence loop bit reader: an absolute bit position instead of a shifting window -------------------------------------
+// The backward bitstream is addressed as bits of the 4-byte-aligned word array W that contains it; `t` is the index of the
+// first bit already consumed (exclusive top), `low` the index of the stream's first bit.  Every sequence loads the three words
+// under `t` (L1 hits; the loads issue together with the table lookups) and cuts all six fields out of them with funnel
+// shifts.  There is no refill branch and no window state on the dependency chain: in a warp whose lanes each walk their own
+// stream, the three divergent refill regions of a shifting window cost a quarter of the loop's instructions.
 __device__ __forceinline__ uint32_t top_bits(uint32_t hi, int skip, int n) { return ((hi << skip) >> 1) >> (31 - n); }   // n in [0,31]
+__device__ __forceinline__ uint32_t peek32(const uint32_t *W, int t) {             // bits [t-32, t) of the stream, t may be anything
+  const int k = max(t >> 5, 0);
+  return __funnelshift_r(W[k - 1], W[k], (uint32_t)t & 31u);
+}
 
 __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
                                                       const SeqInfo &I) {
@@ -419,72 +415,69 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
   const uint8_t *const ll8 = T.t8, *const ml8 = T.t8 + 512, *const of8 = T.t8 + 1024;
   const uint32_t nseq = D->nseq, cap = D->cap, lit_size = D->lit_size;
   uint32_t out_pos = 0, lit_pos = 0, err = ST_OK;
-  BackBits b0;
-  if (!b0.init(src + I.bits_off, I.bits_len)) err = ST_CORRUPT;
+  const uint8_t *const p = src + I.bits_off;
+  const uint32_t nb = I.bits_len;
+  // W[-1], W[-2] are read under the first stream bits: a fast-path frame has >= 12 header bytes before the bitstream
+  if (nb == 0 || I.bits_off < 12 || p[nb - 1] == 0) err = ST_CORRUPT;
   else {
-    b0.refill();
-    uint32_t sl = b0.read((int)I.ll_log), so = b0.read((int)I.of_log);
-    b0.refill();
-    uint32_t sm = b0.read((int)I.ml_log);
-    SeqBits b{b0.wp, b0.floor, b0.win, b0.nextw, b0.avail};
-    const uint32_t *const wp0 = b0.wp;                                             // for the final bit accounting
-    const int avail0 = b0.avail;
+    const uint32_t *const W = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    const int d = (int)((uintptr_t)p & 3), low = 8 * d;
+    int t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);       // the sentinel bit itself is not payload
+    uint32_t sl, so, sm;
+    { const uint32_t a = peek32(W, t); sl = top_bits(a, 0, (int)I.ll_log); so = top_bits(a, (int)I.ll_log, (int)I.of_log);
+      sm = top_bits(a, (int)(I.ll_log + I.of_log), (int)I.ml_log); t -= (int)(I.ll_log + I.of_log + I.ml_log); }
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8, bad = 0, big = 0;
-    const uint32_t *line_mark = b.wp;
+    int mark = (t >> 5) + 1;
     for (uint32_t i = 0; i < nseq; i++) {
       const uint32_t eo = of16[so], em = ml16[sm], el = ll16[sl];
       const uint32_t eo8 = of8[so], em8 = ml8[sm], el8 = ll8[sl];
+      const int k = max(t >> 5, 0);
+      const uint32_t sh = (uint32_t)t & 31u;
+      const uint32_t w0 = W[k], w1 = W[k - 1], w2 = W[k - 2];
       // lanes of a warp stall together: pull the next cache line of this lane's bitstream long before its words are needed
-      if (b.wp <= line_mark) {
-        line_mark = b.wp - 32;
-        if (line_mark >= b.floor) asm volatile("prefetch.global.L1 [%0];" ::"l"(line_mark));
+      if (k <= mark) {
+        mark = k - 32;
+        if (mark >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + mark));
       }
-      b.refill();
+      const uint32_t A = __funnelshift_r(w1, w0, sh), B = __funnelshift_r(w2, w1, sh);     // bits [t-32,t) and [t-64,t-32)
       const int ob = (int)((eo >> 13) | ((eo8 & 3) << 3)), mb = (int)((em >> 13) | ((em8 & 3) << 3)), lb = (int)((el >> 13) | ((el8 & 3) << 3));
       const int xb = ob + mb + lb;
-      uint32_t ov, mx, lx;
+      uint32_t ov, mx, lx, S;                            // S = the 32 bits after the extra bits: the three state updates (<= 26 bits)
       if (xb <= 31) {                                   // the usual case: all extra bits are in the top word
-        const uint32_t hi = (uint32_t)(b.win >> 32);
-        ov = top_bits(hi, 0, ob); mx = top_bits(hi, ob, mb); lx = top_bits(hi, ob + mb, lb);
-        b.win <<= xb; b.avail -= xb;
+        ov = top_bits(A, 0, ob); mx = top_bits(A, ob, mb); lx = top_bits(A, ob + mb, lb);
+        S = __funnelshift_l(B, A, (uint32_t)xb);
       } else {
-        ov = (uint32_t)((b.win >> 1) >> (63 - ob)); b.win <<= ob; b.avail -= ob;
-        b.refill();
-        const uint32_t hi = (uint32_t)(b.win >> 32);
-        mx = top_bits(hi, 0, mb); lx = top_bits(hi, mb, lb);
-        b.win <<= (mb + lb); b.avail -= mb + lb;
+        ov = top_bits(A, 0, ob);
+        const uint32_t a2 = peek32(W, t - ob);
+        mx = top_bits(a2, 0, mb); lx = top_bits(a2, mb, lb);
+        S = peek32(W, t - xb);
       }
-      b.refill();
       {
         const int nl = (int)((el >> 9) & 15), nm = (int)((em >> 9) & 15), no = (int)((eo >> 9) & 15);   // <= 26 bits together
-        const uint32_t hi = (uint32_t)(b.win >> 32);
         const uint32_t last = (i + 1 == nseq) ? 0u : ~0u;                                                     // no state update after the last sequence
-        sl = (el & 511) + (top_bits(hi, 0, nl) & last);
-        sm = (em & 511) + (top_bits(hi, nl, nm) & last);
-        so = (eo & 511) + (top_bits(hi, nl + nm, no) & last);
-        const int ns = (nl + nm + no) & (int)last;
-        b.win <<= ns; b.avail -= ns;
+        sl = (el & 511) + (top_bits(S, 0, nl) & last);
+        sm = (em & 511) + (top_bits(S, nl, nm) & last);
+        so = (eo & 511) + (top_bits(S, nl + nm, no) & last);
+        t -= xb + ((nl + nm + no) & (int)last);
       }
-      // ---- off the chain: values, repeat offsets, positions ----
+      // ---- off the chain: values, repeat offsets (branch-free), positions ----
       ov += 1u << ob;
       const uint32_t ll = bases[el8 >> 2] + lx, ml = bases[40 + (em8 >> 2)] + mx;
-      uint32_t offset;
-      if (ov > 3) { offset = ov - 3; rep2 = rep1; rep1 = rep0; rep0 = offset; }
-      else {
-        const uint32_t idx = ov - 1 + (ll == 0);
-        const uint32_t cand = idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-        if (idx != 0) { if (idx != 1) rep2 = rep1; rep1 = rep0; rep0 = cand; }
-        offset = cand;
-      }
+      // idx: 0 keeps the history, 1 swaps rep0/rep1, >= 2 rotates all three; a new offset rotates like idx 3
+      const bool fresh = ov > 3;
+      const uint32_t idx = fresh ? 3u : ov - 1 + (ll == 0);
+      const uint32_t cand = fresh ? ov - 3 : idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
+      rep2 = idx >= 2 ? rep1 : rep2;
+      rep1 = idx >= 1 ? rep0 : rep1;
+      rep0 = cand;
+      const uint32_t offset = cand;
       bad |= (offset == 0) | (lit_pos + ll > lit_size) | (offset > out_pos + ll);
       __stcs(out + i, make_uint4(out_pos, lit_pos, offset, ml));
       out_pos += ll + ml; lit_pos += ll;
       big |= out_pos > cap;
       // positions stay bounded even on garbage: a set flag stops KC from using them, and they cannot wrap within 65536 sequences
     }
-    // bit accounting: consumed = bits that entered the window - bits still in it
-    const int entered = avail0 + 32 * (int)(wp0 - b.wp);
-    if (entered - b.avail != b0.left) bad |= 1;          // the stream must end exactly (b0.left = payload bits after the initial states)
+    if (t != low) bad |= 1;                               // the stream must end exactly on its first bit
     if (bad) err = ST_CORRUPT; else if (big) err = ST_BUFFER_TOO_SMALL;
   }
   out[nseq] = make_uint4(out_pos, lit_pos, 0, 0);           // sentinel: literal length of the last sequence, block totals

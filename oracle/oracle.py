@@ -34,6 +34,7 @@ class FrameInfo(C.Structure):
         ("n_blocks", C.c_uint32), ("n_raw", C.c_uint32), ("n_rle", C.c_uint32), ("n_comp", C.c_uint32),
         ("lit_mode", C.c_uint32 * 4), ("seq_mode", (C.c_uint32 * 4) * 3),
         ("n_seq", C.c_uint64), ("n_lit", C.c_uint64),
+        ("seq_log", (C.c_uint32 * 10) * 3),
     ]
 
 

@@ -451,6 +451,7 @@ typedef struct {
   /* statistics for the inspector */
   u32 n_blocks, n_raw, n_rle, n_comp, lit_mode[4], seq_mode[3][4];
   u64 n_seq, n_lit;
+  u32 seq_log[3][10];  /* blocks per accuracy log of the table in use, [LL,OF,ML][log] */
 } dctx;
 
 /* returns bytes consumed from src for this table description, or negative */
@@ -553,6 +554,7 @@ static int decode_block(dctx *D, const u8 *src, size_t n, u8 *out_base, size_t o
       r = seq_table_setup(&D->of, (modes >> 4) & 3, src + ip, n - ip, OF_DEF, 28, 5, 31, 8); if (r < 0) return r; ip += (size_t)r;
       r = seq_table_setup(&D->ml, (modes >> 2) & 3, src + ip, n - ip, ML_DEF, 52, 6, 52, 9); if (r < 0) return r; ip += (size_t)r;
       if (ip >= n) return -ORC_CORRUPT;
+      D->seq_log[0][D->ll.log]++; D->seq_log[1][D->of.log]++; D->seq_log[2][D->ml.log]++;
       if (bb_init(&b, src + ip, n - ip) < 0) return -ORC_CORRUPT;
       sl = bb_read(&b, D->ll.log); so = bb_read(&b, D->of.log); sm = bb_read(&b, D->ml.log);
       for (i = 0; i < nseq; i++) {
@@ -610,6 +612,7 @@ typedef struct {
   u32 lit_mode[4];       /* raw, rle, compressed, treeless */
   u32 seq_mode[3][4];    /* [LL,OF,ML][predefined,rle,compressed,repeat] */
   u64 n_seq, n_lit;
+  u32 seq_log[3][10];    /* blocks per accuracy log of the sequence table in use, [LL,OF,ML][log 0..9] */
 } orc_frame_info;
 
 /* Decode every frame in [src, src+n) (skippable frames are skipped, concatenated frames appended).
@@ -717,6 +720,7 @@ int orc_decompress(const u8 *src, size_t n, u8 *dst, size_t cap, size_t *out_siz
     info->n_seq = D->n_seq; info->n_lit = D->n_lit;
     for (a = 0; a < 4; a++) info->lit_mode[a] = D->lit_mode[a];
     for (a = 0; a < 3; a++) for (c = 0; c < 4; c++) info->seq_mode[a][c] = D->seq_mode[a][c];
+    for (a = 0; a < 3; a++) for (c = 0; c < 10; c++) info->seq_log[a][c] = D->seq_log[a][c];
   }
   free(D->lit); free(D);
   *out_size = op;
