@@ -57,10 +57,8 @@ static_assert(sizeof(FastDesc) <= FAST_DESC_BYTES, "descriptor slot too small");
 struct ChunkSlot {
   uint8_t *base, *lit_pool, *seq_pool;
   __device__ __forceinline__ FastDesc *desc() const { return reinterpret_cast<FastDesc *>(base); }
-  __device__ __forceinline__ uint16_t *huf() const { return reinterpret_cast<uint16_t *>(base + FAST_DESC_BYTES); }
-  __device__ __forceinline__ uint2 *ll() const { return reinterpret_cast<uint2 *>(base + FAST_DESC_BYTES + 4096); }
-  __device__ __forceinline__ uint2 *ml() const { return reinterpret_cast<uint2 *>(base + FAST_DESC_BYTES + 8192); }
-  __device__ __forceinline__ uint2 *of() const { return reinterpret_cast<uint2 *>(base + FAST_DESC_BYTES + 12288); }
+  __device__ __forceinline__ uint8_t *seq_info() const { return base + FAST_DESC_BYTES; }          // SeqInfo, 64 B reserved
+  __device__ __forceinline__ uint8_t *seq_tabs() const { return base + FAST_DESC_BYTES + 64; }     // 2560 B uint16 plane, 1280 B uint8 plane
   __device__ __forceinline__ uint8_t *lits() const { return lit_pool + (size_t)desc()->lit_slot * 16; }
   __device__ __forceinline__ uint4 *seqs() const { return reinterpret_cast<uint4 *>(seq_pool + (size_t)desc()->seq_slot * 16); }
 };
@@ -322,19 +320,19 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
 // =================================================================================================
 // KB: FSE tables in shared memory (one warp per chunk), then one lane per sequence stream
 // =================================================================================================
-constexpr int KB_THREADS = 256, KB_WARPS = KB_THREADS / 32;
+constexpr int KB_THREADS = 64;                                  // the two decoding warps; everything else of the SM is left to KC
 constexpr int KB_GROUP = 56;                                   // chunks per CTA pass: 56 x 3.75 KB of packed tables
 constexpr int KB_DEC_WARPS = 2, KB_LANES = KB_GROUP / KB_DEC_WARPS;   // 2 decoding warps x 28 lanes
-struct __align__(16) SeqScratch {                              // per-warp scratch for the table build
-  int16_t norm[3][64];
-  uint8_t item_sym[512];
+__device__ __forceinline__ constexpr int kb_norm_off(int t) { return t == 0 ? 0 : t == 1 ? 40 : 72; }   // LL 36 | OF 32 | ML 53 normalised counts
+struct __align__(16) SeqScratch {                              // per-warp scratch for the table build (432 B: 28 of them fit beside the tables)
+  int16_t norm[128];
   uint16_t sym_next[64];
   int tab_log[3], tab_max[3], tab_mode[3];
   uint32_t bits_off, ok;
 };
 struct SeqInfo { uint32_t ready, ll_log, of_log, ml_log, bits_off, bits_len; };
 constexpr size_t KB_TAB_BYTES = 1280 * 3;                      // LL 512 | ML 512 | OF 256 entries: a uint16 plane and a uint8 plane
-constexpr size_t KB_SMEM = (size_t)KB_GROUP * KB_TAB_BYTES + KB_WARPS * sizeof(SeqScratch) + KB_GROUP * sizeof(SeqInfo) + 96 * 4 + 16;
+constexpr size_t KB_SMEM = (size_t)KB_GROUP * KB_TAB_BYTES + 96 * 4;
 
 // packed decode entry, 24 bits in two planes so that 56 chunks' tables fit in one SM's shared memory:
 //   t16[state] = nextStateBase[0:9) | nbBits[9:13) | extraBits[13:16) (low 3 bits)      t8[state] = extraBits high 2 bits | symbol << 2
@@ -348,9 +346,10 @@ __device__ __forceinline__ void pack_entry(const SeqTab &T, uint32_t idx, int ki
 }
 // fse_build_warp (zstd_decode_tables.cuh) emitting packed entries in place; `off` = first entry of this table in the planes
 __device__ inline void fse_build_warp_packed(const SeqTab &T, uint32_t off, const int16_t *norm, int max_sym, int log, int kind,
-                                             uint8_t *item_sym, uint16_t *sym_next, int lane) {
+                                             uint16_t *sym_next, int lane) {
   const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
   uint8_t *cell = T.t8 + off;                       // the byte plane doubles as the symbol-of-cell scratch
+  uint8_t *item_sym = (uint8_t *)(T.t16 + off);     // and the 16-bit plane, not written before the last pass, holds the sorted symbols
   int high = size - 1, acc = 0;
   for (int s = 0; s <= max_sym; s++) {
     const int c = norm[s];
@@ -484,98 +483,139 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
   D->seq_status = err; D->out_end = out_pos; D->lit_end = lit_pos;
 }
 
-__global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecodeArgs F) {
-  extern __shared__ __align__(16) uint8_t kb_smem[];
-  __shared__ uint32_t s_group;
-  uint16_t *const tab16 = reinterpret_cast<uint16_t *>(kb_smem);                             // [KB_GROUP][1280]: LL 512 | ML 512 | OF 256
-  uint8_t *const tab8 = kb_smem + (size_t)KB_GROUP * 1280 * 2;                               // [KB_GROUP][1280]
-  SeqScratch *const scratch = reinterpret_cast<SeqScratch *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES);
-  SeqInfo *const info = reinterpret_cast<SeqInfo *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES + KB_WARPS * sizeof(SeqScratch));
-  uint32_t *const bases = reinterpret_cast<uint32_t *>(info + KB_GROUP);                      // [0,36) LL bases, [40,93) ML bases
+// ---- KT: sequence table descriptions -> packed decode tables, one warp per chunk, written to the chunk's slot ----
+// The build is a latency chain per chunk (serial header parse, three dependent passes over the cells); run on its own it
+// has every warp slot of the GPU to hide that in, instead of the few warps that fit beside KB's 210 KB of tables.
+constexpr int KT_WARPS = 8;
+__global__ void __launch_bounds__(KT_WARPS * 32) zstd_fast_tab_kernel(FastDecodeArgs F) {
+  __shared__ __align__(16) uint8_t stage[KT_WARPS][KB_TAB_BYTES];
+  __shared__ SeqScratch scratch[KT_WARPS];
   const DecodeArgs &A = F.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SeqScratch &S = scratch[warp];
-  if (threadIdx.x < 36) bases[threadIdx.x] = c_ll_base[threadIdx.x];
-  if (threadIdx.x >= 40 && threadIdx.x < 93) bases[threadIdx.x] = c_ml_base[threadIdx.x - 40];
+  const SeqTab T{reinterpret_cast<uint16_t *>(stage[warp]), stage[warp] + 2560};
+  for (uint32_t chunk = F.lo + blockIdx.x * KT_WARPS + warp; chunk < F.hi; chunk += gridDim.x * KT_WARPS) {
+    ChunkSlot slot = slot_of(F, chunk);
+    FastDesc *D = slot.desc();
+    SeqInfo *const info = reinterpret_cast<SeqInfo *>(slot.seq_info());
+    if (lane == 0) info->ready = 0;
+    if (D->state != 0) continue;                                                              // uniform per warp
+    const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
+    const uint32_t nseq = D->nseq;
+    if (nseq == 0) {
+      if (lane == 0) { slot.seqs()[0] = make_uint4(0, 0, 0, 0); D->seq_status = ST_OK; D->out_end = 0; D->lit_end = 0; }
+      continue;
+    }
+    const uint8_t *const bp = src + D->tab_off;
+    const uint32_t room = D->blk_end - D->tab_off, modes = D->modes;
+    __syncwarp();                                                                             // previous chunk's copy-out is done
+    if (lane == 0) {
+      uint32_t p = 0;
+      bool ok = true;
+      for (int t = 0; t < 3 && ok; t++) {                                                     // stream order: LL, OF, ML
+        const int mode = (modes >> (6 - 2 * t)) & 3;
+        const int max_allowed = (t == 0) ? LL_MAX_SYM : (t == 1) ? OF_MAX_SYM : ML_MAX_SYM;
+        S.tab_mode[t] = mode;
+        if (mode == 0) {
+          const int16_t *def = (t == 0) ? c_ll_def : (t == 1) ? c_of_def : c_ml_def;
+          const int dmax = (t == 0) ? 35 : (t == 1) ? 28 : 52;
+          for (int i = 0; i <= dmax; i++) S.norm[kb_norm_off(t) + i] = def[i];
+          S.tab_max[t] = dmax; S.tab_log[t] = (t == 1) ? OF_DEF_LOG : LL_DEF_LOG;
+        } else if (mode == 1) {
+          if (p >= room || bp[p] > max_allowed) { ok = false; break; }
+          S.tab_max[t] = bp[p]; S.tab_log[t] = 0;
+          p += 1;
+        } else if (mode == 2) {
+          int ms = 0, al = 0;
+          const int max_log = (t == 1) ? OF_MAX_LOG : LL_MAX_LOG;
+          const int used = (p < room) ? read_ncount(bp + p, room - p, S.norm + kb_norm_off(t), max_allowed, max_log, &ms, &al) : -1;
+          if (used < 0) { ok = false; break; }
+          S.tab_max[t] = ms; S.tab_log[t] = al;
+          p += (uint32_t)used;
+        } else ok = false;                                                                    // Repeat needs a previous block
+      }
+      if (p >= room) ok = false;
+      S.bits_off = p;
+      S.ok = ok ? 1u : 0u;
+    }
+    __syncwarp();
+    if (!S.ok) {
+      if (lane == 0) { slot.seqs()[nseq] = make_uint4(0, 0, 0, 0); D->seq_status = ST_CORRUPT; D->out_end = 0; D->lit_end = 0; }
+      continue;
+    }
+    for (int t = 0; t < 3; t++) {
+      const uint32_t toff = (t == 0) ? 0u : (t == 1) ? 1024u : 512u;
+      if (S.tab_mode[t] == 1) { if (lane == 0) pack_entry(T, toff, t, (uint32_t)S.tab_max[t], 0, 0); }
+      else fse_build_warp_packed(T, toff, S.norm + kb_norm_off(t), S.tab_max[t], S.tab_log[t], t, S.sym_next, lane);
+      __syncwarp();
+    }
+    {
+      const uint4 *const from = reinterpret_cast<const uint4 *>(stage[warp]);
+      uint4 *const to = reinterpret_cast<uint4 *>(slot.seq_tabs());
+      for (uint32_t k = lane; k < KB_TAB_BYTES / 16; k += 32) to[k] = from[k];
+    }
+    if (lane == 0) {
+      info->ll_log = (uint32_t)S.tab_log[0]; info->of_log = (uint32_t)S.tab_log[1]; info->ml_log = (uint32_t)S.tab_log[2];
+      info->bits_off = D->tab_off + S.bits_off; info->bits_len = room - S.bits_off;
+      info->ready = 1;
+    }
+  }
+}
+
+// ---- KB: 56 chunks' tables pulled into shared memory by bulk async copies, then one lane per sequence stream ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecodeArgs F) {
+  extern __shared__ __align__(128) uint8_t kb_smem[];
+  __shared__ uint32_t s_group;
+  __shared__ __align__(8) uint64_t s_bar;
+  uint16_t *const tab16 = reinterpret_cast<uint16_t *>(kb_smem);                             // [KB_GROUP][1280]: LL 512 | ML 512 | OF 256
+  uint8_t *const tab8 = kb_smem + (size_t)KB_GROUP * 1280 * 2;                               // [KB_GROUP][1280]
+  uint32_t *const bases = reinterpret_cast<uint32_t *>(kb_smem + (size_t)KB_GROUP * KB_TAB_BYTES);   // [0,36) LL bases, [40,93) ML bases
+  const DecodeArgs &A = F.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 36; i += KB_THREADS) bases[i] = c_ll_base[i];
+  for (int i = threadIdx.x; i < 53; i += KB_THREADS) bases[40 + i] = c_ml_base[i];
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t phase = 0;
   for (;;) {
     if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 1 + F.sub, 1u);
-    __syncthreads();
+    __syncthreads();                                                  // also: every lane is done with the previous group's tables
     const uint32_t g0 = F.lo + s_group * KB_GROUP;
     if (g0 >= F.hi) break;
-    // ---------------- phase 1: table descriptions -> decode tables in shared memory ----------------
-    for (uint32_t c = warp; c < KB_GROUP && g0 + c < F.hi; c += KB_WARPS) {
-      const uint32_t chunk = g0 + c;
-      ChunkSlot slot = slot_of(F, chunk);
-      FastDesc *D = slot.desc();
+    const uint32_t cnt = min((uint32_t)KB_GROUP, F.hi - g0);
+    const uint32_t c = (uint32_t)warp * KB_LANES + (uint32_t)lane;
+    const bool mine = lane < KB_LANES && c < cnt;
+    ChunkSlot slot = slot_of(F, g0 + (mine ? c : 0));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tables about to be overwritten were read through the generic proxy
+    if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(cnt * (uint32_t)KB_TAB_BYTES) : "memory");
+    if (mine) {                                                       // every lane pulls its own chunk's two planes
+      bulk_g2s(tab16 + (size_t)c * 1280, slot.seq_tabs(), 2560, &s_bar);
+      bulk_g2s(tab8 + (size_t)c * 1280, slot.seq_tabs() + 2560, 1280, &s_bar);
+    }
+    SeqInfo info;
+    info.ready = 0;
+    if (mine) info = *reinterpret_cast<const SeqInfo *>(slot.seq_info());
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    if (mine && info.ready) {
       const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
-      if (lane == 0) info[c].ready = 0;
-      if (D->state != 0) continue;                                                            // uniform per warp
-      const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
-      const uint32_t nseq = D->nseq;
-      if (nseq == 0) {
-        if (lane == 0) { slot.seqs()[0] = make_uint4(0, 0, 0, 0); D->seq_status = ST_OK; D->out_end = 0; D->lit_end = 0; }
-        continue;
-      }
-      const uint8_t *const bp = src + D->tab_off;
-      const uint32_t room = D->blk_end - D->tab_off, modes = D->modes;
-      if (lane == 0) {
-        uint32_t p = 0;
-        bool ok = true;
-        for (int t = 0; t < 3 && ok; t++) {                                                   // stream order: LL, OF, ML
-          const int mode = (modes >> (6 - 2 * t)) & 3;
-          const int max_allowed = (t == 0) ? LL_MAX_SYM : (t == 1) ? OF_MAX_SYM : ML_MAX_SYM;
-          S.tab_mode[t] = mode;
-          if (mode == 0) {
-            const int16_t *def = (t == 0) ? c_ll_def : (t == 1) ? c_of_def : c_ml_def;
-            const int dmax = (t == 0) ? 35 : (t == 1) ? 28 : 52;
-            for (int i = 0; i <= dmax; i++) S.norm[t][i] = def[i];
-            S.tab_max[t] = dmax; S.tab_log[t] = (t == 1) ? OF_DEF_LOG : LL_DEF_LOG;
-          } else if (mode == 1) {
-            if (p >= room || bp[p] > max_allowed) { ok = false; break; }
-            S.tab_max[t] = bp[p]; S.tab_log[t] = 0;
-            p += 1;
-          } else if (mode == 2) {
-            int ms = 0, al = 0;
-            const int max_log = (t == 1) ? OF_MAX_LOG : LL_MAX_LOG;
-            const int used = (p < room) ? read_ncount(bp + p, room - p, S.norm[t], max_allowed, max_log, &ms, &al) : -1;
-            if (used < 0) { ok = false; break; }
-            S.tab_max[t] = ms; S.tab_log[t] = al;
-            p += (uint32_t)used;
-          } else ok = false;                                                                  // Repeat needs a previous block
-        }
-        if (p >= room) ok = false;
-        S.bits_off = p;
-        S.ok = ok ? 1u : 0u;
-      }
-      __syncwarp();
-      if (!S.ok) {
-        if (lane == 0) { slot.seqs()[nseq] = make_uint4(0, 0, 0, 0); D->seq_status = ST_CORRUPT; D->out_end = 0; D->lit_end = 0; }
-        continue;
-      }
-      for (int t = 0; t < 3; t++) {
-        const uint32_t toff = (t == 0) ? 0u : (t == 1) ? 1024u : 512u;
-        if (S.tab_mode[t] == 1) { if (lane == 0) pack_entry(T, toff, t, (uint32_t)S.tab_max[t], 0, 0); }
-        else fse_build_warp_packed(T, toff, S.norm[t], S.tab_max[t], S.tab_log[t], t, S.item_sym, S.sym_next, lane);
-        __syncwarp();
-      }
-      if (lane == 0) {
-        info[c].ll_log = (uint32_t)S.tab_log[0]; info[c].of_log = (uint32_t)S.tab_log[1]; info[c].ml_log = (uint32_t)S.tab_log[2];
-        info[c].bits_off = D->tab_off + S.bits_off; info[c].bits_len = room - S.bits_off;
-        info[c].ready = 1;
-      }
-      __syncwarp();
+      fast_decode_sequences((const uint8_t *)A.in_ptrs[g0 + c], slot.desc(), slot.seqs(), T, bases, info);
     }
-    __syncthreads();
-    // ---------------- phase 2: one lane per chunk, KB_DEC_WARPS warps ----------------
-    if (warp < KB_DEC_WARPS && lane < KB_LANES) {
-      const uint32_t c = (uint32_t)warp * KB_LANES + (uint32_t)lane, chunk = g0 + c;
-      if (chunk < F.hi && info[c].ready) {
-        ChunkSlot slot = slot_of(F, chunk);
-        const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
-        fast_decode_sequences((const uint8_t *)A.in_ptrs[chunk], slot.desc(), slot.seqs(), T, bases, info[c]);
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -816,7 +856,9 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
   const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
   zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
-  int count = 1;
+  const uint32_t kt_blocks = (n + KT_WARPS - 1) / KT_WARPS;
+  zstd_fast_tab_kernel<<<kt_blocks < 6 * sms ? kt_blocks : 6 * sms, KT_WARPS * 32, 0, stream>>>(F);
+  int count = 2;
   // KB (SMEM-bound: one CTA and two busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
   // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1
   const uint32_t sub_chunks = sms * KB_GROUP;
