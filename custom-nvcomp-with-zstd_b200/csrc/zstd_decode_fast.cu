@@ -58,7 +58,8 @@ struct ChunkSlot {
   uint8_t *base, *lit_pool, *seq_pool;
   __device__ __forceinline__ FastDesc *desc() const { return reinterpret_cast<FastDesc *>(base); }
   __device__ __forceinline__ uint8_t *seq_info() const { return base + FAST_DESC_BYTES; }          // SeqInfo, 64 B reserved
-  __device__ __forceinline__ uint8_t *seq_tabs() const { return base + FAST_DESC_BYTES + 64; }     // 2560 B uint16 plane, 1280 B uint8 plane
+  __device__ __forceinline__ uint8_t *huf_tab() const { return base + FAST_DESC_BYTES + 64; }      // 2048 x uint16 Huffman decode table
+  __device__ __forceinline__ uint8_t *seq_tabs() const { return base + FAST_DESC_BYTES + 64 + 4096; }   // 2560 B uint16 plane, 1280 B uint8 plane
   __device__ __forceinline__ uint8_t *lits() const { return lit_pool + (size_t)desc()->lit_slot * 16; }
   __device__ __forceinline__ uint4 *seqs() const { return reinterpret_cast<uint4 *>(seq_pool + (size_t)desc()->seq_slot * 16); }
 };
@@ -68,12 +69,13 @@ __device__ __forceinline__ ChunkSlot slot_of(const FastDecodeArgs &F, uint32_t c
 __device__ __forceinline__ uint32_t seg_padded(uint32_t seg) { return (seg + 15u) & ~15u; }
 
 // =================================================================================================
-// KA: headers + Huffman tables (one warp per chunk), then one thread per Huffman stream
+// KP: per-chunk preparation, one warp per chunk -- frame/block/section headers, the Huffman decode table and the three
+// packed FSE decode tables, all written to the chunk's slot.  Every step here is a short serial chain per chunk, so the
+// kernel runs with every warp slot of the GPU instead of inside the decode kernels, whose shared memory is full of tables.
 // =================================================================================================
-constexpr int KA_THREADS = 256, KA_WARPS = KA_THREADS / 32;
-constexpr int KA_GROUP = 24;                                   // chunks per CTA pass: 24 x 4 KB of tables, two CTAs per SM
+constexpr int KP_WARPS = 8;
 struct __align__(16) HufScratch {                              // per-warp scratch of huf_read_table_warp
-  uint16_t *huf;                                               // -> this chunk's table in shared memory
+  uint16_t *huf;                                               // -> the table being built (shared-memory staging)
   uint8_t weights[256];
   uint32_t huf_ft[64];
   int16_t huf_norm[16];
@@ -81,28 +83,10 @@ struct __align__(16) HufScratch {                              // per-warp scrat
   uint32_t rank_start[16];
   int huf_log, huf_valid;
 };
-constexpr size_t KA_SMEM = (size_t)KA_GROUP * 4096 + KA_WARPS * sizeof(HufScratch) + 16;
 
-__device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
-                                                    uint32_t k, uint32_t *status_out);
-
-__global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArgs F) {
-  extern __shared__ __align__(16) uint8_t ka_smem[];
-  __shared__ uint32_t s_group;
-  uint16_t *const tables = reinterpret_cast<uint16_t *>(ka_smem);
-  HufScratch *const scratch = reinterpret_cast<HufScratch *>(ka_smem + (size_t)KA_GROUP * 4096);
-  const DecodeArgs &A = F.base;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  HufScratch &S = scratch[warp];
-  for (;;) {
-    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 0, 1u);
-    __syncthreads();
-    const uint32_t g0 = s_group * KA_GROUP;
-    if (g0 >= A.n) break;
-    // ---------------- phase 1: one warp per chunk ----------------
-   for (uint32_t c = warp; c < KA_GROUP && g0 + c < A.n; c += KA_WARPS) {
-    const uint32_t chunk = g0 + c;
-    if (lane == 0) S.huf = tables + (size_t)c * 2048;
+__device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chunk, uint8_t *stage, HufScratch &S, int lane) {
+    const DecodeArgs &A = F.base;
+    if (lane == 0) S.huf = reinterpret_cast<uint16_t *>(stage);
     __syncwarp();
     const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
     const size_t src_size = A.in_sizes[chunk];
@@ -265,21 +249,85 @@ __global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArg
       *slot.desc() = D;
     }
     __syncwarp();
-   }
-    __threadfence_block();
-    __syncthreads();
-    // ---------------- phase 2: one thread per Huffman stream ----------------
-    if (threadIdx.x < 4 * KA_GROUP) {
-      const uint32_t c = threadIdx.x >> 2, chunk = g0 + c;
-      if (chunk < A.n) {
-        ChunkSlot slot = slot_of(F, chunk);
-        FastDesc *D = slot.desc();
-        if (D->state == 0 && (threadIdx.x & 3) < D->n_streams)
-          fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, threadIdx.x & 3,
-                              &D->lit_status[threadIdx.x & 3]);
+    // the Huffman table leaves the staging buffer before the FSE build reuses it
+    if (slot.desc()->state == 0 && D.lit_type == 2) {
+      const uint4 *const from = reinterpret_cast<const uint4 *>(stage);
+      uint4 *const to = reinterpret_cast<uint4 *>(slot.huf_tab());
+      const uint32_t n16 = (2u << D.huf_log) / 16;                             // 2^log entries x 2 bytes
+      for (uint32_t k = lane; k < n16; k += 32) to[k] = from[k];
+    }
+    __syncwarp();
+}
+
+// =================================================================================================
+// KA: literals -- 28 chunks' Huffman tables pulled into shared memory by bulk async copies (two CTAs per SM), then one
+// thread per Huffman stream
+// =================================================================================================
+constexpr int KA_THREADS = 128;
+constexpr int KA_GROUP = 28;                                   // chunks per CTA pass: 28 x 4 KB of tables, two CTAs per SM
+constexpr size_t KA_SMEM = (size_t)KA_GROUP * 4096;
+
+__device__ __forceinline__ uint32_t top_bits(uint32_t hi, int skip, int n) { return ((hi << skip) >> 1) >> (31 - n); }   // n in [0,31]
+__device__ __forceinline__ uint32_t peek32(const uint32_t *W, int t) {             // bits [t-32, t) of the stream, t may be anything
+  const int k = max(t >> 5, 0);
+  return __funnelshift_r(W[k - 1], W[k], (uint32_t)t & 31u);
+}
+
+__device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
+                                                    uint32_t k, uint32_t *status_out);
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArgs F) {
+  extern __shared__ __align__(128) uint8_t ka_smem[];
+  __shared__ uint32_t s_group;
+  __shared__ __align__(8) uint64_t s_bar;
+  uint16_t *const tables = reinterpret_cast<uint16_t *>(ka_smem);
+  const DecodeArgs &A = F.base;
+  if (threadIdx.x == 0) mbar_init(&s_bar, KA_GROUP);           // one arrival per chunk of the group
+  uint32_t phase = 0;
+  for (;;) {
+    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 0, 1u);
+    __syncthreads();                                            // also: every thread is done with the previous group's tables
+    const uint32_t g0 = s_group * KA_GROUP;
+    if (g0 >= A.n) break;
+    const uint32_t c = threadIdx.x >> 2, k = threadIdx.x & 3, chunk = g0 + c;
+    bool work = false;
+    ChunkSlot slot = slot_of(F, chunk < A.n ? chunk : g0);
+    FastDesc *const D = slot.desc();
+    if (c < KA_GROUP) {
+      const bool live = chunk < A.n && D->state == 0 && D->lit_type == 2;
+      work = live && k < D->n_streams;
+      if (k == 0) {                                             // the chunk's first thread pulls its table
+        if (live) {
+          const uint32_t bytes = 2u << D->huf_log;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_tx(&s_bar, bytes);
+          bulk_g2s(tables + (size_t)c * 2048, slot.huf_tab(), bytes, &s_bar);
+        } else mbar_arrive(&s_bar);
       }
     }
-    __syncthreads();
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    if (work) fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, k, &D->lit_status[k]);
   }
 }
 
@@ -292,27 +340,35 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
   const uint32_t count = (D->n_streams == 1) ? lit_size : (k < 3 ? seg : lit_size - 3 * seg);
   uint8_t *dst = lits + (size_t)k * seg_padded(seg);                          // 16-byte aligned segment
   const int sh = 64 - (int)D->huf_log;
-  BackBits b;
-  bool ok = b.init(src + D->st_off[k], D->st_len[k]);
+  const uint8_t *const p = src + D->st_off[k];
+  const uint32_t nb = D->st_len[k];
+  // position-based reader (see the sequence loop in KB): the words under bit `t` are loaded each round, so there is no
+  // refill branch.  W[-1], W[-2] are read under the first stream bits: >= 12 header bytes always precede a Huffman stream.
+  bool ok = nb != 0 && D->st_off[k] >= 12 && p[nb - 1] != 0;
   if (ok) {
+    const uint32_t *const W = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    const int d = (int)((uintptr_t)p & 3), low = 8 * d;
+    int t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);
     uint32_t i = 0;
     uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-    for (; i + 4 <= count; i += 4) {                                          // 4 symbols -> one aligned 32-bit store
-      b.refill();
-      const uint32_t e0 = tab[b.win >> sh]; b.skip((int)(e0 >> 8));
-      const uint32_t e1 = tab[b.win >> sh]; b.skip((int)(e1 >> 8));
-      b.refill();
-      const uint32_t e2 = tab[b.win >> sh]; b.skip((int)(e2 >> 8));
-      const uint32_t e3 = tab[b.win >> sh]; b.skip((int)(e3 >> 8));
+    for (; i + 4 <= count; i += 4) {                                          // 4 symbols (<= 44 bits) -> one aligned 32-bit store
+      const int kw = max(t >> 5, 0);
+      const uint32_t s = (uint32_t)t & 31u;
+      const uint32_t w0 = W[kw], w1 = W[kw - 1], w2 = W[kw - 2];
+      uint64_t win = ((uint64_t)__funnelshift_r(w1, w0, s) << 32) | __funnelshift_r(w2, w1, s);
+      const uint32_t e0 = tab[win >> sh]; win <<= (e0 >> 8);
+      const uint32_t e1 = tab[win >> sh]; win <<= (e1 >> 8);
+      const uint32_t e2 = tab[win >> sh]; win <<= (e2 >> 8);
+      const uint32_t e3 = tab[win >> sh];
+      t -= (int)((e0 >> 8) + (e1 >> 8) + (e2 >> 8) + (e3 >> 8));
       d32[i >> 2] = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | (e3 << 24);
     }
     for (; i < count; i++) {
-      b.refill();
-      const uint32_t e = tab[b.win >> sh];
-      b.skip((int)(e >> 8));
+      const uint32_t e = tab[((uint64_t)peek32(W, t) << 32) >> sh];
+      t -= (int)(e >> 8);
       dst[i] = (uint8_t)e;
     }
-    ok = b.left == 0;
+    ok = t == low;
   }
   *status_out = ok ? ST_OK : ST_CORRUPT;
 }
@@ -402,12 +458,6 @@ __device__ __forceinline__ uint32_t ml_base_of(uint32_t c) {
 // under `t` (L1 hits; the loads issue together with the table lookups) and cuts all six fields out of them with funnel
 // shifts.  There is no refill branch and no window state on the dependency chain: in a warp whose lanes each walk their own
 // stream, the three divergent refill regions of a shifting window cost a quarter of the loop's instructions.
-__device__ __forceinline__ uint32_t top_bits(uint32_t hi, int skip, int n) { return ((hi << skip) >> 1) >> (31 - n); }   // n in [0,31]
-__device__ __forceinline__ uint32_t peek32(const uint32_t *W, int t) {             // bits [t-32, t) of the stream, t may be anything
-  const int k = max(t >> 5, 0);
-  return __funnelshift_r(W[k - 1], W[k], (uint32_t)t & 31u);
-}
-
 __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
                                                       const SeqInfo &I) {
   const uint16_t *const ll16 = T.t16, *const ml16 = T.t16 + 512, *const of16 = T.t16 + 1024;
@@ -483,18 +533,17 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
   D->seq_status = err; D->out_end = out_pos; D->lit_end = lit_pos;
 }
 
-// ---- KT: sequence table descriptions -> packed decode tables, one warp per chunk, written to the chunk's slot ----
-// The build is a latency chain per chunk (serial header parse, three dependent passes over the cells); run on its own it
-// has every warp slot of the GPU to hide that in, instead of the few warps that fit beside KB's 210 KB of tables.
-constexpr int KT_WARPS = 8;
-__global__ void __launch_bounds__(KT_WARPS * 32) zstd_fast_tab_kernel(FastDecodeArgs F) {
-  __shared__ __align__(16) uint8_t stage[KT_WARPS][KB_TAB_BYTES];
-  __shared__ SeqScratch scratch[KT_WARPS];
+// ---- KP kernel: prep_chunk (headers, Huffman table) followed by the sequence table build, one warp per chunk ----
+__global__ void __launch_bounds__(KP_WARPS * 32) zstd_fast_prep_kernel(FastDecodeArgs F) {
+  __shared__ __align__(16) uint8_t stage[KP_WARPS][4096];       // Huffman table (4 KB), then the packed FSE tables (3.75 KB)
+  __shared__ HufScratch hscratch[KP_WARPS];
+  __shared__ SeqScratch scratch[KP_WARPS];
   const DecodeArgs &A = F.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SeqScratch &S = scratch[warp];
   const SeqTab T{reinterpret_cast<uint16_t *>(stage[warp]), stage[warp] + 2560};
-  for (uint32_t chunk = F.lo + blockIdx.x * KT_WARPS + warp; chunk < F.hi; chunk += gridDim.x * KT_WARPS) {
+  for (uint32_t chunk = blockIdx.x * KP_WARPS + warp; chunk < A.n; chunk += gridDim.x * KP_WARPS) {
+    prep_chunk(F, chunk, stage[warp], hscratch[warp], lane);
     ChunkSlot slot = slot_of(F, chunk);
     FastDesc *D = slot.desc();
     SeqInfo *const info = reinterpret_cast<SeqInfo *>(slot.seq_info());
@@ -563,19 +612,6 @@ __global__ void __launch_bounds__(KT_WARPS * 32) zstd_fast_tab_kernel(FastDecode
 }
 
 // ---- KB: 56 chunks' tables pulled into shared memory by bulk async copies, then one lane per sequence stream ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-               "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-
 __global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecodeArgs F) {
   extern __shared__ __align__(128) uint8_t kb_smem[];
   __shared__ uint32_t s_group;
@@ -587,10 +623,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecode
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 36; i += KB_THREADS) bases[i] = c_ll_base[i];
   for (int i = threadIdx.x; i < 53; i += KB_THREADS) bases[40 + i] = c_ml_base[i];
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   for (;;) {
     if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 1 + F.sub, 1u);
@@ -602,7 +635,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecode
     const bool mine = lane < KB_LANES && c < cnt;
     ChunkSlot slot = slot_of(F, g0 + (mine ? c : 0));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the tables about to be overwritten were read through the generic proxy
-    if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(cnt * (uint32_t)KB_TAB_BYTES) : "memory");
+    if (threadIdx.x == 0) mbar_arrive_tx(&s_bar, cnt * (uint32_t)KB_TAB_BYTES);
     if (mine) {                                                       // every lane pulls its own chunk's two planes
       bulk_g2s(tab16 + (size_t)c * 1280, slot.seq_tabs(), 2560, &s_bar);
       bulk_g2s(tab8 + (size_t)c * 1280, slot.seq_tabs() + 2560, 1280, &s_bar);
@@ -854,10 +887,10 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   // one memset zeroes every counter of the pipeline: general work queue, slow count, pool heads, group counters
   if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
   const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
+  const uint32_t kp_blocks = (n + KP_WARPS - 1) / KP_WARPS;
+  zstd_fast_prep_kernel<<<kp_blocks < 5 * sms ? kp_blocks : 5 * sms, KP_WARPS * 32, 0, stream>>>(F);
   const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
   zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
-  const uint32_t kt_blocks = (n + KT_WARPS - 1) / KT_WARPS;
-  zstd_fast_tab_kernel<<<kt_blocks < 6 * sms ? kt_blocks : 6 * sms, KT_WARPS * 32, 0, stream>>>(F);
   int count = 2;
   // KB (SMEM-bound: one CTA and two busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
   // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1

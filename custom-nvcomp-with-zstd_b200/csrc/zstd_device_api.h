@@ -32,7 +32,7 @@ int decode_ctas_per_sm();
 // ---- batch fast path: three kernels over the whole batch (zstd_decode_fast.cu) --------------------
 constexpr uint32_t FAST_WAVE = 16384;                         // chunks per fast-path wave (bounds the scratch)
 constexpr uint32_t FAST_SEQ_CAP = 65536;                      // sequences per chunk the fast path accepts
-constexpr size_t FAST_TABLE_BYTES = 64 + 3840;                // sequence-stream info + packed LL/ML/OF decode tables (KT -> KB)
+constexpr size_t FAST_TABLE_BYTES = 64 + 4096 + 3840;         // sequence-stream info, Huffman table, packed LL/ML/OF tables (KP -> KA, KB)
 constexpr size_t FAST_DESC_BYTES = 192;
 constexpr size_t FAST_SLOT_BYTES = FAST_DESC_BYTES + FAST_TABLE_BYTES;     // fixed per-chunk slot
 // Literals and sequence records come from two bump-allocated pools sized from the COMPRESSED sizes the
