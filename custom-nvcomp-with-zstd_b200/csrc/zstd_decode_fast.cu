@@ -398,7 +398,7 @@ struct SeqTab { uint16_t *t16; uint8_t *t8; };        // one chunk: t16 = [LL 51
 __device__ __forceinline__ void pack_entry(const SeqTab &T, uint32_t idx, int kind, uint32_t sym, uint32_t next_base, uint32_t nb) {
   const uint32_t xb = kind == 0 ? c_ll_bits[sym] : kind == 1 ? sym : c_ml_bits[sym];
   T.t16[idx] = (uint16_t)(next_base | (nb << 9) | ((xb & 7) << 13));
-  T.t8[idx] = (uint8_t)((xb >> 3) | (sym << 2));
+  T.t8[idx] = kind == 1 ? (uint8_t)xb : (uint8_t)((xb >> 3) | (sym << 2));   // an offset code IS its extra-bit count: no unpacking on the chain
 }
 // fse_build_warp (zstd_decode_tables.cuh) emitting packed entries in place; `off` = first entry of this table in the planes
 __device__ inline void fse_build_warp_packed(const SeqTab &T, uint32_t off, const int16_t *norm, int max_sym, int log, int kind,
@@ -458,79 +458,93 @@ __device__ __forceinline__ uint32_t ml_base_of(uint32_t c) {
 // under `t` (L1 hits; the loads issue together with the table lookups) and cuts all six fields out of them with funnel
 // shifts.  There is no refill branch and no window state on the dependency chain: in a warp whose lanes each walk their own
 // stream, the three divergent refill regions of a shifting window cost a quarter of the loop's instructions.
+// select without giving the compiler the chance to turn a chain of ?: into divergent branches
+__device__ __forceinline__ uint32_t sel_eq(uint32_t x, uint32_t k, uint32_t a, uint32_t b) {      // x == k ? a : b
+  uint32_t r;
+  asm("{\n.reg .pred p;\nsetp.eq.u32 p, %1, %2;\nselp.u32 %0, %3, %4, p;\n}" : "=r"(r) : "r"(x), "r"(k), "r"(a), "r"(b));
+  return r;
+}
+struct SeqLane {                                      // one lane's decoder state; everything lives in registers
+  const uint16_t *ll16, *ml16, *of16;
+  const uint8_t *ll8, *ml8, *of8;
+  const uint32_t *W, *bases;
+  uint4 *out;
+  uint32_t sl, so, sm, rep0, rep1, rep2, out_pos, lit_pos;
+  int t;
+  // LAST: the final sequence of a block is not followed by state updates
+  template <bool LAST> __device__ __forceinline__ void step(uint32_t i) {
+    const uint32_t eo = of16[so], em = ml16[sm], el = ll16[sl];
+    const uint32_t eo8 = of8[so], em8 = ml8[sm], el8 = ll8[sl];
+    const int k = max(t >> 5, 0);
+    const uint32_t sh = (uint32_t)t & 31u;
+    const uint32_t w0 = W[k], w1 = W[k - 1], w2 = W[k - 2];
+    // lanes of a warp stall together: pull the next cache line of this lane's bitstream long before its words are needed
+    // (eight sequences never consume 128 bytes, and `i` is warp-uniform: no divergence)
+    if ((i & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + max(k - 32, 0)));
+    const uint32_t A = __funnelshift_r(w1, w0, sh), B = __funnelshift_r(w2, w1, sh);     // bits [t-32,t) and [t-64,t-32)
+    const int ob = (int)eo8, mb = (int)((em >> 13) | ((em8 & 3) << 3)), lb = (int)((el >> 13) | ((el8 & 3) << 3));
+    const int xb = ob + mb + lb;
+    uint32_t ov, mx, lx, S;                            // S = the 32 bits after the extra bits: the three state updates (<= 26 bits)
+    if (xb <= 31) {                                   // the usual case: all extra bits are in the top word
+      ov = top_bits(A, 0, ob); mx = top_bits(A, ob, mb); lx = top_bits(A, ob + mb, lb);
+      S = __funnelshift_l(B, A, (uint32_t)xb);
+    } else {
+      ov = top_bits(A, 0, ob);
+      const uint32_t a2 = peek32(W, t - ob);
+      mx = top_bits(a2, 0, mb); lx = top_bits(a2, mb, lb);
+      S = peek32(W, t - xb);
+    }
+    if (!LAST) {
+      const int nl = (int)((el >> 9) & 15), nm = (int)((em >> 9) & 15), no = (int)((eo >> 9) & 15);   // <= 26 bits together
+      sl = (el & 511) + top_bits(S, 0, nl);
+      sm = (em & 511) + top_bits(S, nl, nm);
+      so = (eo & 511) + top_bits(S, nl + nm, no);
+      t -= xb + nl + nm + no;
+    } else t -= xb;
+    // ---- off the chain: values, repeat offsets (branch-free), positions.  Range checks are KC's (it has a lane per sequence) ----
+    ov += 1u << ob;
+    const uint32_t ll = bases[el8 >> 2] + lx, ml = bases[40 + (em8 >> 2)] + mx;
+    // idx: 0 keeps the history, 1 swaps rep0/rep1, >= 2 rotates all three; a new offset rotates like idx 3
+    const bool fresh = ov > 3;
+    const uint32_t idx = fresh ? 3u : ov - 1 + (ll == 0);
+    uint32_t cand = sel_eq(idx, 1, rep1, rep0);
+    cand = sel_eq(idx, 2, rep2, cand);
+    cand = sel_eq(idx, 3, fresh ? ov - 3 : rep0 - 1, cand);
+    rep2 = idx >= 2 ? rep1 : rep2;
+    rep1 = idx >= 1 ? rep0 : rep1;
+    rep0 = cand;
+    __stcs(out + i, make_uint4(out_pos, lit_pos, cand, ml));
+    out_pos += ll + ml; lit_pos += ll;
+  }
+};
+
 __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
                                                       const SeqInfo &I) {
-  const uint16_t *const ll16 = T.t16, *const ml16 = T.t16 + 512, *const of16 = T.t16 + 1024;
-  const uint8_t *const ll8 = T.t8, *const ml8 = T.t8 + 512, *const of8 = T.t8 + 1024;
-  const uint32_t nseq = D->nseq, cap = D->cap, lit_size = D->lit_size;
-  uint32_t out_pos = 0, lit_pos = 0, err = ST_OK;
+  const uint32_t nseq = D->nseq;
+  uint32_t err = ST_OK;
+  SeqLane L;
+  L.out_pos = 0; L.lit_pos = 0;
   const uint8_t *const p = src + I.bits_off;
   const uint32_t nb = I.bits_len;
   // W[-1], W[-2] are read under the first stream bits: a fast-path frame has >= 12 header bytes before the bitstream
   if (nb == 0 || I.bits_off < 12 || p[nb - 1] == 0) err = ST_CORRUPT;
   else {
-    const uint32_t *const W = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    L.ll16 = T.t16; L.ml16 = T.t16 + 512; L.of16 = T.t16 + 1024;
+    L.ll8 = T.t8; L.ml8 = T.t8 + 512; L.of8 = T.t8 + 1024;
+    L.bases = bases; L.out = out;
+    L.W = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
     const int d = (int)((uintptr_t)p & 3), low = 8 * d;
-    int t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);       // the sentinel bit itself is not payload
-    uint32_t sl, so, sm;
-    { const uint32_t a = peek32(W, t); sl = top_bits(a, 0, (int)I.ll_log); so = top_bits(a, (int)I.ll_log, (int)I.of_log);
-      sm = top_bits(a, (int)(I.ll_log + I.of_log), (int)I.ml_log); t -= (int)(I.ll_log + I.of_log + I.ml_log); }
-    uint32_t rep0 = 1, rep1 = 4, rep2 = 8, bad = 0, big = 0;
-    int mark = (t >> 5) + 1;
-    for (uint32_t i = 0; i < nseq; i++) {
-      const uint32_t eo = of16[so], em = ml16[sm], el = ll16[sl];
-      const uint32_t eo8 = of8[so], em8 = ml8[sm], el8 = ll8[sl];
-      const int k = max(t >> 5, 0);
-      const uint32_t sh = (uint32_t)t & 31u;
-      const uint32_t w0 = W[k], w1 = W[k - 1], w2 = W[k - 2];
-      // lanes of a warp stall together: pull the next cache line of this lane's bitstream long before its words are needed
-      if (k <= mark) {
-        mark = k - 32;
-        if (mark >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + mark));
-      }
-      const uint32_t A = __funnelshift_r(w1, w0, sh), B = __funnelshift_r(w2, w1, sh);     // bits [t-32,t) and [t-64,t-32)
-      const int ob = (int)((eo >> 13) | ((eo8 & 3) << 3)), mb = (int)((em >> 13) | ((em8 & 3) << 3)), lb = (int)((el >> 13) | ((el8 & 3) << 3));
-      const int xb = ob + mb + lb;
-      uint32_t ov, mx, lx, S;                            // S = the 32 bits after the extra bits: the three state updates (<= 26 bits)
-      if (xb <= 31) {                                   // the usual case: all extra bits are in the top word
-        ov = top_bits(A, 0, ob); mx = top_bits(A, ob, mb); lx = top_bits(A, ob + mb, lb);
-        S = __funnelshift_l(B, A, (uint32_t)xb);
-      } else {
-        ov = top_bits(A, 0, ob);
-        const uint32_t a2 = peek32(W, t - ob);
-        mx = top_bits(a2, 0, mb); lx = top_bits(a2, mb, lb);
-        S = peek32(W, t - xb);
-      }
-      {
-        const int nl = (int)((el >> 9) & 15), nm = (int)((em >> 9) & 15), no = (int)((eo >> 9) & 15);   // <= 26 bits together
-        const uint32_t last = (i + 1 == nseq) ? 0u : ~0u;                                                     // no state update after the last sequence
-        sl = (el & 511) + (top_bits(S, 0, nl) & last);
-        sm = (em & 511) + (top_bits(S, nl, nm) & last);
-        so = (eo & 511) + (top_bits(S, nl + nm, no) & last);
-        t -= xb + ((nl + nm + no) & (int)last);
-      }
-      // ---- off the chain: values, repeat offsets (branch-free), positions ----
-      ov += 1u << ob;
-      const uint32_t ll = bases[el8 >> 2] + lx, ml = bases[40 + (em8 >> 2)] + mx;
-      // idx: 0 keeps the history, 1 swaps rep0/rep1, >= 2 rotates all three; a new offset rotates like idx 3
-      const bool fresh = ov > 3;
-      const uint32_t idx = fresh ? 3u : ov - 1 + (ll == 0);
-      const uint32_t cand = fresh ? ov - 3 : idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-      rep2 = idx >= 2 ? rep1 : rep2;
-      rep1 = idx >= 1 ? rep0 : rep1;
-      rep0 = cand;
-      const uint32_t offset = cand;
-      bad |= (offset == 0) | (lit_pos + ll > lit_size) | (offset > out_pos + ll);
-      __stcs(out + i, make_uint4(out_pos, lit_pos, offset, ml));
-      out_pos += ll + ml; lit_pos += ll;
-      big |= out_pos > cap;
-      // positions stay bounded even on garbage: a set flag stops KC from using them, and they cannot wrap within 65536 sequences
-    }
-    if (t != low) bad |= 1;                               // the stream must end exactly on its first bit
-    if (bad) err = ST_CORRUPT; else if (big) err = ST_BUFFER_TOO_SMALL;
+    L.t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);       // the sentinel bit itself is not payload
+    { const uint32_t a = peek32(L.W, L.t); L.sl = top_bits(a, 0, (int)I.ll_log); L.so = top_bits(a, (int)I.ll_log, (int)I.of_log);
+      L.sm = top_bits(a, (int)(I.ll_log + I.of_log), (int)I.ml_log); L.t -= (int)(I.ll_log + I.of_log + I.ml_log); }
+    L.rep0 = 1; L.rep1 = 4; L.rep2 = 8;
+    for (uint32_t i = 0; i + 1 < nseq; i++) L.step<false>(i);
+    L.step<true>(nseq - 1);
+    // positions stay bounded even on garbage (they cannot wrap within 65536 sequences), and KC checks every record before using it
+    if (L.t != low) err = ST_CORRUPT;                      // the stream must end exactly on its first bit
   }
-  out[nseq] = make_uint4(out_pos, lit_pos, 0, 0);           // sentinel: literal length of the last sequence, block totals
-  D->seq_status = err; D->out_end = out_pos; D->lit_end = lit_pos;
+  out[nseq] = make_uint4(L.out_pos, L.lit_pos, 0, 0);       // sentinel: literal length of the last sequence, block totals
+  D->seq_status = err; D->out_end = L.out_pos; D->lit_end = L.lit_pos;
 }
 
 // ---- KP kernel: prep_chunk (headers, Huffman table) followed by the sequence table build, one warp per chunk ----
@@ -756,6 +770,11 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
         const uint32_t ll = valid ? next_lit - r.y : 0;
         const uint32_t group_start = __shfl_sync(0xffffffffu, r.x, 0);
         const uint32_t d = r.x + ll;
+        // range checks (KB only decodes): a record that would read before the output, past the literals or write past the
+        // capacity ends the chunk before anything of its group is executed
+        const bool oob = valid && (r.z == 0 || r.z > d || r.y + ll > lit_size);
+        const bool over = valid && (unsigned long long)r.x + ll + r.w > cap;    // 64-bit: garbage lengths may wrap
+        if (__any_sync(0xffffffffu, oob || over)) { status = __any_sync(0xffffffffu, oob) ? ST_CORRUPT : ST_BUFFER_TOO_SMALL; break; }
         const bool indep = valid && (d - r.z + r.w <= group_start);            // whole source precedes this group's output
         // ---- piece-parallel phase: the literal run of every sequence and every independent match are cut into
         // destination-aligned 16-byte pieces; pieces are dealt to lanes round-robin, so the work per lane is
@@ -843,7 +862,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
       }
       // trailing literals
       const uint32_t out_end = D->out_end, lit_end = D->lit_end, rest = lit_size - lit_end;
-      if (rest > cap - out_end) status = ST_BUFFER_TOO_SMALL;
+      if (status != ST_OK) {}
+      else if (lit_end > lit_size) status = ST_CORRUPT;
+      else if (rest > cap - out_end) status = ST_BUFFER_TOO_SMALL;
       else {
         for (uint32_t k = lane; k < rest; k += 32) out[out_end + k] = L.at(lit_end + k);
         total = out_end + rest;
