@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
 
 // KC grid: a bounded number of resident CTAs per SM, each striding over chunks.  Fewer chunks in flight keep the
 // recently written output (the match sources) inside the 126 MB L2 instead of re-reading it from HBM.
-static int g_exec_ctas_per_sm = 16;
+static int g_exec_ctas_per_sm = 8;    // = what 64 registers x 128 threads leave resident: every CTA of the grid runs at once
 extern "C" void cuda_zstd_b200_tune_exec_ctas(int v) { if (v > 0) g_exec_ctas_per_sm = v; }
 static uint32_t exec_grid(uint32_t chunks, uint32_t sms) {
   const uint32_t blocks = (chunks + EXEC_WARPS - 1) / EXEC_WARPS, cap = sms * (uint32_t)g_exec_ctas_per_sm;
