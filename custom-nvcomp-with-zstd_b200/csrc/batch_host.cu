@@ -404,8 +404,11 @@ Status ZstdBatchManager::configure(const CompressionConfig &c) {
   return Status::SUCCESS;
 }
 CompressionConfig ZstdBatchManager::get_config() const { return pimpl_->cfg; }
-size_t ZstdBatchManager::get_compress_temp_size(size_t n) const { return pimpl_->enc_temp(1, &n); }
-size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const { return pimpl_->dec_temp(1, &n); }
+// single-buffer sizes include the tail that stages pageable host buffers (input; for compress also the worst-case output)
+size_t ZstdBatchManager::get_compress_temp_size(size_t n) const {
+  return n == 0 ? 0 : pimpl_->enc_temp(1, &n) + align_up(n, 256) + align_up(estimate_compressed_size(n, pimpl_->cfg.level), 256) + 256;
+}
+size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const { return n == 0 ? 0 : pimpl_->dec_temp(1, &n) + align_up(n, 256) + 256; }
 size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
 size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size(), v.data()); }
 size_t ZstdBatchManager::get_batch_decompress_temp_size(const std::vector<size_t> &v) const { return pimpl_->dec_temp(v.size(), v.data()); }
@@ -475,26 +478,62 @@ Status ZstdBatchManager::decompress_batch_preallocated(std::vector<BatchItem> &i
   return run_items(*pimpl_, false, items, ws, ws_bytes, stream);
 }
 
+// Single-buffer calls take device memory, pinned host memory (read/written in place over the bus) or, like the
+// reference's CPU route (manager.cu:1604-1668; tests/test_two_phase_unit.cu:56 passes a std::vector), plain pageable
+// host memory.  Pageable buffers are staged through the tail of the caller's workspace: the temp-size queries include
+// room for the input and, for compress, the worst-case output.  Nothing is allocated here.
+namespace {
+enum class Mem { DEVICE, PINNED, PAGEABLE };
+Mem mem_of(const void *p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return Mem::PAGEABLE; }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return Mem::DEVICE;
+  return at.type == cudaMemoryTypeHost ? Mem::PINNED : Mem::PAGEABLE;
+}
+size_t stage_room(size_t bytes) { return align_up(bytes, 256); }
+}  // namespace
+
+static Status single_buffer(ZstdBatchManager::Impl &I, bool compress, const void *src, size_t n, void *dst, size_t *dst_size, void *ws,
+                            size_t ws_bytes, cudaStream_t stream) {
+  const char *fn = compress ? "compress" : "decompress";
+  const bool stage_in = mem_of(src) == Mem::PAGEABLE, stage_out = mem_of(dst) == Mem::PAGEABLE;
+  const size_t cap = *dst_size;
+  const size_t tail = (stage_in ? stage_room(n) : 0) + (stage_out ? stage_room(cap) : 0);
+  if (tail > ws_bytes) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace has no room to stage pageable host buffers");
+  const size_t body = (ws_bytes - tail) & ~(size_t)255;
+  unsigned char *stage = static_cast<unsigned char *>(ws) + body;
+  const void *d_src = src;
+  void *d_dst = dst;
+  cudaError_t e;
+  if (stage_in) {
+    if ((e = cudaMemcpyAsync(stage, src, n, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    d_src = stage;
+  }
+  if (stage_out) d_dst = stage + (stage_in ? stage_room(n) : 0);
+  std::vector<BatchItem> it(1);
+  it[0].input_ptr = const_cast<void *>(d_src); it[0].input_size = n; it[0].output_ptr = d_dst; it[0].output_size = cap;
+  Status s = run_items(I, compress, it, ws, body, stream);
+  if (s != Status::SUCCESS) return it[0].status != Status::SUCCESS ? it[0].status : s;
+  if (stage_out) {
+    if ((e = cudaMemcpyAsync(dst, d_dst, it[0].output_size, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);
+  }
+  *dst_size = it[0].output_size;
+  return s;
+}
+
 Status ZstdBatchManager::compress(const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes, const void *dict,
                                   size_t dict_size, cudaStream_t stream, void *) {
   if (!src || !dst || !dst_size || !ws) return fail(Status::ERROR_INVALID_PARAMETER, "compress", "null argument");   // manager.cu:1549-1552
   if (n == 0) return fail(Status::ERROR_INVALID_PARAMETER, "compress", "zero-size input");                            // manager.cu:1554-1558
   if (dict || dict_size) return fail(Status::ERROR_NOT_IMPLEMENTED, "compress", "dictionaries are out of scope");
-  std::vector<BatchItem> it(1);
-  it[0].input_ptr = const_cast<void *>(src); it[0].input_size = n; it[0].output_ptr = dst; it[0].output_size = *dst_size;
-  Status s = run_items(*pimpl_, true, it, ws, ws_bytes, stream);
-  if (s == Status::SUCCESS) { *dst_size = it[0].output_size; return s; }
-  return it[0].status != Status::SUCCESS ? it[0].status : s;
+  return single_buffer(*pimpl_, true, src, n, dst, dst_size, ws, ws_bytes, stream);
 }
 Status ZstdBatchManager::decompress(const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes, cudaStream_t stream) {
   if (!src || !dst || !dst_size || !ws) return fail(Status::ERROR_INVALID_PARAMETER, "decompress", "null argument");
   if (n < 4) return fail(Status::ERROR_INVALID_PARAMETER, "decompress", "input shorter than a magic number");         // manager.cu:3202-3206
   if (*dst_size == 0) return fail(Status::ERROR_BUFFER_TOO_SMALL, "decompress", "zero output capacity");
-  std::vector<BatchItem> it(1);
-  it[0].input_ptr = const_cast<void *>(src); it[0].input_size = n; it[0].output_ptr = dst; it[0].output_size = *dst_size;
-  Status s = run_items(*pimpl_, false, it, ws, ws_bytes, stream);
-  if (s == Status::SUCCESS) { *dst_size = it[0].output_size; return s; }
-  return it[0].status != Status::SUCCESS ? it[0].status : s;
+  return single_buffer(*pimpl_, false, src, n, dst, dst_size, ws, ws_bytes, stream);
 }
 Status ZstdBatchManager::decompress_to_preallocated(const void *src, size_t n, void *out, size_t cap, size_t *actual, void *ws,
                                                     size_t ws_bytes, cudaStream_t stream) {
@@ -576,7 +615,17 @@ Status decompress_simple(const void *src, size_t n, void *dst, size_t *dst_size,
 // ============================================================================================
 namespace nvcomp_v5 {
 
-bool is_compatible_with_nvcomp_v5(u32 v) { return (v >> 16) == 5; }
+bool is_compatible_with_nvcomp_v5(u32 v) { return v == get_nvcomp_v5_format_version(); }   // reference nvcomp.cpp:153-155
+// a Zstandard or skippable frame magic at the front; the data may be device or host memory (reference nvcomp.cpp:129-151)
+bool is_nvcomp_v5_zstd_format(const void *data, size_t size) {
+  if (!data || size < 4) return false;
+  u32 magic = 0;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, data) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+    if (cudaMemcpy(&magic, data, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  } else { (void)cudaGetLastError(); std::memcpy(&magic, data, 4); }
+  return magic == ZSTD_MAGIC || (magic & 0xFFFFFFF0u) == 0x184D2A50u;
+}
 NvcompV5Options to_nvcomp_v5_opts(const CompressionConfig &c) {
   NvcompV5Options o;
   o.level = c.level; o.chunk_size = c.block_size; o.enable_checksum = c.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY;

@@ -16,6 +16,7 @@
 namespace cuda_zstd {
 namespace nvcomp_v5 {
 
+bool is_nvcomp_v5_zstd_format(const void *compressed_data, size_t compressed_size);   // device or host pointer
 constexpr u32 get_nvcomp_v5_format_version() { return 0x00050000; }
 bool is_compatible_with_nvcomp_v5(u32 format_version);
 

@@ -13,6 +13,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 namespace cuda_zstd {
 
@@ -175,6 +176,13 @@ constexpr u32 DEFAULT_COMPRESSION_LEVEL = 3;
 constexpr u32 MIN_WINDOW_LOG = 10;
 constexpr u32 MAX_WINDOW_LOG = 31;
 constexpr u32 DEFAULT_BLOCK_SIZE = 128 * 1024;
+// headroom the allocation helpers (cuda_zstd_safe_alloc.h) leave free; reference include/cuda_zstd_types.h:447-450
+constexpr size_t VRAM_SAFETY_BUFFER_BYTES = 256ULL * 1024 * 1024;
+constexpr size_t RAM_SAFETY_BUFFER_BYTES = 512ULL * 1024 * 1024;
+
+// small helpers callers of the batch path use (reference include/cuda_zstd_types.h:505-511)
+inline float get_compression_ratio(size_t uncompressed, size_t compressed) { return compressed ? (float)uncompressed / (float)compressed : 0.0f; }
+inline bool is_valid_compression_level(int level) { return level >= (int)MIN_COMPRESSION_LEVEL && level <= (int)MAX_COMPRESSION_LEVEL; }
 
 } // namespace cuda_zstd
 #endif // CUDA_ZSTD_TYPES_H

@@ -126,6 +126,25 @@ static void test_single_buffer_and_inference_api() {
   std::vector<unsigned char> back(n);
   CUDA_OK(cudaMemcpy(back.data(), d_back, n, cudaMemcpyDeviceToHost));
   CHECK(std::memcmp(back.data(), h.data(), n) == 0);
+  // pageable host buffers on either side are staged through the workspace tail (tests/test_two_phase_unit.cu:56 passes
+  // a std::vector as the compress input): 256 KB = two blocks in one frame
+  {
+    const size_t m = 256 * 1024;
+    std::vector<unsigned char> hi(m), hc(mgr.get_max_compressed_size(m)), hb(m);
+    fill(hi, 9);
+    const size_t wb = mgr.get_compress_temp_size(m);
+    void *w2;
+    CUDA_OK(cudaMalloc(&w2, wb));
+    size_t hcs = hc.size();
+    CHECK(mgr.compress(hi.data(), m, hc.data(), &hcs, w2, wb, nullptr, 0) == Status::SUCCESS && hcs > 0 && hcs < m);
+    CHECK(hc[0] == 0x28 && hc[1] == 0xB5 && hc[2] == 0x2F && hc[3] == 0xFD);
+    size_t hbs = m;
+    CHECK(mgr.decompress(hc.data(), hcs, hb.data(), &hbs, w2, wb) == Status::SUCCESS && hbs == m);
+    CHECK(std::memcmp(hb.data(), hi.data(), m) == 0);
+    size_t small = 64;                                             // no room to stage the output: refused, not a fault
+    CHECK(mgr.compress(hi.data(), m, hc.data(), &hcs, w2, small, nullptr, 0) == Status::ERROR_BUFFER_TOO_SMALL);
+    cudaFree(w2);
+  }
   // corrupt magic -> ERROR_INVALID_MAGIC
   unsigned char zero = 0;
   CUDA_OK(cudaMemcpy(d_comp, &zero, 1, cudaMemcpyHostToDevice));
