@@ -292,6 +292,72 @@ public:
     return std::max(e, dec_fixed(n) + wave_of(n) * (size_t)(64 * 1024));
   }
 
+  // ---- one large buffer as ONE frame of independently encoded 128 KB blocks ----
+  // Every block is a work item of the batch encoder (block mode: header + payload only, repeat offsets unknown at the
+  // block start), a device scan places the blocks behind the frame header and the pack kernel moves them.  Workspace:
+  // [header | 5 block tables + offsets | encoder scratch for min(B, resident) CTAs | B staging slots].
+  static constexpr size_t BIG_BLOCK = 128 * 1024;
+  static size_t big_blocks(size_t n) { return (n + BIG_BLOCK - 1) / BIG_BLOCK; }
+  static size_t big_slot() { return align_up(BIG_BLOCK + 3 + 64, 256); }
+  static size_t big_tables(size_t B) { return align_up(B * 44 + (B + 1) * 8, 256); }
+  size_t big_temp(size_t n) const {
+    const size_t B = big_blocks(n);
+    return b200zstd::WS_HEADER_BYTES + big_tables(B) + (size_t)enc_grid(B) * b200zstd::encode_cta_scratch_bytes(enc_params()) + B * big_slot();
+  }
+  Status compress_big(const void *d_src, size_t n, void *d_dst, size_t *dst_size, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    const char *fn = "compress";
+    const size_t B = big_blocks(n), cap = *dst_size;
+    const bool ck = cfg.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
+    if (n > 0xFFFF0000ull) return fail(Status::ERROR_UNSUPPORTED_VERSION, fn, "single buffers of 4 GiB and more are not supported");
+    if (ws_bytes < big_temp(n)) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
+    // frame header: windowed (128 KB: no match leaves its block) with a 4-byte content size (RFC 8878 3.1.1.1)
+    unsigned char hdr[10] = {0x28, 0xB5, 0x2F, 0xFD, (unsigned char)(0x80 | (ck ? 0x04 : 0)), (17 - 10) << 3,
+                             (unsigned char)n, (unsigned char)(n >> 8), (unsigned char)(n >> 16), (unsigned char)(n >> 24)};
+    if (cap < sizeof hdr + n + 3 * B + (ck ? 4 : 0)) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "output capacity below the worst case");
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    u32 *counter = reinterpret_cast<u32 *>(w);
+    unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
+    unsigned char *scratch = tab + big_tables(B);
+    const int grid = enc_grid(B);
+    unsigned char *slots = scratch + (size_t)grid * b200zstd::encode_cta_scratch_bytes(enc_params());
+    std::vector<u64> host(4 * B);
+    for (size_t i = 0; i < B; ++i) {
+      host[i] = (u64)(uintptr_t)(static_cast<const unsigned char *>(d_src) + i * BIG_BLOCK);
+      host[B + i] = std::min(BIG_BLOCK, n - i * BIG_BLOCK);
+      host[2 * B + i] = (u64)(uintptr_t)(slots + i * big_slot());
+      host[3 * B + i] = big_slot();
+    }
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(tab, host.data(), 4 * B * 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = cudaMemcpyAsync(d_dst, hdr, sizeof hdr, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    u64 *d_offsets = reinterpret_cast<u64 *>(tab + 4 * B * 8);
+    u32 *d_status = reinterpret_cast<u32 *>(tab + 4 * B * 8 + (B + 1) * 8);
+    b200zstd::EncodeArgs a{};
+    a.in_ptrs = reinterpret_cast<const void *const *>(tab); a.in_sizes = reinterpret_cast<const size_t *>(tab + B * 8);
+    a.out_ptrs = reinterpret_cast<void *const *>(tab + 2 * B * 8); a.out_sizes = reinterpret_cast<size_t *>(tab + 3 * B * 8);
+    a.statuses = d_status; a.counter = counter; a.scratch = scratch; a.n = (uint32_t)B; a.block_mode = 1; a.prm = enc_params();
+    a.prm.checksum = 0;
+    if ((e = b200zstd::launch_encode_batch(a, grid, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = b200zstd::launch_scan_sizes(a.out_sizes, B, sizeof hdr, reinterpret_cast<uint64_t *>(d_offsets), stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = b200zstd::launch_pack(a.out_ptrs, a.out_sizes, reinterpret_cast<const uint64_t *>(d_offsets), B, d_dst, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    last_launches = 3;
+    if (ck) {
+      if ((e = b200zstd::launch_frame_checksum(d_src, n, d_dst, reinterpret_cast<const uint64_t *>(d_offsets + B), stream)) != cudaSuccess) return cuda_fail(e, fn);
+      last_launches = 4;
+    }
+    std::vector<u32> st(B);
+    u64 total = 0;
+    if ((e = cudaMemcpyAsync(st.data(), d_status, B * 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = cudaMemcpyAsync(&total, d_offsets + B, 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);
+    for (size_t i = 0; i < B; ++i)
+      if (st[i] != 0) return fail(static_cast<Status>(st[i]), fn, "a block failed to encode");
+    *dst_size = (size_t)total + (ck ? 4 : 0);
+    stats.input_bytes += n; stats.output_bytes += *dst_size; stats.bytes_compressed += n; stats.bytes_produced += *dst_size;
+    return Status::SUCCESS;
+  }
+
   // Direction-agnostic batch driver.  tables_on_device: the five tables already live in device
   // memory (no staging, and with sync == false no host synchronisation at all).
   Status run(bool compress, const void *const *in_ptrs, const size_t *in_sizes, size_t n, void *const *out_ptrs,
@@ -406,7 +472,9 @@ Status ZstdBatchManager::configure(const CompressionConfig &c) {
 CompressionConfig ZstdBatchManager::get_config() const { return pimpl_->cfg; }
 // single-buffer sizes include the tail that stages pageable host buffers (input; for compress also the worst-case output)
 size_t ZstdBatchManager::get_compress_temp_size(size_t n) const {
-  return n == 0 ? 0 : pimpl_->enc_temp(1, &n) + align_up(n, 256) + align_up(estimate_compressed_size(n, pimpl_->cfg.level), 256) + 256;
+  if (n == 0) return 0;
+  const size_t core = n > Impl::BIG_BLOCK ? std::max(pimpl_->big_temp(n), pimpl_->enc_temp(1, &n)) : pimpl_->enc_temp(1, &n);
+  return core + align_up(n, 256) + align_up(estimate_compressed_size(n, pimpl_->cfg.level), 256) + 256;
 }
 size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const { return n == 0 ? 0 : pimpl_->dec_temp(1, &n) + align_up(n, 256) + 256; }
 size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
@@ -512,8 +580,17 @@ static Status single_buffer(ZstdBatchManager::Impl &I, bool compress, const void
   if (stage_out) d_dst = stage + (stage_in ? stage_room(n) : 0);
   std::vector<BatchItem> it(1);
   it[0].input_ptr = const_cast<void *>(d_src); it[0].input_size = n; it[0].output_ptr = d_dst; it[0].output_size = cap;
-  Status s = run_items(I, compress, it, ws, body, stream);
-  if (s != Status::SUCCESS) return it[0].status != Status::SUCCESS ? it[0].status : s;
+  Status s;
+  if (compress && n > ZstdBatchManager::Impl::BIG_BLOCK) {
+    // more than one block: the blocks are encoded side by side and assembled into one frame
+    size_t out = cap;
+    s = I.compress_big(d_src, n, d_dst, &out, ws, body, stream);
+    if (s != Status::SUCCESS) return s;
+    it[0].output_size = out;
+  } else {
+    s = run_items(I, compress, it, ws, body, stream);
+    if (s != Status::SUCCESS) return it[0].status != Status::SUCCESS ? it[0].status : s;
+  }
   if (stage_out) {
     if ((e = cudaMemcpyAsync(dst, d_dst, it[0].output_size, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);

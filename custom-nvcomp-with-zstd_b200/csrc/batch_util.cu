@@ -3,6 +3,7 @@
 // place the batch path needs it: turning per-chunk compressed sizes into packed offsets
 // ("device-side offset gather").
 #include "zstd_device_api.h"
+#include "zstd_common.cuh"
 #include <cuda_runtime.h>
 
 namespace b200zstd {
@@ -72,6 +73,22 @@ __global__ void __launch_bounds__(256) pack_kernel(const void *const *__restrict
       for (size_t k = threadIdx.x; k < len; k += blockDim.x) dst[k] = src[k];
     }
   }
+}
+
+// Content checksum of a frame assembled from independently encoded blocks: XXH64 is one sequential chain of 32-byte
+// stripes, so one warp walks the whole buffer (16-byte loads, four accumulator lanes) and drops the low 32 bits behind
+// the last block.  `where` = device word holding the offset at which the 4 bytes go.
+__global__ void __launch_bounds__(32) frame_checksum_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ dst,
+                                                            const uint64_t *__restrict__ where) {
+  const uint64_t h = xxh64_warp(src, (uint32_t)n, threadIdx.x);
+  if (threadIdx.x == 0) {
+    uint8_t *p = dst + *where;
+    p[0] = (uint8_t)h; p[1] = (uint8_t)(h >> 8); p[2] = (uint8_t)(h >> 16); p[3] = (uint8_t)(h >> 24);
+  }
+}
+cudaError_t launch_frame_checksum(const void *d_src, size_t n, void *d_dst, const uint64_t *d_where, cudaStream_t stream) {
+  frame_checksum_kernel<<<1, 32, 0, stream>>>((const uint8_t *)d_src, n, (uint8_t *)d_dst, d_where);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream) {

@@ -70,12 +70,15 @@ struct EncodeArgs {
   uint32_t *counter;
   uint8_t *scratch;         // grid * encode_cta_scratch_bytes()
   uint32_t n;
+  uint32_t block_mode;      // 1: items are the consecutive <= 128 KB blocks of one frame (no frame header / checksum, see kernel)
   EncodeParams prm;
 };
 size_t encode_cta_scratch_bytes(const EncodeParams &prm);
 cudaError_t launch_encode_batch(const EncodeArgs &args, int grid, cudaStream_t stream);
 int encode_ctas_per_sm(const EncodeParams &prm);
 
+// low 32 bits of XXH64(src[0..n)) written at dst + *d_where (n < 4 GiB)
+cudaError_t launch_frame_checksum(const void *d_src, size_t n, void *d_dst, const uint64_t *d_where, cudaStream_t stream);
 // exclusive scan of sizes (+ base) -> offsets[0..n], offsets[n] = base + total; single CTA.
 cudaError_t launch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream);
 // gather frames into a packed buffer

@@ -466,7 +466,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(Enco
     else if (n == 0) status = ST_INVALID_PARAMETER;                       // reference: manager.cu:1554-1558
     else if (n > 0xFFFF0000ull) status = ST_UNSUPPORTED;
     const size_t nblocks = (n + BLOCK_BYTES - 1) / BLOCK_BYTES;
-    if (status == ST_OK && cap < (size_t)frame_header_size(n) + n + 3 * nblocks + (P.checksum ? 4 : 0)) status = ST_BUFFER_TOO_SMALL;
+    // block mode: the items are the consecutive blocks of ONE frame (a large single buffer cut into independent
+    // 128 KB blocks, one warp each); an item emits block header + payload only, the caller assembles the frame
+    const bool blocks_only = A.block_mode != 0;
+    if (status == ST_OK && blocks_only && n > BLOCK_BYTES) status = ST_INVALID_PARAMETER;
+    if (status == ST_OK && cap < (blocks_only ? 0 : (size_t)frame_header_size(n) + (P.checksum ? 4 : 0)) + n + 3 * nblocks) status = ST_BUFFER_TOO_SMALL;
 
     if (status == ST_OK) {
       ParseCtx C;
@@ -483,13 +487,19 @@ __global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(Enco
       C.tab2 = P.long_log ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
       C.chain = P.chain_depth > 0 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
 
-      if (lane == 0) op = write_frame_header(dst, n, P.checksum != 0);
-      op = __shfl_sync(0xffffffffu, (unsigned long long)op, 0);
+      if (!blocks_only) {
+        if (lane == 0) op = write_frame_header(dst, n, P.checksum != 0);
+        op = __shfl_sync(0xffffffffu, (unsigned long long)op, 0);
+      }
+      // a block encoded on its own does not know the repeat offsets the decoder will hold when it gets there: 0 =
+      // unknown, never matched against and never equal to a real offset, so such a block only uses the history it
+      // builds itself (the decoder's own history shifts the same way, RFC 8878 3.1.1.5)
       uint32_t rep[3] = {1, 4, 8};
+      if (blocks_only && chunk_id != 0) { rep[0] = 0; rep[1] = 0; rep[2] = 0; }
       size_t ip_chunk = 0;
       while (ip_chunk < n) {
         const uint32_t bn = (uint32_t)min((size_t)BLOCK_BYTES, n - ip_chunk);
-        const bool last = ip_chunk + bn == n;
+        const bool last = blocks_only ? chunk_id + 1 == A.n : ip_chunk + bn == n;
         const uint32_t blk_off = (uint32_t)ip_chunk;
         // ---- RLE block? ----
         {
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(Enco
               }
               c1 = (int64_t)((pos & ~0xFFFFu) | (C.t1_global ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
               if (c1 >= (int64_t)pos) c1 -= 0x10000;
-              const bool vr = blk_off + pos >= rep[0];
+              const bool vr = rep[0] != 0 && blk_off + pos >= rep[0];
               const uint64_t x2 = c2 >= 0 ? C.src.ld64(blk_off + (uint32_t)c2) : ~v;
               const uint64_t x1 = c1 >= 0 ? C.src.ld64(blk_off + (uint32_t)c1) : ~v;
               const uint64_t xr = vr ? C.src.ld64(blk_off + pos - rep[0]) : ~v;
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(Enco
                 if (d == 0) break;
                 c -= d;
               }
-              if (blk_off + pos >= rep[0]) {
+              if (rep[0] != 0 && blk_off + pos >= rep[0]) {
                 uint32_t l = common8(v, C.src.ld64(blk_off + pos - rep[0]));
                 if (l == 8) l = extend_lane(C, pos, rep[0], P.lane_cap);
                 if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
@@ -657,7 +667,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(Enco
         __syncwarp();
         ip_chunk += bn;
       }
-      if (P.checksum) {
+      if (P.checksum && !blocks_only) {
         // hash in <= 1 GiB pieces is not needed: chunks are far below 4 GiB (checked above)
         const uint64_t h = xxh64_warp(chunk, (uint32_t)n, lane);
         if (lane == 0) { dst[op] = (uint8_t)h; dst[op + 1] = (uint8_t)(h >> 8); dst[op + 2] = (uint8_t)(h >> 16); dst[op + 3] = (uint8_t)(h >> 24); }

@@ -16,7 +16,16 @@ TESTS="test_c_api.cpp test_c_api_edge_cases.cu test_compressible_data.cu test_co
 test_extended_validation.cu test_gpu_bitstream.cu test_inference_api.cu test_lz77_comprehensive.cu test_metadata_roundtrip.cu
 test_nvcomp_batch.cu test_nvcomp_interface.cu test_parallel_compression.cu test_rfc8878_compliance.cu test_roundtrip.cu
 test_scale_repro.cu test_two_phase_unit.cu"
+# ... and the reference's benchmark programs of the same path (run by hand: tools/run_ref_benchmarks.sh)
+BENCHES="benchmark_batch_throughput.cu benchmark_nvcomp_interface.cu benchmark_c_api.cu benchmark_block_size.cu"
 ok=0; bad=0
+build_bench() {
+  local f="$1" t="${1%.*}"
+  if [ "$OUT/$t" -nt "$REF/benchmarks/$f" ] && [ "$OUT/$t" -nt "$LIBDIR/libcuda_zstd_b200.so" ]; then return 0; fi
+  nvcc -std=c++17 -x cu -O2 -Xcompiler -fopenmp -gencode arch=compute_100a,code=sm_100a -I"$ROOT/include" -I"$REF/benchmarks" -I"$REF/tests" \
+       "$REF/benchmarks/$f" -o "$OUT/$t" -L"$LIBDIR" -lcuda_zstd_b200 -lgomp \
+       -Xlinker -rpath -Xlinker '$ORIGIN/../../../custom-nvcomp-with-zstd_b200' > "$OUT/$t.build.log" 2>&1
+}
 build_one() {
   local f="$1" t="${1%.*}"
   if [ "$OUT/$t" -nt "$REF/tests/$f" ] && [ "$OUT/$t" -nt "$LIBDIR/libcuda_zstd_b200.so" ]; then return 0; fi
@@ -25,7 +34,8 @@ build_one() {
 }
 pids=()
 for f in $TESTS; do build_one "$f" & pids+=($!); if [ ${#pids[@]} -ge 6 ]; then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi; done
+for f in $BENCHES; do build_bench "$f" & done
 wait
-for f in $TESTS; do t="${f%.*}"; if [ -x "$OUT/$t" ]; then ok=$((ok+1)); else bad=$((bad+1)); echo "FAILED to build $t (see $OUT/$t.build.log)"; fi; done
+for f in $TESTS $BENCHES; do t="${f%.*}"; if [ -x "$OUT/$t" ]; then ok=$((ok+1)); else bad=$((bad+1)); echo "FAILED to build $t (see $OUT/$t.build.log)"; fi; done
 echo "reference test programs built against the drop-in: $ok ok, $bad failed"
 [ "$bad" -eq 0 ]

@@ -145,6 +145,36 @@ static void test_single_buffer_and_inference_api() {
     CHECK(mgr.compress(hi.data(), m, hc.data(), &hcs, w2, small, nullptr, 0) == Status::ERROR_BUFFER_TOO_SMALL);
     cudaFree(w2);
   }
+  // a checksummed multi-block frame (blocks encoded side by side, XXH64 over the whole content appended): the decoder
+  // verifies it, and a flipped payload byte is reported
+  {
+    CompressionConfig cc = CompressionConfig::from_level(3);
+    cc.checksum = ChecksumPolicy::COMPUTE_AND_VERIFY;
+    ZstdBatchManager cm(cc);
+    const size_t m = (1 << 20) + 777;
+    std::vector<unsigned char> hi(m), hb(m);
+    fill(hi, 11);
+    unsigned char *di, *dc, *db; void *w3;
+    const size_t cb = cm.get_max_compressed_size(m), wb = cm.get_compress_temp_size(m);
+    CUDA_OK(cudaMalloc(&di, m)); CUDA_OK(cudaMalloc(&dc, cb)); CUDA_OK(cudaMalloc(&db, m)); CUDA_OK(cudaMalloc(&w3, wb));
+    CUDA_OK(cudaMemcpy(di, hi.data(), m, cudaMemcpyHostToDevice));
+    size_t cs = cb;
+    CHECK(cm.compress(di, m, dc, &cs, w3, wb, nullptr, 0) == Status::SUCCESS && cs > 14 && cs < m);
+    unsigned char fh[6];
+    CUDA_OK(cudaMemcpy(fh, dc, 6, cudaMemcpyDeviceToHost));
+    CHECK((fh[4] & 0x04) && (fh[4] >> 6) == 2 && fh[5] == 0x38);
+    size_t os = m;
+    CHECK(cm.decompress(dc, cs, db, &os, w3, wb) == Status::SUCCESS && os == m);
+    CUDA_OK(cudaMemcpy(hb.data(), db, m, cudaMemcpyDeviceToHost));
+    CHECK(std::memcmp(hb.data(), hi.data(), m) == 0);
+    unsigned char last4[4];
+    CUDA_OK(cudaMemcpy(last4, dc + cs - 4, 4, cudaMemcpyDeviceToHost));
+    last4[0] ^= 0x55;
+    CUDA_OK(cudaMemcpy(dc + cs - 4, last4, 4, cudaMemcpyHostToDevice));
+    os = m;
+    CHECK(cm.decompress(dc, cs, db, &os, w3, wb) == Status::ERROR_CHECKSUM_FAILED);
+    cudaFree(di); cudaFree(dc); cudaFree(db); cudaFree(w3);
+  }
   // corrupt magic -> ERROR_INVALID_MAGIC
   unsigned char zero = 0;
   CUDA_OK(cudaMemcpy(d_comp, &zero, 1, cudaMemcpyHostToDevice));

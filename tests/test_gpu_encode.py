@@ -123,3 +123,38 @@ def test_scan_and_pack(oracle, pkg):
     codec.pack(ptrs, d_sizes, off0, packed)
     back, bsz = codec.decompress_chunks(packed, off0.cpu().numpy()[:-1].astype(np.uint64), sizes, chunk)
     assert torch.equal(back, dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, 3, 5, 9])
+def test_large_single_buffer_is_one_frame_of_parallel_blocks(oracle, libzstd, pkg, level):
+    """a single buffer above 128 KB is cut into independent 128 KB blocks encoded side by side and
+    assembled into ONE stock frame (windowed header, 4-byte content size).  libzstd and the oracle must decode it."""
+    if True:
+        for n in (131073, (1 << 20) + 12345, 6 << 20):
+            x = oracle.gen_batch(65536, (n + 65535) // 65536, 0, 26000)[:n].copy()
+            if n > (4 << 20):
+                x[1 << 20:(1 << 20) + 300000] = 7                       # an all-RLE block and a partly constant one
+                x[3 << 20:(3 << 20) + 131072] = np.frombuffer(np.random.default_rng(5).bytes(131072), np.uint8)  # a raw block
+            xd = torch.from_numpy(x).cuda()
+            s = pkg.ZstdSingle(level)
+            # (the single-buffer C API has no checksum switch: checksummed big frames are covered by tests/cpp)
+            cap = n + n // 255 + 3 * ((n + 131071) // 131072) + 512
+            comp = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            w = torch.empty(s.compress_workspace(n), dtype=torch.uint8, device="cuda")
+            rc, csz = s.compress(xd, n, comp, cap, w, w.numel())
+            assert rc == 0 and 0 < csz < n
+            frame = comp.cpu().numpy()[:csz]
+            assert frame[4] & 0x20 == 0 and frame[4] >> 6 == 2 and frame[5] == 0x38        # windowed, 4-byte content size, 128 KB window
+            assert libzstd.frame_content_size(frame) == n
+            assert np.array_equal(libzstd.decompress(frame, n), x)
+            rc2, out = oracle.decompress(frame, n)
+            assert rc2 == 0 and np.array_equal(out, x)
+            # and this library decodes its own multi-block frame
+            back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            wd = torch.empty(max(s.decompress_workspace(csz), 1), dtype=torch.uint8, device="cuda")
+            rc, dsz = s.decompress(comp, csz, back, n, wd, wd.numel())
+            assert rc == 0 and dsz == n and torch.equal(back, xd)
+            # capacity below the worst case is refused up front
+            assert s.compress(xd, n, comp, n // 2, w, w.numel())[0] == 7
+            s.close()
