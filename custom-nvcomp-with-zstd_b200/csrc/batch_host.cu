@@ -217,6 +217,7 @@ public:
   int sm_count = 0;
   int dec_ctas_per_sm = 1;
   int last_launches = 0;
+  bool bare_mode = false;      // run(): the items are the block units of one frame (decompress_big)
   std::mutex mu;   // one manager per thread is the contract; the lock keeps misuse safe (reference: api_mutex)
   b200zstd::FastOverlap overlap{};     // helper stream + events, created on first decode (no device memory)
   bool overlap_ready = false;
@@ -358,6 +359,53 @@ public:
     return Status::SUCCESS;
   }
 
+  // ---- one multi-block frame decoded block-parallel (decode half) ----
+  // launch_split_frame cuts the frame into block units (speculating that every block but the last regenerates 128 KB),
+  // the units go through the batch fast path as bare blocks, the whole-content checksum is verified by one warp.
+  // Returns ERROR_NOT_IMPLEMENTED when the frame is not of that kind or the workspace is too small for it: the caller
+  // then decodes serially (general kernel), which is also what settles any error a unit reports.
+  size_t big_dec_tail(size_t B) const { return align_up(B * 32 + sizeof(b200zstd::SplitInfo) + 64, 256); }
+  size_t big_dec_temp(size_t n, size_t B) const { return dec_fixed(B) + align_up(8 * n + 3072 * B, 256) + big_dec_tail(B); }
+  Status decompress_big(const void *d_src, size_t n, void *d_dst, size_t cap, size_t *out, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    const char *fn = "decompress";
+    const size_t Bcap = (cap + BIG_BLOCK - 1) / BIG_BLOCK;
+    if (Bcap < 2 || Bcap > 0xFFFFFFu || ws_bytes < big_dec_temp(n, Bcap)) return Status::ERROR_NOT_IMPLEMENTED;
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t tail = big_dec_tail(Bcap), body = (ws_bytes - tail) & ~(size_t)255;
+    unsigned char *t = static_cast<unsigned char *>(ws) + body;
+    const void **u_in = reinterpret_cast<const void **>(t);
+    size_t *u_in_sz = reinterpret_cast<size_t *>(t + Bcap * 8);
+    void **u_out = reinterpret_cast<void **>(t + Bcap * 16);
+    size_t *u_out_sz = reinterpret_cast<size_t *>(t + Bcap * 24);
+    b200zstd::SplitInfo *d_info = reinterpret_cast<b200zstd::SplitInfo *>(t + Bcap * 32);
+    u32 *d_flag = reinterpret_cast<u32 *>(t + Bcap * 32 + sizeof(b200zstd::SplitInfo));
+    cudaError_t e;
+    if ((e = b200zstd::launch_split_frame(d_src, n, d_dst, cap, (uint32_t)Bcap, u_in, u_in_sz, u_out, u_out_sz, d_info, stream)) != cudaSuccess)
+      return cuda_fail(e, fn);
+    b200zstd::SplitInfo info{};
+    if ((e = cudaMemcpyAsync(&info, d_info, sizeof info, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if (!info.ok || info.units < 2) return Status::ERROR_NOT_IMPLEMENTED;
+    std::vector<u32> st;
+    bare_mode = true;
+    Status s = run(false, u_in, u_in_sz, info.units, u_out, u_out_sz, nullptr, true, ws, body, stream, true, &st, nullptr);
+    bare_mode = false;
+    const int launches = last_launches + 1;
+    if (s != Status::SUCCESS) return Status::ERROR_NOT_IMPLEMENTED;                  // some unit was not self-contained: serial decode decides
+    if (info.has_checksum && cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY) {
+      u32 bad = 0;
+      if ((e = b200zstd::launch_verify_checksum(d_dst, (size_t)info.content_size, static_cast<const unsigned char *>(d_src) + info.checksum_off,
+                                                d_flag, stream)) != cudaSuccess) return cuda_fail(e, fn);
+      if ((e = cudaMemcpyAsync(&bad, d_flag, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+      if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);
+      if (bad) return fail(Status::ERROR_CHECKSUM_FAILED, fn, "content checksum mismatch");
+      last_launches = launches + 1;
+    } else last_launches = launches;
+    *out = (size_t)info.content_size;
+    stats.input_bytes += n; stats.output_bytes += *out; stats.bytes_decompressed += *out;
+    return Status::SUCCESS;
+  }
+
   // Direction-agnostic batch driver.  tables_on_device: the five tables already live in device
   // memory (no staging, and with sync == false no host synchronisation at all).
   Status run(bool compress, const void *const *in_ptrs, const size_t *in_sizes, size_t n, void *const *out_ptrs,
@@ -425,6 +473,8 @@ public:
         f.group_counters = counter + 48;
         f.sm_count = sm_count;
         f.general_grid = dec_grid(m);
+        f.bare_blocks = bare_mode ? 1u : 0u;
+        f.unit_base = (uint32_t)w0;
         int k = 0;
         e = b200zstd::launch_decode_fast(f, stream, get_overlap(), &k);
         last_launches += k;
@@ -476,7 +526,14 @@ size_t ZstdBatchManager::get_compress_temp_size(size_t n) const {
   const size_t core = n > Impl::BIG_BLOCK ? std::max(pimpl_->big_temp(n), pimpl_->enc_temp(1, &n)) : pimpl_->enc_temp(1, &n);
   return core + align_up(n, 256) + align_up(estimate_compressed_size(n, pimpl_->cfg.level), 256) + 256;
 }
-size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const { return n == 0 ? 0 : pimpl_->dec_temp(1, &n) + align_up(n, 256) + 256; }
+size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const {
+  if (n == 0) return 0;
+  // the decompressed size is not known here: provision the block-parallel path for a ratio of 16 (at most 4096 blocks);
+  // a frame that needs more decodes serially
+  const size_t est = std::min<size_t>(4096, (16 * n + Impl::BIG_BLOCK - 1) / Impl::BIG_BLOCK);
+  const size_t core = est >= 2 ? std::max(pimpl_->dec_temp(1, &n), pimpl_->big_dec_temp(n, est)) : pimpl_->dec_temp(1, &n);
+  return core + align_up(n, 256) + 256;
+}
 size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
 size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size(), v.data()); }
 size_t ZstdBatchManager::get_batch_decompress_temp_size(const std::vector<size_t> &v) const { return pimpl_->dec_temp(v.size(), v.data()); }
@@ -588,8 +645,18 @@ static Status single_buffer(ZstdBatchManager::Impl &I, bool compress, const void
     if (s != Status::SUCCESS) return s;
     it[0].output_size = out;
   } else {
-    s = run_items(I, compress, it, ws, body, stream);
-    if (s != Status::SUCCESS) return it[0].status != Status::SUCCESS ? it[0].status : s;
+    s = Status::ERROR_NOT_IMPLEMENTED;
+    if (!compress && cap > ZstdBatchManager::Impl::BIG_BLOCK) {
+      // possibly a multi-block frame: try its blocks side by side; anything but success or a checksum verdict falls through
+      size_t out = 0;
+      s = I.decompress_big(d_src, n, d_dst, cap, &out, ws, body, stream);
+      if (s == Status::SUCCESS) it[0].output_size = out;
+      else if (s == Status::ERROR_CHECKSUM_FAILED) return s;
+    }
+    if (s != Status::SUCCESS) {
+      s = run_items(I, compress, it, ws, body, stream);
+      if (s != Status::SUCCESS) return it[0].status != Status::SUCCESS ? it[0].status : s;
+    }
   }
   if (stage_out) {
     if ((e = cudaMemcpyAsync(dst, d_dst, it[0].output_size, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
@@ -644,7 +711,12 @@ Status ZstdBatchManager::decompress_async_no_sync(const void *src, size_t n, voi
   e = b200zstd::launch_decode_batch(a, 1, stream);
   return e == cudaSuccess ? Status::SUCCESS : cuda_fail(e, "decompress_async_no_sync");
 }
-size_t ZstdBatchManager::get_inference_workspace_size(size_t mc, size_t) const { return pimpl_->dec_temp(1, &mc); }
+// both sizes are known here, so the block-parallel path for multi-block frames is provisioned exactly
+size_t ZstdBatchManager::get_inference_workspace_size(size_t mc, size_t mo) const {
+  const size_t B = (mo + Impl::BIG_BLOCK - 1) / Impl::BIG_BLOCK;
+  const size_t core = B >= 2 ? std::max(pimpl_->dec_temp(1, &mc), pimpl_->big_dec_temp(mc, B)) : pimpl_->dec_temp(1, &mc);
+  return core + align_up(mc, 256) + 256;
+}
 Status ZstdBatchManager::allocate_inference_workspace(size_t mc, size_t mo, void **p, size_t *sz) {
   if (!p || !sz) return Status::ERROR_INVALID_PARAMETER;
   *sz = get_inference_workspace_size(mc, mo);

@@ -100,15 +100,24 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
     __syncwarp();
     do {
       if (src == nullptr || (dst == nullptr && dst_cap != 0) || src_size < 4) { status = ST_INVALID_PARAMETER; break; }
+      uint32_t n, h;
+      uint64_t fcs;
+      int has_ck;
+      if (F.bare_blocks) {
+        // a unit cut out of a multi-block frame: no frame header, and it must regenerate exactly its capacity
+        if (src_size > 0x7FFFFFFFull || dst_cap > BLOCK_MAX) { status = ST_CORRUPT; break; }
+        n = (uint32_t)src_size; h = 0; fcs = dst_cap; has_ck = 0;
+      } else {
       const uint32_t magic = ld_le32(src);
       if ((magic & 0xFFFFFFF0u) == ZSTD_SKIP_MAGIC) { route = true; break; }
       if (magic != ZSTD_FRAME_MAGIC) { status = ST_INVALID_MAGIC; break; }
       if (src_size > 0x7FFFFFFFull) { route = true; break; }
-      const uint32_t n = (uint32_t)src_size;
-      uint32_t h = 4;
+      n = (uint32_t)src_size;
+      h = 4;
       if (h >= n) { status = ST_CORRUPT; break; }
       const uint32_t fhd = src[h++];
-      const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_ck = (fhd >> 2) & 1, did_flag = fhd & 3;
+      const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did_flag = fhd & 3;
+      has_ck = (fhd >> 2) & 1;
       if (fhd & 0x08) { status = ST_UNSUPPORTED; break; }
       const uint32_t did_size = did_flag == 3 ? 4 : did_flag, fcs_size = fcs_flag == 0 ? single : (1u << fcs_flag);
       if (h + (single ? 0 : 1) + did_size + fcs_size > n) { status = ST_CORRUPT; break; }
@@ -116,7 +125,7 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
       uint32_t dict_id = 0;
       for (uint32_t k = 0; k < did_size; k++) dict_id |= (uint32_t)src[h + k] << (8 * k);
       h += did_size;
-      uint64_t fcs = ~0ull;
+      fcs = ~0ull;
       if (fcs_size) {
         fcs = 0;
         for (uint32_t k = 0; k < fcs_size; k++) fcs |= (uint64_t)src[h + k] << (8 * k);
@@ -125,12 +134,13 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
       }
       if (dict_id != 0) { status = ST_DICT_MISMATCH; break; }
       if (fcs != ~0ull && fcs > dst_cap) { status = ST_BUFFER_TOO_SMALL; break; }
+      }
       const uint32_t cap = dst_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)dst_cap;
       // ---- the single block ----
       if (n - h < 3) { status = ST_CORRUPT; break; }
       const uint32_t bh = ld_le24(src + h);
       h += 3;
-      const int last = bh & 1, btype = (bh >> 1) & 3;
+      const int last = F.bare_blocks ? 1 : (int)(bh & 1), btype = (bh >> 1) & 3;
       const uint32_t bsize = bh >> 3;
       if (btype == 3 || bsize > BLOCK_MAX) { status = ST_CORRUPT; break; }
       const uint32_t body = (btype == 1) ? 1u : bsize;
@@ -274,7 +284,7 @@ __device__ __forceinline__ uint32_t peek32(const uint32_t *W, int t) {          
 }
 
 __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
-                                                    uint32_t k, uint32_t *status_out);
+                                                    uint32_t k, uint32_t *status_out, uint32_t lead);
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
@@ -327,15 +337,16 @@ __global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArg
     }
     mbar_wait(&s_bar, phase);
     phase ^= 1;
-    if (work) fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, k, &D->lit_status[k]);
+    if (work) fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, k, &D->lit_status[k], F.bare_blocks ? 6u : 0u);
   }
 }
 
 // =================================================================================================
 // Huffman stream decode (one thread), table in shared memory
 // =================================================================================================
+// `lead` = bytes known to be readable in front of src (0 for a frame, 6 for a block unit inside a frame)
 __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
-                                                    uint32_t k, uint32_t *status_out) {
+                                                    uint32_t k, uint32_t *status_out, uint32_t lead) {
   const uint32_t seg = D->seg, lit_size = D->lit_size;
   const uint32_t count = (D->n_streams == 1) ? lit_size : (k < 3 ? seg : lit_size - 3 * seg);
   uint8_t *dst = lits + (size_t)k * seg_padded(seg);                          // 16-byte aligned segment
@@ -344,7 +355,7 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
   const uint32_t nb = D->st_len[k];
   // position-based reader (see the sequence loop in KB): the words under bit `t` are loaded each round, so there is no
   // refill branch.  W[-1], W[-2] are read under the first stream bits: >= 12 header bytes always precede a Huffman stream.
-  bool ok = nb != 0 && D->st_off[k] >= 12 && p[nb - 1] != 0;
+  bool ok = nb != 0 && D->st_off[k] + lead >= 12 && p[nb - 1] != 0;
   if (ok) {
     const uint32_t *const W = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
     const int d = (int)((uintptr_t)p & 3), low = 8 * d;
@@ -518,8 +529,11 @@ struct SeqLane {                                      // one lane's decoder stat
   }
 };
 
+// `lead`: see fast_decode_huffman.  `unknown_history`: a block unit other than the first of its frame starts with repeat
+// offsets nobody knows yet; sentinels far above any legal offset make every use of them fail KC's range check, which
+// sends the whole frame to the serial decoder
 __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
-                                                      const SeqInfo &I) {
+                                                      const SeqInfo &I, uint32_t lead, bool unknown_history) {
   const uint32_t nseq = D->nseq;
   uint32_t err = ST_OK;
   SeqLane L;
@@ -527,7 +541,7 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
   const uint8_t *const p = src + I.bits_off;
   const uint32_t nb = I.bits_len;
   // W[-1], W[-2] are read under the first stream bits: a fast-path frame has >= 12 header bytes before the bitstream
-  if (nb == 0 || I.bits_off < 12 || p[nb - 1] == 0) err = ST_CORRUPT;
+  if (nb == 0 || I.bits_off + lead < 12 || p[nb - 1] == 0) err = ST_CORRUPT;
   else {
     L.ll16 = T.t16; L.ml16 = T.t16 + 512; L.of16 = T.t16 + 1024;
     L.ll8 = T.t8; L.ml8 = T.t8 + 512; L.of8 = T.t8 + 1024;
@@ -538,6 +552,7 @@ __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDe
     { const uint32_t a = peek32(L.W, L.t); L.sl = top_bits(a, 0, (int)I.ll_log); L.so = top_bits(a, (int)I.ll_log, (int)I.of_log);
       L.sm = top_bits(a, (int)(I.ll_log + I.of_log), (int)I.ml_log); L.t -= (int)(I.ll_log + I.of_log + I.ml_log); }
     L.rep0 = 1; L.rep1 = 4; L.rep2 = 8;
+    if (unknown_history) { L.rep0 = 0xFFFFFF01u; L.rep1 = 0xFFFFFF02u; L.rep2 = 0xFFFFFF03u; }
     for (uint32_t i = 0; i + 1 < nseq; i++) L.step<false>(i);
     L.step<true>(nseq - 1);
     // positions stay bounded even on garbage (they cannot wrap within 65536 sequences), and KC checks every record before using it
@@ -661,7 +676,8 @@ __global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecode
     phase ^= 1;
     if (mine && info.ready) {
       const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
-      fast_decode_sequences((const uint8_t *)A.in_ptrs[g0 + c], slot.desc(), slot.seqs(), T, bases, info);
+      fast_decode_sequences((const uint8_t *)A.in_ptrs[g0 + c], slot.desc(), slot.seqs(), T, bases, info, F.bare_blocks ? 6u : 0u,
+                            F.bare_blocks && (F.unit_base + g0 + c) != 0);
     }
   }
 }
@@ -881,6 +897,73 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
       if (A.statuses) A.statuses[chunk] = status;
     }
   }
+}
+
+// =================================================================================================
+// Multi-block frames: cut ONE frame into block units so that its blocks decode side by side
+// =================================================================================================
+// One thread walks the block headers (a frame of B blocks costs B dependent 3-byte reads).  The cut is speculative: unit k
+// is given the output range [k * 128 KB, +min(128 KB, rest)), i.e. every block but the last is assumed to regenerate a
+// full block -- what one-shot compressors (libzstd's, and this library's block-parallel one) emit.  The units are then
+// decoded as bare blocks; a unit that regenerates anything else, uses repeat offsets it did not establish itself,
+// reaches behind its own output, or needs a previous block's tables fails, and the caller decodes the frame serially.
+__global__ void zstd_split_frame_kernel(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, uint32_t max_units, const void **in_ptrs,
+                                        size_t *in_sizes, void **out_ptrs, size_t *out_sizes, SplitInfo *info) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  SplitInfo R{};
+  do {
+    if (n < 9 || n > 0x7FFFFFFFull || ld_le32(src) != ZSTD_FRAME_MAGIC) break;
+    uint32_t h = 4;
+    const uint32_t fhd = src[h++];
+    const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, did_flag = fhd & 3;
+    if ((fhd & 0x08) || did_flag) break;                                   // reserved bit / dictionaries: serial path reports them
+    const uint32_t fcs_size = fcs_flag == 0 ? single : (1u << fcs_flag);
+    if (fcs_size == 0) break;                                             // no content size: nothing to speculate on
+    if (h + (single ? 0 : 1) + fcs_size + 3 > n) break;
+    if (!single) h++;
+    uint64_t fcs = 0;
+    for (uint32_t k = 0; k < fcs_size; k++) fcs |= (uint64_t)src[h + k] << (8 * k);
+    if (fcs_size == 2) fcs += 256;
+    h += fcs_size;
+    if (fcs <= BLOCK_MAX || fcs > cap) break;                             // one block: the ordinary path is as good
+    const uint64_t want = (fcs + BLOCK_MAX - 1) / BLOCK_MAX;
+    if (want > max_units) break;
+    uint32_t units = 0;
+    bool good = true, last = false;
+    while (!last) {
+      if ((uint64_t)h + 3 > n || units >= want) { good = false; break; }
+      const uint32_t bh = ld_le24(src + h);
+      last = bh & 1;
+      const uint32_t btype = (bh >> 1) & 3, bsize = bh >> 3;
+      const uint32_t body = btype == 1 ? 1u : bsize;
+      if (btype == 3 || bsize > BLOCK_MAX || (uint64_t)h + 3 + body > n) { good = false; break; }
+      in_ptrs[units] = src + h;
+      in_sizes[units] = 3 + (size_t)body;
+      out_ptrs[units] = dst + (size_t)units * BLOCK_MAX;
+      const uint64_t rest = fcs - (uint64_t)units * BLOCK_MAX;
+      out_sizes[units] = rest < BLOCK_MAX ? rest : BLOCK_MAX;
+      units++;
+      h += 3 + body;
+    }
+    const uint32_t has_ck = (fhd >> 2) & 1;
+    if (!good || units != want || (uint64_t)h + (has_ck ? 4 : 0) != n) break;      // trailing frames etc.: serial path
+    R.ok = 1; R.units = units; R.content_size = fcs; R.has_checksum = has_ck; R.checksum_off = h;
+  } while (false);
+  *info = R;
+}
+cudaError_t launch_split_frame(const void *d_src, size_t n, void *d_dst, size_t cap, uint32_t max_units, const void **d_in_ptrs,
+                               size_t *d_in_sizes, void **d_out_ptrs, size_t *d_out_sizes, SplitInfo *d_info, cudaStream_t stream) {
+  zstd_split_frame_kernel<<<1, 32, 0, stream>>>((const uint8_t *)d_src, n, (uint8_t *)d_dst, cap, max_units, d_in_ptrs, d_in_sizes, d_out_ptrs,
+                                                d_out_sizes, d_info);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(32) zstd_verify_checksum_kernel(const uint8_t *data, size_t n, const uint8_t *expect, uint32_t *flag) {
+  const uint64_t hsh = xxh64_warp(data, (uint32_t)n, threadIdx.x);
+  if (threadIdx.x == 0) *flag = ((uint32_t)hsh != ld_le32(expect)) ? 1u : 0u;
+}
+cudaError_t launch_verify_checksum(const void *d_data, size_t n, const void *d_expect, uint32_t *d_flag, cudaStream_t stream) {
+  zstd_verify_checksum_kernel<<<1, 32, 0, stream>>>((const uint8_t *)d_data, n, (const uint8_t *)d_expect, d_flag);
+  return cudaGetLastError();
 }
 
 // KC grid: a bounded number of resident CTAs per SM, each striding over chunks.  Fewer chunks in flight keep the

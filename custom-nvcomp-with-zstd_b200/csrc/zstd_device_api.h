@@ -50,7 +50,23 @@ struct FastDecodeArgs {
   int general_grid;
   int sm_count;
   uint32_t lo, hi, sub;     // set by the launcher: chunk sub-range and work-queue index of a KB / KC launch
+  // bare-block mode (a multi-block frame cut into units by launch_split_frame): every item starts at a block header,
+  // must regenerate exactly its capacity, and -- except global unit 0 -- starts with an unknown repeat-offset history
+  uint32_t bare_blocks, unit_base;
 };
+// Result of cutting one frame into block units (device memory, 64 bytes)
+struct SplitInfo {
+  uint32_t ok;              // 1: the tables hold `units` self-describing block units
+  uint32_t units;
+  uint64_t content_size;
+  uint32_t has_checksum, checksum_off;
+  uint32_t pad[10];
+};
+// one warp walks the block headers of the frame at d_src and fills the four unit tables (max_units entries each)
+cudaError_t launch_split_frame(const void *d_src, size_t n, void *d_dst, size_t cap, uint32_t max_units, const void **d_in_ptrs,
+                               size_t *d_in_sizes, void **d_out_ptrs, size_t *d_out_sizes, SplitInfo *d_info, cudaStream_t stream);
+// compares the low 32 bits of XXH64(d_data[0..n)) with the 4 bytes at d_expect; *d_flag = 1 on mismatch
+cudaError_t launch_verify_checksum(const void *d_data, size_t n, const void *d_expect, uint32_t *d_flag, cudaStream_t stream);
 // optional helper stream + events (owned by the manager) that let KC overlap the next KB sub-wave
 struct FastOverlap {
   static constexpr int MAX_SUB = 8;

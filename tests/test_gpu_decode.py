@@ -195,3 +195,27 @@ def test_small_workspace_routes_to_general_kernel(oracle, libzstd, gpu_codec_fac
     rc = codec.decompress_tables((np.uint64(comp.data_ptr()) + offs).astype(np.uint64), sizes, n,
                                  (np.uint64(out.data_ptr()) + idx * np.uint64(chunk)).astype(np.uint64), osz, ws)
     assert rc == 0 and (osz == chunk).all() and np.array_equal(out.cpu().numpy(), d)
+
+
+def test_multi_block_frames_block_parallel_or_serial(oracle, libzstd, pkg):
+    """SURVEY.md 8f.1, decode half.  A multi-block frame is cut into block units that decode side by side when every block is
+    self-contained; libzstd's own multi-block frames (cross-block matches, repeat offsets carried over, Repeat_Mode tables)
+    fail that speculation and must come out of the serial decoder bit-exact."""
+    s = pkg.ZstdSingle(3)
+    for n, lvl in (((1 << 20) + 999, 3), (3 << 20, 1), (600000, 9)):
+        x = oracle.gen_batch(65536, (n + 65535) // 65536, 0, 30000)[:n].copy()
+        frame = libzstd.compress(x, lvl)
+        d = torch.from_numpy(frame).cuda()
+        w = torch.empty(s.compress_workspace(n), dtype=torch.uint8, device="cuda")      # roomy: the parallel path is attempted
+        back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        rc, dsz = s.decompress(d, frame.size, back, n, w, w.numel())
+        assert rc == 0 and dsz == n and np.array_equal(back.cpu().numpy(), x)
+    # a frame of stored (raw) and RLE blocks only is self-contained by construction: exercises the unit path end to end
+    x = np.concatenate([np.frombuffer(np.random.default_rng(3).bytes(300000), np.uint8), np.full(200000, 9, np.uint8)])
+    frame = libzstd.compress(x, 1)
+    d = torch.from_numpy(frame).cuda()
+    w = torch.empty(s.compress_workspace(x.size), dtype=torch.uint8, device="cuda")
+    back = torch.zeros(x.size, dtype=torch.uint8, device="cuda")
+    rc, dsz = s.decompress(d, frame.size, back, x.size, w, w.numel())
+    assert rc == 0 and dsz == x.size and np.array_equal(back.cpu().numpy(), x)
+    s.close()
