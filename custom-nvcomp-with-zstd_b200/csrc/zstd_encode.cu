@@ -629,19 +629,26 @@ __global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(Enco
             s -= ext; len += ext;
             if (ext < 32) break;
           }
-          // tables: window positions before the match ...
-          if (s > ip) insert_hashed(C, ip, (uint32_t)lane < min(s - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
-          // ... emit ...
+          // emit ...
           const uint32_t llen = s - anchor;
           for (uint32_t k = lane; k < llen; k += 32) lits[nlit + k] = chunk[blk_off + anchor + k];
           const uint32_t code = offset_to_code(off, llen, rep);
           if (lane == 0) { s_ll[nseq] = llen; s_ml[nseq] = len; s_of[nseq] = code; }
           nlit += llen; nseq++;
-          // ... and the positions the match covers
+          // ... and the tables: every position up to the end of the match, in order.  The window's own positions (before
+          // the match and under it) already have their hashes: one update for all of them -- the same table state as
+          // separate updates, since the highest position of a hash wins either way -- and only what lies beyond the
+          // window is loaded and hashed again
           {
-            const uint32_t from = s > ip ? s : ip, end = s + len;
-            if (P.insert_all) { for (uint32_t p = from; p < end; p += 32) insert_stripe(C, p, min(end - p, 32u), lane); }
-            else { insert_stripe(C, from, 1, lane); if (end >= 2) insert_stripe(C, end - 2, 1, lane); }
+            const uint32_t end = s + len;
+            if (P.insert_all) {
+              insert_hashed(C, ip, (uint32_t)lane < min(end - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
+              for (uint32_t p = ip + 32; p < end; p += 32) insert_stripe(C, p, min(end - p, 32u), lane);
+            } else {
+              const uint32_t from = s > ip ? s : ip;
+              if (s > ip) insert_hashed(C, ip, (uint32_t)lane < min(s - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
+              insert_stripe(C, from, 1, lane); if (end >= 2) insert_stripe(C, end - 2, 1, lane);
+            }
           }
           ip = anchor = s + len;
         }
