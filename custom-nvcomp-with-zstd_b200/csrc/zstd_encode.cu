@@ -437,7 +437,7 @@ __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits, uint32
   return op + nbytes;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 32) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
+__global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_chunk;
   const int lane = threadIdx.x;
