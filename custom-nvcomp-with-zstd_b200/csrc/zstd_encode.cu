@@ -151,37 +151,37 @@ __device__ __forceinline__ uint32_t extend_lane(const ParseCtx &C, uint32_t pos,
 
 // table update for one stripe of up to 32 consecutive positions [p0, p0+cnt): sequential semantics.
 // h1 / h2 are the lane's hashes of position p0+lane (only read where `act`).
-__device__ __forceinline__ void insert_hashed(const ParseCtx &C, uint32_t p0, bool act, uint32_t h1_in, uint32_t h2_in, int lane) {
+template <int S> __device__ __forceinline__ void insert_hashed(const ParseCtx &C, uint32_t p0, bool act, uint32_t h1_in, uint32_t h2_in, int lane) {
   const uint32_t pos = p0 + (uint32_t)lane;
   // inactive lanes get unique keys above any real hash so they never group with active lanes
   const uint32_t h1 = act ? h1_in : 0x80000000u + (uint32_t)lane;
   const uint32_t g1 = __match_any_sync(0xffffffffu, h1);
   if (act) {
     const uint32_t lower = g1 & lanemask_lt();
-    if (C.chain) {
-      const uint32_t prev = lower ? (p0 + (uint32_t)(31 - __clz(lower))) : (uint32_t)(C.t1_global ? __ldcg(C.tab1 + h1) : C.tab1[h1]);
+    if (S == 2) {
+      const uint32_t prev = lower ? (p0 + (uint32_t)(31 - __clz(lower))) : (uint32_t)(S != 1 ? __ldcg(C.tab1 + h1) : C.tab1[h1]);
       C.chain[pos] = (uint16_t)((pos - prev) & 0xFFFF);
     }
   }
   __syncwarp();
-  if (act && (g1 >> lane) == 1u) { if (C.t1_global) __stcg(C.tab1 + h1, (uint16_t)pos); else C.tab1[h1] = (uint16_t)pos; }
-  if (C.tab2) {
+  if (act && (g1 >> lane) == 1u) { if (S != 1) __stcg(C.tab1 + h1, (uint16_t)pos); else C.tab1[h1] = (uint16_t)pos; }
+  if (S == 1) {
     const uint32_t h2 = act ? h2_in : 0x80000000u + (uint32_t)lane;
     const uint32_t g2 = __match_any_sync(0xffffffffu, h2);
     if (act && (g2 >> lane) == 1u) __stcg(C.tab2 + h2, (uint16_t)pos);
   }
   __syncwarp();
 }
-__device__ __forceinline__ void insert_stripe(const ParseCtx &C, uint32_t p0, uint32_t cnt, int lane) {
+template <int S> __device__ __forceinline__ void insert_stripe(const ParseCtx &C, uint32_t p0, uint32_t cnt, int lane) {
   const uint32_t pos = p0 + (uint32_t)lane;
   const bool act = (uint32_t)lane < cnt && pos < C.ilimit;
   uint32_t h1 = 0, h2 = 0;
   if (act) {
     const uint64_t v = C.src.ld64(C.blk_off + pos);
     h1 = hash_short(v, C.P.hash_bytes, C.P.hash_log);
-    if (C.tab2) h2 = hash_long(v, C.P.long_log);
+    if (S == 1) h2 = hash_long(v, C.P.long_log);
   }
-  insert_hashed(C, p0, act, h1, h2, lane);
+  insert_hashed<S>(C, p0, act, h1, h2, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -437,6 +437,10 @@ __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits, uint32
   return op + nbytes;
 }
 
+// S: strategy class fixed at compile time -- 0 FAST (one table, L2-resident), 1 DFAST (short table in shared memory + long
+// table), 2 chain levels (L2-resident table + hash chain) -- so that the parse carries neither the branches nor the
+// registers of the other two
+template <int S>
 __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_chunk;
@@ -479,13 +483,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
       C.src.w = (const uint32_t *)((uintptr_t)chunk & ~(uintptr_t)3);
       C.src.delta = (uint32_t)((uintptr_t)chunk & 3);
       C.src.last_word = (uint32_t)((n - 1 + C.src.delta) >> 2);
-      C.t1_global = ((size_t)2 << P.hash_log) > ENC_SMEM_TABLE_MAX;
+      C.t1_global = S != 1;
       // scratch homes: [chain_off, +64 KB) long table (DFAST) or primary table (FAST); chain levels keep the chain there
       // and the primary table right behind it
-      C.tab1 = !C.t1_global ? (uint16_t *)smem
+      C.tab1 = S == 1 ? (uint16_t *)smem
                             : (uint16_t *)(scratch + (P.chain_depth > 0 ? EncScratch::chain_tab_off : EncScratch::chain_off + (P.long_log ? 32 * 1024 : 0)));
-      C.tab2 = P.long_log ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
-      C.chain = P.chain_depth > 0 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
+      C.tab2 = S == 1 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
+      C.chain = S == 2 ? (uint16_t *)(scratch + EncScratch::chain_off) : nullptr;
 
       if (!blocks_only) {
         if (lane == 0) op = write_frame_header(dst, n, P.checksum != 0);
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
         // ---- parse ----
         C.blk_off = blk_off; C.bn = bn; C.ilimit = bn > 8 ? bn - 8 : 0;
         {
-          if (!C.t1_global) {
+          if (S == 1) {
             const uint32_t words = ((uint32_t)2 << P.hash_log) >> 2;
             uint32_t *z = (uint32_t *)smem;
             for (uint32_t k = lane; k < words; k += 32) z[k] = 0;
@@ -525,14 +529,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
             const uint32_t vecs = ((uint32_t)2 << P.hash_log) >> 4;
             for (uint32_t k = lane; k < vecs; k += 32) __stcg(z1 + k, make_uint4(0, 0, 0, 0));
           }
-          if (C.tab2) {
+          if (S == 1) {
             uint4 *z2 = (uint4 *)C.tab2;
             const uint32_t vecs = ((uint32_t)2 << P.long_log) >> 4;
             for (uint32_t k = lane; k < vecs; k += 32) __stcg(z2 + k, make_uint4(0, 0, 0, 0));
           }
           // "ghost" candidates of never-written buckets are positions 0 and 65536: their chain links
           // must read as end-of-chain until those positions are really inserted
-          if (C.chain && lane == 0) { C.chain[0] = 0; if (bn > 65536) C.chain[65536] = 0; }
+          if (S == 2 && lane == 0) { C.chain[0] = 0; if (bn > 65536) C.chain[65536] = 0; }
         }
         __syncwarp();
         const uint32_t rep_save0 = rep[0], rep_save1 = rep[1], rep_save2 = rep[2];
@@ -544,15 +548,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
           if (pos < C.ilimit) {
             const uint64_t v = C.src.ld64(blk_off + pos);
             wh1 = hash_short(v, P.hash_bytes, P.hash_log);
-            if (C.tab2) wh2 = hash_long(v, P.long_log);
-            if (!C.chain) {
+            if (S == 1) wh2 = hash_long(v, P.long_log);
+            if (S != 2) {
               // table candidates and the repeat offset: positions first, then all loads in flight together
               int64_t c2 = -1, c1;
-              if (C.tab2) {
+              if (S == 1) {
                 c2 = (int64_t)((pos & ~0xFFFFu) | __ldcg(C.tab2 + wh2));
                 if (c2 >= (int64_t)pos) c2 -= 0x10000;
               }
-              c1 = (int64_t)((pos & ~0xFFFFu) | (C.t1_global ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
+              c1 = (int64_t)((pos & ~0xFFFFu) | (S != 1 ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
               if (c1 >= (int64_t)pos) c1 -= 0x10000;
               const bool vr = rep[0] != 0 && blk_off + pos >= rep[0];
               const uint64_t x2 = c2 >= 0 ? C.src.ld64(blk_off + (uint32_t)c2) : ~v;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
                 if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
               }
             } else {
-              int64_t c = (int64_t)((pos & ~0xFFFFu) | (C.t1_global ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
+              int64_t c = (int64_t)((pos & ~0xFFFFu) | (S != 1 ? __ldcg(C.tab1 + wh1) : C.tab1[wh1]));
               if (c >= (int64_t)pos) c -= 0x10000;
               int depth = P.chain_depth;
               while (depth-- > 0 && c >= 0) {
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
           if (lane == 0 && ip + 640 < bn) asm volatile("prefetch.global.L2 [%0];" ::"l"(chunk + blk_off + ip + 512));
           const uint32_t mask = __ballot_sync(0xffffffffu, has);
           if (mask == 0) {
-            insert_hashed(C, ip, pos < C.ilimit, wh1, wh2, lane);
+            insert_hashed<S>(C, ip, pos < C.ilimit, wh1, wh2, lane);
             ip += 32;
             continue;
           }
@@ -642,12 +646,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
           {
             const uint32_t end = s + len;
             if (P.insert_all) {
-              insert_hashed(C, ip, (uint32_t)lane < min(end - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
-              for (uint32_t p = ip + 32; p < end; p += 32) insert_stripe(C, p, min(end - p, 32u), lane);
+              insert_hashed<S>(C, ip, (uint32_t)lane < min(end - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
+              for (uint32_t p = ip + 32; p < end; p += 32) insert_stripe<S>(C, p, min(end - p, 32u), lane);
             } else {
               const uint32_t from = s > ip ? s : ip;
-              if (s > ip) insert_hashed(C, ip, (uint32_t)lane < min(s - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
-              insert_stripe(C, from, 1, lane); if (end >= 2) insert_stripe(C, end - 2, 1, lane);
+              if (s > ip) insert_hashed<S>(C, ip, (uint32_t)lane < min(s - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
+              insert_stripe<S>(C, from, 1, lane); if (end >= 2) insert_stripe<S>(C, end - 2, 1, lane);
             }
           }
           ip = anchor = s + len;
@@ -689,23 +693,44 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
   }
 }
 
+// strategy class of a parameter set; the shared-memory / L2 placement of the primary table is tied to it
+static int strategy_class(const EncodeParams &p) { return p.long_log ? 1 : p.chain_depth > 0 ? 2 : 0; }
+static bool class_consistent(const EncodeParams &p) {
+  const bool t1_in_smem = ((size_t)2 << p.hash_log) <= ENC_SMEM_TABLE_MAX;
+  return t1_in_smem == (strategy_class(p) == 1);
+}
+template <int S> static cudaError_t launch_class(const EncodeArgs &args, int grid, size_t smem, cudaStream_t stream) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(zstd_encode_batch_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  zstd_encode_batch_kernel<S><<<grid, ENC_THREADS, smem, stream>>>(args, encode_cta_scratch_bytes(args.prm));
+  return cudaGetLastError();
+}
 cudaError_t launch_encode_batch(const EncodeArgs &args, int grid, cudaStream_t stream) {
   if (args.n == 0) return cudaSuccess;
+  if (!class_consistent(args.prm)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(args.counter, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   const size_t smem = encode_smem_bytes(args.prm);
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(zstd_encode_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+  switch (strategy_class(args.prm)) {
+    case 0: return launch_class<0>(args, grid, smem, stream);
+    case 1: return launch_class<1>(args, grid, smem, stream);
+    default: return launch_class<2>(args, grid, smem, stream);
   }
-  zstd_encode_batch_kernel<<<grid, ENC_THREADS, smem, stream>>>(args, encode_cta_scratch_bytes(args.prm));
-  return cudaGetLastError();
 }
 
 static int g_enc_ctas_cap = 0;                      // 0 = whatever fits; tools/tune_enc.py sweeps it
 int encode_ctas_per_sm(const EncodeParams &prm) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel, ENC_THREADS, encode_smem_bytes(prm)) != cudaSuccess || n < 1) n = 8;
+  const size_t smem = encode_smem_bytes(prm);
+  cudaError_t e;
+  switch (strategy_class(prm)) {
+    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<0>, ENC_THREADS, smem); break;
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<1>, ENC_THREADS, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<2>, ENC_THREADS, smem); break;
+  }
+  if (e != cudaSuccess || n < 1) n = 8;
   if (g_enc_ctas_cap > 0 && n > g_enc_ctas_cap) n = g_enc_ctas_cap;
   return n;
 }
