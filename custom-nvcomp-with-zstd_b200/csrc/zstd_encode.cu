@@ -178,7 +178,7 @@ template <int S> __device__ __forceinline__ void insert_stripe(const ParseCtx &C
   uint32_t h1 = 0, h2 = 0;
   if (act) {
     const uint64_t v = C.src.ld64(C.blk_off + pos);
-    h1 = hash_short(v, C.P.hash_bytes, C.P.hash_log);
+    h1 = hash_short(v, S == 2 ? 4 : 5, C.P.hash_log);
     if (S == 1) h2 = hash_long(v, C.P.long_log);
   }
   insert_hashed<S>(C, p0, act, h1, h2, lane);
@@ -440,8 +440,10 @@ __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits, uint32
 // S: strategy class fixed at compile time -- 0 FAST (one table, L2-resident), 1 DFAST (short table in shared memory + long
 // table), 2 chain levels (L2-resident table + hash chain) -- so that the parse carries neither the branches nor the
 // registers of the other two
-template <int S>
+// LZ: lanes behind the first match that may replace it (lazy depth 0..2).  Hashed bytes and the shortest match follow the class.
+template <int S, int LZ>
 __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(EncodeArgs A, size_t cta_scratch) {
+  constexpr int HASH_BYTES = S == 2 ? 4 : 5, MIN_MATCH = S == 2 ? 4 : 5;
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_chunk;
   const int lane = threadIdx.x;
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
           bool has = false;
           if (pos < C.ilimit) {
             const uint64_t v = C.src.ld64(blk_off + pos);
-            wh1 = hash_short(v, P.hash_bytes, P.hash_log);
+            wh1 = hash_short(v, HASH_BYTES, P.hash_log);
             if (S == 1) wh2 = hash_long(v, P.long_log);
             if (S != 2) {
               // table candidates and the repeat offset: positions first, then all loads in flight together
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
               if (c2 >= 0 && common8(v, x2) == 8) { best = 8; bo = pos - (uint32_t)c2; }
               if (c1 >= 0) {
                 const uint32_t l = common8(v, x1);
-                if (l >= (uint32_t)P.min_match && l > best) { best = l; bo = pos - (uint32_t)c1; }
+                if (l >= (uint32_t)MIN_MATCH && l > best) { best = l; bo = pos - (uint32_t)c1; }
               }
               if (vr) {
                 const uint32_t l = common8(v, xr);
@@ -578,7 +580,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
               while (depth-- > 0 && c >= 0) {
                 uint32_t l = common8(v, C.src.ld64(blk_off + (uint32_t)c));
                 if (l == 8) l = extend_lane(C, pos, pos - (uint32_t)c, P.lane_cap);
-                if (l >= (uint32_t)P.min_match && l > best) { best = l; bo = pos - (uint32_t)c; }
+                if (l >= (uint32_t)MIN_MATCH && l > best) { best = l; bo = pos - (uint32_t)c; }
                 const uint32_t d = C.chain[(uint32_t)c];
                 if (d == 0) break;
                 c -= d;
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
                 if (l >= 4 && l + P.rep_bonus > best) { best = l; bo = rep[0]; }
               }
             }
-            has = best >= (uint32_t)P.min_match || (bo == rep[0] && best >= 4);
+            has = best >= (uint32_t)MIN_MATCH || (bo == rep[0] && best >= 4);
           }
           // the input is read once, front to back: keep the line four windows ahead on its way from HBM
           if (lane == 0 && ip + 640 < bn) asm volatile("prefetch.global.L2 [%0];" ::"l"(chunk + blk_off + ip + 512));
@@ -605,13 +607,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
           const uint32_t bl_f = __shfl_sync(0xffffffffu, best, f);
           uint32_t len;
           uint32_t len_g1 = 0;
-          const bool g1 = P.lazy >= 1 && f + 1 < 32 && ((mask >> (f + 1)) & 1);
+          const bool g1 = LZ >= 1 && f + 1 < 32 && ((mask >> (f + 1)) & 1);
           if (g1) {
             // first match and its lazy rival measured in the same memory round trips: 16 lanes each
             const uint32_t bl_g = __shfl_sync(0xffffffffu, best, f + 1), off_g = __shfl_sync(0xffffffffu, bo, f + 1);
             extend_pair(C, s, off, bl_f < 8 ? bl_f : 8, s + 1, off_g, bl_g < 8 ? bl_g : 8, lane, &len, &len_g1);
           } else len = extend_warp(C, s, off, bl_f < 8 ? bl_f : 8, lane);
-          for (int step = 1; step <= P.lazy; step++) {
+          #pragma unroll
+          for (int step = 1; step <= LZ; step++) {
             const int g = f + step;
             if (g >= 32 || !((mask >> g) & 1)) continue;
             const uint32_t bl_g = __shfl_sync(0xffffffffu, best, g), off2 = __shfl_sync(0xffffffffu, bo, g);
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
           // window is loaded and hashed again
           {
             const uint32_t end = s + len;
-            if (P.insert_all) {
+            if (true) {                                   // every level inserts all covered positions (P.insert_all)
               insert_hashed<S>(C, ip, (uint32_t)lane < min(end - ip, 32u) && pos < C.ilimit, wh1, wh2, lane);
               for (uint32_t p = ip + 32; p < end; p += 32) insert_stripe<S>(C, p, min(end - p, 32u), lane);
             } else {
@@ -697,26 +700,32 @@ __global__ void __launch_bounds__(ENC_THREADS, 24) zstd_encode_batch_kernel(Enco
 static int strategy_class(const EncodeParams &p) { return p.long_log ? 1 : p.chain_depth > 0 ? 2 : 0; }
 static bool class_consistent(const EncodeParams &p) {
   const bool t1_in_smem = ((size_t)2 << p.hash_log) <= ENC_SMEM_TABLE_MAX;
-  return t1_in_smem == (strategy_class(p) == 1);
+  const int s = strategy_class(p);
+  return t1_in_smem == (s == 1) && p.hash_bytes == (s == 2 ? 4 : 5) && p.min_match == (s == 2 ? 4 : 5) && p.insert_all == 1 &&
+         p.lazy == (s == 0 ? 0 : s == 1 ? 1 : p.lazy) && p.lazy >= 0 && p.lazy <= 2;
 }
-template <int S> static cudaError_t launch_class(const EncodeArgs &args, int grid, size_t smem, cudaStream_t stream) {
+template <int S, int LZ> static cudaError_t launch_class(const EncodeArgs &args, int grid, size_t smem, cudaStream_t stream) {
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(zstd_encode_batch_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(zstd_encode_batch_kernel<S, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  zstd_encode_batch_kernel<S><<<grid, ENC_THREADS, smem, stream>>>(args, encode_cta_scratch_bytes(args.prm));
+  zstd_encode_batch_kernel<S, LZ><<<grid, ENC_THREADS, smem, stream>>>(args, encode_cta_scratch_bytes(args.prm));
   return cudaGetLastError();
 }
+// the five instantiations: FAST, DFAST, and the chain levels with lazy depth 0 / 1 / 2
+static int kernel_variant(const EncodeParams &p) { const int s = strategy_class(p); return s < 2 ? s : 2 + p.lazy; }
 cudaError_t launch_encode_batch(const EncodeArgs &args, int grid, cudaStream_t stream) {
   if (args.n == 0) return cudaSuccess;
   if (!class_consistent(args.prm)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(args.counter, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   const size_t smem = encode_smem_bytes(args.prm);
-  switch (strategy_class(args.prm)) {
-    case 0: return launch_class<0>(args, grid, smem, stream);
-    case 1: return launch_class<1>(args, grid, smem, stream);
-    default: return launch_class<2>(args, grid, smem, stream);
+  switch (kernel_variant(args.prm)) {
+    case 0: return launch_class<0, 0>(args, grid, smem, stream);
+    case 1: return launch_class<1, 1>(args, grid, smem, stream);
+    case 2: return launch_class<2, 0>(args, grid, smem, stream);
+    case 3: return launch_class<2, 1>(args, grid, smem, stream);
+    default: return launch_class<2, 2>(args, grid, smem, stream);
   }
 }
 
@@ -725,10 +734,12 @@ int encode_ctas_per_sm(const EncodeParams &prm) {
   int n = 0;
   const size_t smem = encode_smem_bytes(prm);
   cudaError_t e;
-  switch (strategy_class(prm)) {
-    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<0>, ENC_THREADS, smem); break;
-    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<1>, ENC_THREADS, smem); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<2>, ENC_THREADS, smem); break;
+  switch (kernel_variant(prm)) {
+    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<0, 0>, ENC_THREADS, smem); break;
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<1, 1>, ENC_THREADS, smem); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<2, 0>, ENC_THREADS, smem); break;
+    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<2, 1>, ENC_THREADS, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zstd_encode_batch_kernel<2, 2>, ENC_THREADS, smem); break;
   }
   if (e != cudaSuccess || n < 1) n = 8;
   if (g_enc_ctas_cap > 0 && n > g_enc_ctas_cap) n = g_enc_ctas_cap;
