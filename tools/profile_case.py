@@ -17,6 +17,7 @@ ap.add_argument("mode", choices=["decode", "encode"])
 ap.add_argument("--chunks", type=int, default=2368)
 ap.add_argument("--level", type=int, default=3)
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--no-check", action="store_true", help="timing experiments with deliberately wrong kernels")
 a = ap.parse_args()
 pkg = ge.import_package()
 data, blob, offs, sizes = make_workload(0, a.chunks, 8)
@@ -25,8 +26,13 @@ n = a.chunks
 if a.mode == "decode":
     comp = torch.from_numpy(blob).cuda()
     for _ in range(a.iters):
-        out, osz = codec.decompress_chunks(comp, offs, sizes, CHUNK)
-    assert np.array_equal(out.cpu().numpy(), data)
+        try:
+            out, osz = codec.decompress_chunks(comp, offs, sizes, CHUNK)
+        except RuntimeError:
+            if not a.no_check:
+                raise
+            out = None
+    assert a.no_check or np.array_equal(out.cpu().numpy(), data)
 else:
     dev = torch.from_numpy(data).cuda()
     for _ in range(a.iters):
