@@ -219,3 +219,52 @@ def test_multi_block_frames_block_parallel_or_serial(oracle, libzstd, pkg):
     rc, dsz = s.decompress(d, frame.size, back, x.size, w, w.numel())
     assert rc == 0 and dsz == x.size and np.array_equal(back.cpu().numpy(), x)
     s.close()
+
+
+def test_corrupted_multi_block_frames_agree_with_libzstd(oracle, libzstd, pkg):
+    """Random damage to a frame of independently encoded blocks: whichever way it is decoded (block-parallel units, or the
+    serial kernel after a unit failed) the verdict and the bytes must be libzstd's."""
+    rng = np.random.default_rng(11)
+    s = pkg.ZstdSingle(3)
+    n = (1 << 20) + 4321
+    x = oracle.gen_batch(65536, (n + 65535) // 65536, 0, 30000)[:n].copy()
+    xd = torch.from_numpy(x).cuda()
+    cap = n + n // 255 + 3 * ((n + 131071) // 131072) + 512
+    comp = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    w = torch.empty(s.compress_workspace(n), dtype=torch.uint8, device="cuda")
+    rc, csz = s.compress(xd, n, comp, cap, w, w.numel())
+    assert rc == 0
+    good = comp.cpu().numpy()[:csz].copy()
+    agree_fail = agree_ok = 0
+    for trial in range(48):
+        bad = good.copy()
+        if trial % 3 == 0:
+            pos = int(rng.integers(0, 64))                              # frame / first block headers
+        else:
+            pos = int(rng.integers(0, csz))
+        bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        if trial % 8 == 7:
+            bad = bad[: int(rng.integers(csz // 2, csz))]               # truncation
+        try:
+            ref = libzstd.decompress(bad, n)
+        except RuntimeError:
+            ref = None
+        rc_o, out_o = oracle.decompress(bad, n)
+        d = torch.from_numpy(bad).cuda()
+        back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        rc, dsz = s.decompress(d, bad.size, back, n, w, w.numel())
+        # the verdict is the oracle's (RFC 8878: every entropy stream must be consumed exactly).  libzstd 1.5.5 is laxer in one
+        # place -- its fast Huffman loop checks the regenerated length but not that the stream ended on its first bit -- so a
+        # damaged literal stream may pass there; whatever it rejects must be rejected here too
+        assert (rc == 0) == (rc_o == 0), f"trial {trial} (byte {pos}): status {rc}, oracle {rc_o}"
+        if ref is None:
+            assert rc != 0, f"trial {trial}: libzstd rejects the frame (byte {pos}), this decoder returned success"
+        if rc == 0:
+            got = back.cpu().numpy()[:dsz]
+            assert dsz == out_o.size and np.array_equal(got, out_o), f"trial {trial} (byte {pos})"
+            assert ref is not None and np.array_equal(got, ref)
+            agree_ok += 1
+        else:
+            agree_fail += 1
+    assert agree_fail > 0 and agree_ok > 0
+    s.close()
