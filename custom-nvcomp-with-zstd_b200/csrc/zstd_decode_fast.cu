@@ -1,27 +1,27 @@
 // zstd_decode_fast.cu -- batch fast path of the Zstandard decoder for sm_100a.
 //
-// The general decoder (zstd_decode.cu) keeps one chunk per CTA and is bound by the single lane that
-// walks the FSE sequence bitstream (ncu, profiles/r1_decode_general.md).  The serial parts of
-// Zstandard -- one Huffman stream, one interleaved FSE sequence stream -- cannot be split, but a batch
-// has tens of thousands of them.  The fast path therefore runs every serial stream of the WHOLE BATCH
-// as its own thread, and only the embarrassingly parallel parts per warp:
+// The general decoder (zstd_decode.cu) keeps one chunk per CTA and is bound by the single lane that walks the FSE
+// sequence bitstream.  The serial parts of Zstandard -- one Huffman stream, one interleaved FSE sequence stream -- cannot
+// be split, but a batch has tens of thousands of them.  The fast path therefore runs every serial stream of the WHOLE
+// BATCH as its own thread with its table in SHARED memory, and everything else warp- or piece-parallel:
 //
-//   KA literals   persistent CTAs, 48 chunks at a time: one warp per chunk parses the frame / block /
-//                 section headers and builds the Huffman DTable in SHARED memory, then one THREAD per
-//                 Huffman stream (192 per CTA) decodes against those tables
-//   KB sequences  persistent CTAs, 20 chunks at a time: one warp per chunk reads the three FSE table
-//                 descriptions and builds the decode tables in SHARED memory, then one LANE per chunk
-//                 walks its interleaved sequence bitstream and emits 16-byte records
-//   (a first version kept the tables in global memory: every lookup missed L2 -- 7.8 GB of DRAM reads
-//   per GiB decoded, ncu profiles/r1_fast_entropy_global_tables.md -- hence shared memory)
-//   KC execute    one warp per chunk, one LANE per sequence: literal runs and every match whose source
-//               lies before the current group of 32 sequences are copied concurrently; the few
-//               matches that depend on the group itself are replayed in order by the whole warp
+//   KP prepare    warp per chunk: frame / block / section headers, pool allocation, the Huffman decode table and the three
+//                 packed FSE decode tables, built in shared-memory staging and written to the chunk's slot (global, L2)
+//   KA literals   28 chunks per CTA, two CTAs per SM: the Huffman tables arrive by cp.async.bulk (TMA) copies on an
+//                 mbarrier, then one THREAD per Huffman stream decodes against them
+//   KB sequences  56 chunks per CTA (the shared memory of an SM): the FSE tables arrive the same way, then one LANE per
+//                 chunk walks its interleaved sequence bitstream and streams out 16-byte records
+//   (a first version kept the tables in global memory: every lookup missed L2 -- 7.8 GB of DRAM reads per GiB decoded --
+//   hence shared memory; building the tables inside KA / KB left their SMs idle for a third of each pass, hence KP)
+//   KC execute    one warp per chunk, one LANE per sequence: record range checks, then literal runs and every match whose
+//                 source lies before the current group of 32 sequences are copied as destination-aligned 16-byte pieces;
+//                 the matches that depend on the group itself are replayed in order by the whole warp.  Runs on a side
+//                 stream beside KB of the next sub-wave.
 //
-// It handles the batch case: a chunk that is exactly one frame with one block (what libzstd and this
-// library's compressor emit for <= 128 KB chunks).  Anything else (several blocks or frames, skippable
-// frames, more than FAST_SEQ_CAP sequences) is appended to a device-side list and decoded by the
-// general kernel in the same call.  Same reference functions replaced as zstd_decode.cu.
+// It handles the batch case: a chunk that is exactly one frame with one block (what libzstd and this library's compressor
+// emit for <= 128 KB chunks) -- or, in bare-block mode, one block of a multi-block frame that launch_split_frame cut into
+// units.  Anything else (several blocks or frames, skippable frames, more than FAST_SEQ_CAP sequences) is appended to a
+// device-side list and decoded by the general kernel in the same call.  Same reference functions replaced as zstd_decode.cu.
 #include "zstd_common.cuh"
 #include "zstd_decode_tables.cuh"
 #include "zstd_device_api.h"
@@ -450,13 +450,6 @@ __device__ inline void fse_build_warp_packed(const SeqTab &T, uint32_t off, cons
   }
   __syncwarp();
 }
-__device__ __forceinline__ uint32_t ll_base_of(uint32_t c) {
-  return c < 16 ? c : c < 20 ? 16 + 2 * (c - 16) : c < 22 ? 24 + 4 * (c - 20) : c < 24 ? 32 + 8 * (c - 22) : c == 24 ? 48u : 1u << (c - 19);
-}
-__device__ __forceinline__ uint32_t ml_base_of(uint32_t c) {
-  return c < 32 ? c + 3 : c < 36 ? 35 + 2 * (c - 32) : c < 38 ? 43 + 4 * (c - 36) : c < 40 ? 51 + 8 * (c - 38)
-                                                   : c < 42 ? 67 + 16 * (c - 40) : c == 42 ? 99u : (1u << (c - 36)) + 3;
-}
 
 // One lane walks one interleaved sequence stream.  A single in-order warp runs this loop, so its cost
 // is (instructions on the path) x (issue latency): the body is written branch-free where it can be --
@@ -704,26 +697,6 @@ struct LitSrc {
     return base[p + s * pad];
   }
 };
-
-constexpr uint32_t LANE_COPY_MAX = 48;      // longest run a single lane copies by itself
-
-// One lane copies n <= LANE_COPY_MAX bytes, source and destination do not overlap.  Loads are issued
-// eight at a time before the stores so that the copy pays one memory latency per 8 bytes, not per byte.
-__device__ __forceinline__ void lane_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n) {
-  uint32_t k = 0;
-  for (; k + 8 <= n; k += 8) {
-    uint8_t t[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) t[u] = src[k + u];
-#pragma unroll
-    for (int u = 0; u < 8; u++) dst[k + u] = t[u];
-  }
-  uint8_t t[8];
-#pragma unroll
-  for (int u = 0; u < 8; u++) if (k + u < n) t[u] = src[k + u];
-#pragma unroll
-  for (int u = 0; u < 8; u++) if (k + u < n) dst[k + u] = t[u];
-}
 
 // Whole-warp match copy (RFC 8878 3.1.2.5 semantics incl. overlap): 32 consecutive bytes per step,
 // four steps in flight when source and destination are disjoint.
