@@ -362,17 +362,28 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
     int t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);
     uint32_t i = 0;
     uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    // Five words ride in registers: q0..q2 = W[k], W[k-1], W[k-2] feed this round, q3 and q4 were requested one round
+    // earlier.  A round consumes at most 44 bits, so the window moves down by 0, 1 or 2 words: three selects, and no load on
+    // the path from one round's bit position to the next round's table lookups (the lanes of a warp stall together, and
+    // with 32 streams in lockstep some lane would miss the small L1 on almost every round)
+    int k = max(t >> 5, 0);
+    uint32_t q0 = W[k], q1 = W[max(k - 1, -2)], q2 = W[max(k - 2, -2)], q3 = W[max(k - 3, -2)], q4 = W[max(k - 4, -2)];
     for (; i + 4 <= count; i += 4) {                                          // 4 symbols (<= 44 bits) -> one aligned 32-bit store
-      const int kw = max(t >> 5, 0);
       const uint32_t s = (uint32_t)t & 31u;
-      const uint32_t w0 = W[kw], w1 = W[kw - 1], w2 = W[kw - 2];
-      uint64_t win = ((uint64_t)__funnelshift_r(w1, w0, s) << 32) | __funnelshift_r(w2, w1, s);
+      if ((i & 31u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + max(k - 32, 0)));
+      uint64_t win = ((uint64_t)__funnelshift_r(q1, q0, s) << 32) | __funnelshift_r(q2, q1, s);
       const uint32_t e0 = tab[win >> sh]; win <<= (e0 >> 8);
       const uint32_t e1 = tab[win >> sh]; win <<= (e1 >> 8);
       const uint32_t e2 = tab[win >> sh]; win <<= (e2 >> 8);
       const uint32_t e3 = tab[win >> sh];
       t -= (int)((e0 >> 8) + (e1 >> 8) + (e2 >> 8) + (e3 >> 8));
       d32[i >> 2] = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | (e3 << 24);
+      const int kn = max(t >> 5, 0), dk = k - kn;
+      const uint32_t n0 = dk == 0 ? q0 : dk == 1 ? q1 : q2;
+      const uint32_t n1 = dk == 0 ? q1 : dk == 1 ? q2 : q3;
+      const uint32_t n2 = dk == 0 ? q2 : dk == 1 ? q3 : q4;
+      q0 = n0; q1 = n1; q2 = n2; k = kn;
+      q3 = W[max(k - 3, -2)]; q4 = W[max(k - 4, -2)];
     }
     for (; i < count; i++) {
       const uint32_t e = tab[((uint64_t)peek32(W, t) << 32) >> sh];
