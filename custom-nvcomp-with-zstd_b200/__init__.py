@@ -10,6 +10,7 @@ from .binding import (  # noqa: F401
     LIB_PATH,
     Status,
     ZstdBatchCodec,
+    ZstdPipeline,
     ZstdSingle,
     load_library,
     status_to_nvcomp_error,

@@ -51,7 +51,12 @@ EXPORTS = [
     "nvcomp_zstd_create_manager_v5", "nvcomp_zstd_destroy_manager_v5", "nvcomp_zstd_compress_async_v5",
     "nvcomp_zstd_decompress_async_v5", "nvcomp_zstd_get_compress_temp_size_v5", "nvcomp_zstd_get_decompress_temp_size_v5",
     "nvcomp_zstd_get_metadata_v5",
+    "cuda_zstd_pipeline_create", "cuda_zstd_pipeline_destroy", "cuda_zstd_pipeline_compress",
 ]
+
+# callbacks of include/pipeline_manager.hpp
+PIPELINE_INPUT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t))
+PIPELINE_OUTPUT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 def load_library() -> C.CDLL:
@@ -106,6 +111,11 @@ def load_library() -> C.CDLL:
     lib.cuda_zstd_set_dictionary.argtypes = [vp, vp]
     lib.cuda_zstd_train_dictionary.restype = vp
     lib.cuda_zstd_train_dictionary.argtypes = [vp, vp, sz, sz]
+    lib.cuda_zstd_pipeline_create.restype = vp
+    lib.cuda_zstd_pipeline_create.argtypes = [i32, i32, sz, i32]
+    lib.cuda_zstd_pipeline_destroy.argtypes = [vp]
+    lib.cuda_zstd_pipeline_compress.restype = i32
+    lib.cuda_zstd_pipeline_compress.argtypes = [vp, PIPELINE_INPUT_FN, PIPELINE_OUTPUT_FN, vp]
     _LIB = lib
     return lib
 
@@ -280,3 +290,58 @@ class ZstdSingle:
         size = C.c_size_t(cap)
         rc = f(self.h, _addr(src), n, _addr(dst), C.byref(size), _addr(ws), ws_bytes, _stream_handle(stream))
         return int(rc), int(size.value)
+
+
+class ZstdPipeline:
+    """PipelinedBatchManager (reference src/pipeline_manager.hpp:35-66) over the C ABI: host-resident data in,
+    concatenated Zstandard frames out (one frame per batch), H2D / compress / D2H of neighbouring batches overlapped."""
+
+    def __init__(self, level: int = 3, checksum: bool = False, batch_bytes: int = 64 << 20, slots: int = 3):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("ZstdPipeline needs a CUDA device: there is no CPU route")
+        self.batch_bytes = batch_bytes
+        self.h = self.lib.cuda_zstd_pipeline_create(level, int(checksum), batch_bytes, slots)
+        if not self.h:
+            raise RuntimeError("cuda_zstd_pipeline_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cuda_zstd_pipeline_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def compress(self, data: np.ndarray, out: Optional[np.ndarray] = None):
+        """Streams the host array through the pipeline.  Returns (frames, sizes): the concatenated frames (a view of
+        `out` when given, else a new array) and the list of per-batch frame sizes."""
+        src = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        total = src.size
+        if out is None:
+            nb = (total + self.batch_bytes - 1) // self.batch_bytes
+            out = np.empty(total + total // 255 + nb * 1100 + 4096, dtype=np.uint8)
+        state = {"rd": 0, "wr": 0, "sizes": [], "ovf": False}
+        src_addr, out_addr = src.ctypes.data, out.ctypes.data
+
+        def fill(_user, buf, cap, out_len):
+            n = min(cap, total - state["rd"])
+            if n:
+                C.memmove(buf, src_addr + state["rd"], n)
+            state["rd"] += n
+            out_len[0] = n
+            return 1 if state["rd"] < total else 0
+
+        def sink(_user, buf, n):
+            if state["wr"] + n > out.size:
+                state["ovf"] = True
+                return
+            C.memmove(out_addr + state["wr"], buf, n)
+            state["wr"] += n
+            state["sizes"].append(n)
+
+        rc = self.lib.cuda_zstd_pipeline_compress(self.h, PIPELINE_INPUT_FN(fill), PIPELINE_OUTPUT_FN(sink), None)
+        if rc != 0:
+            raise RuntimeError(f"pipeline compress failed: {self.lib.cuda_zstd_batch_error_string(rc).decode()}")
+        if state["ovf"]:
+            raise RuntimeError("pipeline output buffer too small")
+        return out[: state["wr"]], state["sizes"]

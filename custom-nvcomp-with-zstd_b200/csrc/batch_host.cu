@@ -305,9 +305,12 @@ public:
     const size_t B = big_blocks(n);
     return b200zstd::WS_HEADER_BYTES + big_tables(B) + (size_t)enc_grid(B) * b200zstd::encode_cta_scratch_bytes(enc_params()) + B * big_slot();
   }
-  Status compress_big(const void *d_src, size_t n, void *d_dst, size_t *dst_size, void *ws, size_t ws_bytes, cudaStream_t stream) {
+  // Enqueue only: nothing is synchronised.  The outcome {frame bytes, first failing block status} lands in the 16-byte
+  // device mailbox at ws + 64 and, when h_result is given (pinned host memory), is copied there on the same stream.
+  Status compress_big_enqueue(const void *d_src, size_t n, void *d_dst, size_t cap, void *ws, size_t ws_bytes, cudaStream_t stream,
+                              u64 *h_result) {
     const char *fn = "compress";
-    const size_t B = big_blocks(n), cap = *dst_size;
+    const size_t B = big_blocks(n);
     const bool ck = cfg.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
     if (n > 0xFFFF0000ull) return fail(Status::ERROR_UNSUPPORTED_VERSION, fn, "single buffers of 4 GiB and more are not supported");
     if (ws_bytes < big_temp(n)) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
@@ -318,6 +321,7 @@ public:
     std::lock_guard<std::mutex> lock(mu);
     unsigned char *w = static_cast<unsigned char *>(ws);
     u32 *counter = reinterpret_cast<u32 *>(w);
+    u64 *d_result = reinterpret_cast<u64 *>(w + 64);
     unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
     unsigned char *scratch = tab + big_tables(B);
     const int grid = enc_grid(B);
@@ -330,6 +334,7 @@ public:
       host[3 * B + i] = big_slot();
     }
     cudaError_t e;
+    // (pageable -> device async copies are staged by the runtime before they return, so the locals may go out of scope)
     if ((e = cudaMemcpyAsync(tab, host.data(), 4 * B * 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = cudaMemcpyAsync(d_dst, hdr, sizeof hdr, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
     u64 *d_offsets = reinterpret_cast<u64 *>(tab + 4 * B * 8);
@@ -342,19 +347,24 @@ public:
     if ((e = b200zstd::launch_encode_batch(a, grid, stream)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = b200zstd::launch_scan_sizes(a.out_sizes, B, sizeof hdr, reinterpret_cast<uint64_t *>(d_offsets), stream)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = b200zstd::launch_pack(a.out_ptrs, a.out_sizes, reinterpret_cast<const uint64_t *>(d_offsets), B, d_dst, stream)) != cudaSuccess) return cuda_fail(e, fn);
-    last_launches = 3;
+    last_launches = 4;
     if (ck) {
       if ((e = b200zstd::launch_frame_checksum(d_src, n, d_dst, reinterpret_cast<const uint64_t *>(d_offsets + B), stream)) != cudaSuccess) return cuda_fail(e, fn);
-      last_launches = 4;
+      last_launches = 5;
     }
-    std::vector<u32> st(B);
-    u64 total = 0;
-    if ((e = cudaMemcpyAsync(st.data(), d_status, B * 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
-    if ((e = cudaMemcpyAsync(&total, d_offsets + B, 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = b200zstd::launch_big_result(d_status, B, reinterpret_cast<const uint64_t *>(d_offsets + B), ck ? 4 : 0, d_result, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    if (h_result && (e = cudaMemcpyAsync(h_result, d_result, 16, cudaMemcpyDefault, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    return Status::SUCCESS;
+  }
+  Status compress_big(const void *d_src, size_t n, void *d_dst, size_t *dst_size, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    const char *fn = "compress";
+    u64 res[2] = {0, 0};
+    Status s = compress_big_enqueue(d_src, n, d_dst, *dst_size, ws, ws_bytes, stream, res);
+    if (s != Status::SUCCESS) return s;
+    cudaError_t e;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, fn);
-    for (size_t i = 0; i < B; ++i)
-      if (st[i] != 0) return fail(static_cast<Status>(st[i]), fn, "a block failed to encode");
-    *dst_size = (size_t)total + (ck ? 4 : 0);
+    if (res[1] != 0) return fail(static_cast<Status>((u32)res[1]), fn, "a block failed to encode");
+    *dst_size = (size_t)res[0];
     stats.input_bytes += n; stats.output_bytes += *dst_size; stats.bytes_compressed += n; stats.bytes_produced += *dst_size;
     return Status::SUCCESS;
   }
@@ -707,6 +717,35 @@ Status ZstdBatchManager::decompress_async_no_sync(const void *src, size_t n, voi
   a.verify_checksum = I.cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY;
   e = b200zstd::launch_decode_batch(a, 1, stream);
   return e == cudaSuccess ? Status::SUCCESS : cuda_fail(e, "decompress_async_no_sync");
+}
+// Compress counterpart of decompress_async_no_sync (additive; the reference has none): device buffers only, nothing is
+// synchronised; result16 receives {frame bytes, status} as two 64-bit words once `stream` reaches that point (pinned
+// host memory or device memory).  Inputs of at most one block go through the batch encoder as a batch of one.
+Status ZstdBatchManager::compress_async_no_sync(const void *src, size_t n, void *dst, size_t cap, unsigned long long *result16, void *ws,
+                                                size_t ws_bytes, cudaStream_t stream) {
+  const char *fn = "compress_async_no_sync";
+  if (!src || !dst || !result16 || !ws) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null argument");
+  if (n == 0) return fail(Status::ERROR_INVALID_PARAMETER, fn, "zero-size input");
+  Impl &I = *pimpl_;
+  if (n > Impl::BIG_BLOCK) return I.compress_big_enqueue(src, n, dst, cap, ws, ws_bytes, stream, reinterpret_cast<u64 *>(result16));
+  if (ws_bytes < I.enc_temp(1)) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
+  std::lock_guard<std::mutex> lock(I.mu);
+  unsigned char *w = static_cast<unsigned char *>(ws);
+  unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
+  u64 *d_result = reinterpret_cast<u64 *>(w + 64);
+  const u64 words[4] = {(u64)(uintptr_t)src, (u64)n, (u64)(uintptr_t)dst, (u64)cap};
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(tab, words, 32, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return cuda_fail(e, fn);
+  b200zstd::EncodeArgs a{};
+  a.in_ptrs = reinterpret_cast<const void *const *>(tab); a.in_sizes = reinterpret_cast<const size_t *>(tab + 8);
+  a.out_ptrs = reinterpret_cast<void *const *>(tab + 16); a.out_sizes = reinterpret_cast<size_t *>(tab + 24);
+  a.statuses = reinterpret_cast<u32 *>(tab + 32); a.counter = reinterpret_cast<u32 *>(w); a.scratch = tab + Impl::table_bytes(1);
+  a.n = 1; a.prm = I.enc_params();
+  if ((e = b200zstd::launch_encode_batch(a, 1, stream)) != cudaSuccess) return cuda_fail(e, fn);
+  if ((e = b200zstd::launch_big_result(a.statuses, 1, reinterpret_cast<const uint64_t *>(tab + 24), 0, d_result, stream)) != cudaSuccess) return cuda_fail(e, fn);
+  if ((e = cudaMemcpyAsync(result16, d_result, 16, cudaMemcpyDefault, stream)) != cudaSuccess) return cuda_fail(e, fn);
+  I.last_launches = 2;
+  return Status::SUCCESS;
 }
 // both sizes are known here, so the block-parallel path for multi-block frames is provisioned exactly
 size_t ZstdBatchManager::get_inference_workspace_size(size_t mc, size_t mo) const {

@@ -91,6 +91,27 @@ cudaError_t launch_frame_checksum(const void *d_src, size_t n, void *d_dst, cons
   return cudaGetLastError();
 }
 
+// Outcome of one block-parallel frame (compress_big) folded into 16 bytes so that a caller who does not want to
+// synchronise can fetch it with a single small copy: {frame bytes, first non-zero block status, 0}.
+__global__ void __launch_bounds__(256) big_result_kernel(const uint32_t *__restrict__ statuses, size_t n, const uint64_t *__restrict__ total,
+                                                         uint64_t add, uint64_t *__restrict__ result) {
+  __shared__ unsigned int first_bad;
+  if (threadIdx.x == 0) first_bad = 0xFFFFFFFFu;
+  __syncthreads();
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x)
+    if (statuses[i] != 0) atomicMin(&first_bad, (unsigned int)i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    result[0] = *total + add;
+    result[1] = first_bad == 0xFFFFFFFFu ? 0 : (uint64_t)statuses[first_bad];
+  }
+}
+cudaError_t launch_big_result(const uint32_t *d_statuses, size_t n, const uint64_t *d_total, uint64_t add, uint64_t *d_result,
+                              cudaStream_t stream) {
+  big_result_kernel<<<1, 256, 0, stream>>>(d_statuses, n, d_total, add, d_result);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream) {
   scan_sizes_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_sizes, n, base, d_offsets);
   return cudaGetLastError();

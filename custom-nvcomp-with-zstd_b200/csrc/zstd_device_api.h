@@ -95,6 +95,9 @@ int encode_ctas_per_sm(const EncodeParams &prm);
 
 // low 32 bits of XXH64(src[0..n)) written at dst + *d_where (n < 4 GiB)
 cudaError_t launch_frame_checksum(const void *d_src, size_t n, void *d_dst, const uint64_t *d_where, cudaStream_t stream);
+// d_result[0] = *d_total + add, d_result[1] = first non-zero entry of d_statuses[0..n) (0 if none)
+cudaError_t launch_big_result(const uint32_t *d_statuses, size_t n, const uint64_t *d_total, uint64_t add, uint64_t *d_result,
+                              cudaStream_t stream);
 // exclusive scan of sizes (+ base) -> offsets[0..n], offsets[n] = base + total; single CTA.
 cudaError_t launch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream);
 // gather frames into a packed buffer

@@ -90,6 +90,12 @@ public:
   Status decompress_async_no_sync(const void *compressed_data, size_t compressed_size, void *preallocated_output,
                                   size_t output_capacity, size_t *d_actual_size, void *temp_workspace, size_t temp_size,
                                   cudaStream_t stream);
+  // Additive (no reference counterpart): compress without any host synchronisation.  Device buffers only; result16 gets
+  // {bytes written, Status} as two 64-bit words in stream order (pinned host or device memory).  Used by
+  // PipelinedBatchManager to keep H2D, compress and D2H of neighbouring batches in flight together.
+  Status compress_async_no_sync(const void *uncompressed_data, size_t uncompressed_size, void *compressed_data,
+                                size_t compressed_capacity, unsigned long long *result16, void *temp_workspace, size_t temp_size,
+                                cudaStream_t stream);
   size_t get_inference_workspace_size(size_t max_compressed_size, size_t max_output_size) const;
   Status allocate_inference_workspace(size_t max_compressed_size, size_t max_output_size, void **workspace_ptr,
                                       size_t *workspace_size);

@@ -15,7 +15,7 @@ mkdir -p "$OUT"
 TESTS="test_c_api.cpp test_c_api_edge_cases.cu test_compressible_data.cu test_concurrency_repro.cu test_correctness.cu
 test_extended_validation.cu test_gpu_bitstream.cu test_inference_api.cu test_lz77_comprehensive.cu test_metadata_roundtrip.cu
 test_nvcomp_batch.cu test_nvcomp_interface.cu test_parallel_compression.cu test_rfc8878_compliance.cu test_roundtrip.cu
-test_scale_repro.cu test_two_phase_unit.cu"
+test_scale_repro.cu test_two_phase_unit.cu test_pipeline_integration.cu"
 # ... and the reference's benchmark programs of the same path (run by hand: tools/run_ref_benchmarks.sh)
 BENCHES="benchmark_batch_throughput.cu benchmark_nvcomp_interface.cu benchmark_c_api.cu benchmark_block_size.cu"
 ok=0; bad=0

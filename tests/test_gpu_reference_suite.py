@@ -14,7 +14,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "tests")
 PROGRAMS = ["test_c_api", "test_c_api_edge_cases", "test_compressible_data", "test_concurrency_repro", "test_correctness",
             "test_extended_validation", "test_gpu_bitstream", "test_inference_api", "test_lz77_comprehensive",
             "test_metadata_roundtrip", "test_nvcomp_batch", "test_nvcomp_interface", "test_parallel_compression",
-            "test_rfc8878_compliance", "test_roundtrip", "test_scale_repro", "test_two_phase_unit"]
+            "test_rfc8878_compliance", "test_roundtrip", "test_scale_repro", "test_two_phase_unit", "test_pipeline_integration"]
 OUT_OF_SCOPE_SUBTESTS = {"test_c_api_edge_cases": ["C API Dictionary Round-trip"]}
 
 
@@ -26,6 +26,9 @@ def test_reference_program(name):
         pytest.skip("reference test programs not built (oracle/build_ref_tests.sh needs the reference tree)")
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "custom-nvcomp-with-zstd_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    # tests/test_pipeline_integration.cu:34-37 verifies its output with `zstd -q -t`; the image has libzstd but not the
+    # command line tool, so tests/bin/zstd (stock libzstd behind the same command line) stands in for it
+    env["PATH"] = os.path.join(ROOT, "tests", "bin") + ":" + env.get("PATH", "")
     r = subprocess.run([exe], cwd=BIN, env=env, capture_output=True, text=True, errors="replace", timeout=600)
     tail = (r.stdout[-3000:] + "\n--- stderr ---\n" + r.stderr[-2000:])
     if name in OUT_OF_SCOPE_SUBTESTS and r.returncode != 0:
@@ -34,4 +37,5 @@ def test_reference_program(name):
         failed = [ln.strip() for ln in r.stdout.splitlines() if ln.strip().endswith(": FAIL")]
         assert failed == [s + ": FAIL" for s in OUT_OF_SCOPE_SUBTESTS[name]], f"{name}: unexpected failures {failed}\n{tail}"
         return
+    assert r.returncode != 77, f"{name} skipped itself\n{tail}"
     assert r.returncode == 0, f"{name} exited {r.returncode}\n{tail}"
