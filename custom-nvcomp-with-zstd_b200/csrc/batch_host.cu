@@ -264,13 +264,10 @@ public:
     return b200zstd::WS_HEADER_BYTES + table_bytes(n) + slow_list_bytes(n) + general_scratch_bytes(n) +
            wave_of(n) * b200zstd::FAST_SLOT_BYTES;
   }
-  // pools for one wave, sized from the compressed bytes of the largest wave: literals regenerate to at
-  // most ~2x their coded size on compressible data, and a sequence costs >= ~2.7 coded bytes (16-byte
-  // records).  Too small a pool is not an error: the overflow chunks take the general kernel.
-  static void pool_split(size_t pool_bytes, size_t *lit, size_t *seq) {
-    *lit = (pool_bytes / 4) & ~(size_t)255;
-    *seq = (pool_bytes - *lit) & ~(size_t)255;
-  }
+  // pool for one wave (literals and 16-byte sequence records share it), sized from the compressed bytes of the
+  // largest wave: Huffman literals regenerate to at most ~2x their coded size on compressible data and a sequence
+  // costs >= ~2.2 coded bytes (match-heavy P=0.90 frames: 4,400 sequences in 9.5 KB), so 8 x compressed covers both
+  // extremes.  Too small a pool is not an error: the overflow chunks take the general kernel.
   static size_t pool_share(size_t compressed) { return std::min<size_t>(8 * compressed, 192 * 1024) + 3072; }
   size_t dec_temp(size_t n, const size_t *sizes = nullptr) const {
     if (n == 0) return 0;
@@ -465,8 +462,7 @@ public:
       unsigned char *gen_scratch = slow_list + slow_list_bytes(n);
       unsigned char *slots = gen_scratch + general_scratch_bytes(n);
       unsigned char *pools = slots + wave_of(n) * b200zstd::FAST_SLOT_BYTES;
-      size_t lit_pool = 0, seq_pool = 0;
-      pool_split(ws_bytes - (size_t)(pools - w), &lit_pool, &seq_pool);
+      const size_t pool_bytes = (ws_bytes - (size_t)(pools - w)) & ~(size_t)255;
       e = cudaSuccess;
       for (size_t w0 = 0; w0 < n && e == cudaSuccess; w0 += b200zstd::FAST_WAVE) {
         const size_t m = std::min<size_t>(b200zstd::FAST_WAVE, n - w0);
@@ -475,8 +471,7 @@ public:
         f.base.statuses = d_status + w0; f.base.counter = counter; f.base.lit_scratch = gen_scratch; f.base.n = (uint32_t)m;
         f.base.verify_checksum = cfg.checksum == ChecksumPolicy::COMPUTE_AND_VERIFY;   // reference gates on the manager's policy (manager.cu:3654)
         f.slots = slots;
-        f.lit_pool = pools; f.lit_pool_bytes = lit_pool;
-        f.seq_pool = pools + lit_pool; f.seq_pool_bytes = seq_pool;
+        f.lit_pool = f.seq_pool = pools; f.lit_pool_bytes = f.seq_pool_bytes = pool_bytes;
         f.pool_heads = reinterpret_cast<unsigned long long *>(w + 128);
         f.slow_list = reinterpret_cast<u32 *>(slow_list);
         f.slow_count = counter + 16;

@@ -29,7 +29,9 @@ PipelinedBatchManager::PipelinedBatchManager(const CompressionConfig &config, si
     : manager_(create_manager(config)), config_(config), batch_size_(std::max<size_t>(batch_size_bytes, 1)),
       num_slots_(std::max(num_slots, 2)) {
   ring_buffer_.resize((size_t)num_slots_);
-  streams_.assign(3, nullptr);
+  // [0] upload, [1] compress, [2] download as in the reference, then one more compress stream per further slot: a batch
+  // of B blocks occupies only B of the encoder's ~3,500 resident warps, so batches in different slots run side by side
+  streams_.assign(3 + (size_t)(num_slots_ - 1), nullptr);
   if (init_resources() != Status::SUCCESS) cleanup_resources();     // compress_stream_pipeline then reports ERROR_NOT_INITIALIZED
 }
 
@@ -72,10 +74,11 @@ void PipelinedBatchManager::cleanup_resources() {
 Status PipelinedBatchManager::compress_stream_pipeline(std::function<bool(void *, size_t, size_t *)> input_callback,
                                                        std::function<void(const void *, size_t)> output_callback) {
   if (!input_callback || !output_callback) return Status::ERROR_INVALID_PARAMETER;
-  if (!manager_ || streams_.size() != 3 || !streams_[0] || ring_buffer_.empty() || !ring_buffer_[0].h_input) return Status::ERROR_NOT_INITIALIZED;
+  if (!manager_ || streams_.size() < 3 || !streams_[0] || ring_buffer_.empty() || !ring_buffer_[0].h_input) return Status::ERROR_NOT_INITIALIZED;
   ZstdBatchManager *codec = batch_of(manager_.get());
-  cudaStream_t up = streams_[0], run = streams_[1], down = streams_[2];
+  cudaStream_t up = streams_[0], down = streams_[2];
   const size_t S = ring_buffer_.size();
+  auto run_of = [&](size_t slot) { return slot == 0 || 2 + slot >= streams_.size() ? streams_[1] : streams_[2 + slot]; };
   // slot states by batch number: batches [drained, fetched) have their D2H in flight, [fetched, issued) are compressing
   size_t issued = 0, fetched = 0, drained = 0;
   Status result = Status::SUCCESS;
@@ -111,6 +114,7 @@ Status PipelinedBatchManager::compress_stream_pipeline(std::function<bool(void *
     }
     if (result != Status::SUCCESS) break;
     RingBufferSlot &s = ring_buffer_[issued % S];
+    cudaStream_t run = run_of(issued % S);
     size_t len = 0;
     more = input_callback(s.h_input, s.input_capacity, &len);
     if (len > s.input_capacity) { result = Status::ERROR_INVALID_PARAMETER; break; }
@@ -124,9 +128,11 @@ Status PipelinedBatchManager::compress_stream_pipeline(std::function<bool(void *
     if (result != Status::SUCCESS) break;
     if (cudaEventRecord(s.event_compressed, run) != cudaSuccess) { result = Status::ERROR_CUDA_ERROR; break; }
     ++issued;
-    // with this batch on its way, settle the one before it: its size is (almost certainly) known by now,
-    // so its download overlaps this batch's compress and the next batch's fill + upload
-    while (result == Status::SUCCESS && fetched + 1 < issued) result = fetch_one();
+    // with this batch on its way, settle older ones: whatever has finished compressing starts its download now, and the
+    // host blocks only to keep at most S - 1 batches compressing (one slot is always being filled)
+    while (result == Status::SUCCESS && fetched < issued &&
+           (fetched + (S - 1) < issued || cudaEventQuery(ring_buffer_[fetched % S].event_compressed) == cudaSuccess))
+      result = fetch_one();
     // frames whose download has finished go out as soon as they are there (keeps the caller's sink busy)
     while (result == Status::SUCCESS && drained < fetched && cudaEventQuery(ring_buffer_[drained % S].event_downloaded) == cudaSuccess)
       result = drain_one();

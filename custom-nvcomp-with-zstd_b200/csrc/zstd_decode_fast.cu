@@ -84,6 +84,53 @@ struct __align__(16) HufScratch {                              // per-warp scrat
   int huf_log, huf_valid;
 };
 
+// Raw and RLE blocks are finished by the prepare kernel's warp.  The payload of a raw block sits at an arbitrary byte
+// offset of its frame (10 for a single-block frame), the destination is usually 16-byte aligned: aligned 32-bit loads
+// realigned with funnel shifts feed 16-byte stores, two vectors per lane in flight.  `src_room` = readable bytes from src
+// on (the rest of the frame); the words in front of src hold the block header, so reading them is safe.
+template <int U>       // U > 1: that many 16-byte vectors per lane in flight
+__device__ __forceinline__ void warp_copy_block(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t src_room, int lane) {
+  uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+  if (head > n) head = n;
+  for (uint32_t k = lane; k < head; k += 32) dst[k] = src[k];
+  // vector j covers src bytes [head + 16 j, head + 16 j + 16) and needs the aligned words up to 3 bytes past them
+  uint32_t vecs = (n - head) >> 4;
+  while (vecs && head + 16 * vecs + 3 > src_room) vecs--;
+  const uint8_t *s0 = src + head;
+  const uint32_t sh = (uint32_t)((uintptr_t)s0 & 3) * 8;
+  const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t)s0 & ~(uintptr_t)3);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  uint32_t j = (uint32_t)lane;
+  for (; U > 1 && j + 32 * (U - 1) < vecs; j += 32 * U) {
+    uint32_t a[U][5];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int q = 0; q < 5; q++) a[u][q] = __ldg(w + 4 * (j + 32 * u) + q);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      d4[j + 32 * u] = make_uint4(__funnelshift_r(a[u][0], a[u][1], sh), __funnelshift_r(a[u][1], a[u][2], sh),
+                                  __funnelshift_r(a[u][2], a[u][3], sh), __funnelshift_r(a[u][3], a[u][4], sh));
+  }
+  for (; j < vecs; j += 32) {
+    uint32_t a[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) a[q] = __ldg(w + 4 * j + q);
+    d4[j] = make_uint4(__funnelshift_r(a[0], a[1], sh), __funnelshift_r(a[1], a[2], sh), __funnelshift_r(a[2], a[3], sh),
+                       __funnelshift_r(a[3], a[4], sh));
+  }
+  for (uint32_t k = head + 16 * vecs + lane; k < n; k += 32) dst[k] = src[k];
+}
+__device__ __forceinline__ void warp_fill_block(uint8_t *dst, uint8_t v, uint32_t n, int lane) {
+  uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+  if (head > n) head = n;
+  for (uint32_t k = lane; k < head; k += 32) dst[k] = v;
+  const uint32_t vecs = (n - head) >> 4, x = 0x01010101u * v;
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  for (uint32_t j = lane; j < vecs; j += 32) d4[j] = make_uint4(x, x, x, x);
+  for (uint32_t k = head + 16 * vecs + lane; k < n; k += 32) dst[k] = v;
+}
+
 __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chunk, uint8_t *stage, HufScratch &S, int lane) {
     const DecodeArgs &A = F.base;
     if (lane == 0) S.huf = reinterpret_cast<uint16_t *>(stage);
@@ -153,8 +200,8 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
       if (btype == 0 || btype == 1) {
         if (bsize > cap) { status = ST_BUFFER_TOO_SMALL; break; }
         if (fcs != ~0ull && fcs != bsize) { status = ST_CORRUPT; break; }
-        if (btype == 0) for (uint32_t k = lane; k < bsize; k += 32) dst[k] = src[h + k];
-        else { const uint8_t v = src[h]; for (uint32_t k = lane; k < bsize; k += 32) dst[k] = v; }
+        if (btype == 0) warp_copy_block<2>(dst, src + h, bsize, n - h, lane);
+        else warp_fill_block(dst, src[h], bsize, lane);
         __syncwarp();
         if (has_ck && A.verify_checksum) {
           const uint64_t hs = xxh64_warp(dst, bsize, lane);
@@ -241,9 +288,10 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
       // bump-allocate this chunk's literal and sequence storage; pool exhaustion -> general kernel
       const unsigned long long lit_need = D.lit_type == 2 ? (unsigned long long)4 * seg_padded(D.seg ? D.seg : 1) : 0ull;
       const unsigned long long seq_need = (unsigned long long)(D.nseq + 1) * 16;
-      const unsigned long long lo = atomicAdd(&F.pool_heads[0], lit_need), so = atomicAdd(&F.pool_heads[1], seq_need);
-      if (lo + lit_need > F.lit_pool_bytes || so + seq_need > F.seq_pool_bytes) route = true;
-      D.lit_slot = (uint32_t)(lo >> 4); D.seq_slot = (uint32_t)(so >> 4);
+      // (one pool, one head: a literal-only block may take all of its share for literals, a match-heavy one for records)
+      const unsigned long long lo = atomicAdd(&F.pool_heads[0], lit_need + seq_need);
+      if (lo + lit_need + seq_need > F.lit_pool_bytes) route = true;
+      D.lit_slot = (uint32_t)(lo >> 4); D.seq_slot = (uint32_t)((lo + lit_need) >> 4);
     }
     route = __shfl_sync(0xffffffffu, route ? 1 : 0, 0) != 0;
     if (lane == 0) {
@@ -733,7 +781,8 @@ __device__ __forceinline__ void warp_copy_match(uint8_t *out, uint32_t d, uint32
   }
 }
 
-__global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDecodeArgs F) {
+// (9 CTAs per SM by registers = 56 per thread: eight resident KC CTAs then leave room for KB's CTA beside them)
+__global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(FastDecodeArgs F) {
   const DecodeArgs &A = F.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * EXEC_WARPS;
@@ -866,7 +915,20 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) zstd_fast_exec_kernel(FastDec
       else if (lit_end > lit_size) status = ST_CORRUPT;
       else if (rest > cap - out_end) status = ST_BUFFER_TOO_SMALL;
       else {
-        for (uint32_t k = lane; k < rest; k += 32) out[out_end + k] = L.at(lit_end + k);
+        // (a literal-only block has all of its bytes here: vector copies, per Huffman segment where the literals are split)
+        if (rest < 64) { for (uint32_t k = lane; k < rest; k += 32) out[out_end + k] = L.at(lit_end + k); }
+        else if (L.mode == 1) warp_fill_block(out + out_end, L.base[0], rest, lane);
+        else if (L.mode == 0)
+          warp_copy_block<1>(out + out_end, L.base + lit_end, rest, D->lit_type == 2 ? rest + 3 : (uint32_t)A.in_sizes[chunk] - D->lit_src - lit_end, lane);
+        else {
+          uint32_t p = lit_end, o = out_end;
+          while (p < lit_size) {
+            const uint32_t sg = (p >= L.seg) + (p >= 2 * L.seg) + (p >= 3 * L.seg);
+            const uint32_t len = (sg == 3 ? lit_size : (sg + 1) * L.seg) - p;
+            warp_copy_block<1>(out + o, L.base + p + sg * L.pad, len, len + 3, lane);      // segments are padded to 16 bytes in the pool
+            p += len; o += len;
+          }
+        }
         total = out_end + rest;
         if (D->content != 0xFFFFFFFFu && D->content != total) status = ST_CORRUPT;
       }

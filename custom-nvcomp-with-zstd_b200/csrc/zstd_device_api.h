@@ -35,15 +35,15 @@ constexpr uint32_t FAST_SEQ_CAP = 65536;                      // sequences per c
 constexpr size_t FAST_TABLE_BYTES = 64 + 4096 + 3840;         // sequence-stream info, Huffman table, packed LL/ML/OF tables (KP -> KA, KB)
 constexpr size_t FAST_DESC_BYTES = 192;
 constexpr size_t FAST_SLOT_BYTES = FAST_DESC_BYTES + FAST_TABLE_BYTES;     // fixed per-chunk slot
-// Literals and sequence records come from two bump-allocated pools sized from the COMPRESSED sizes the
-// caller passes to the temp-size query; a chunk that does not fit takes the general kernel instead.
+// Literals and sequence records come from ONE bump-allocated pool sized from the COMPRESSED sizes the caller passes
+// to the temp-size query (lit_pool == seq_pool, one head); a chunk that does not fit takes the general kernel instead.
 struct FastDecodeArgs {
   DecodeArgs base;          // tables, sizes, statuses; base.counter / lit_scratch serve the general kernel
   uint8_t *slots;           // n * FAST_SLOT_BYTES
   uint8_t *lit_pool;        // 16-byte aligned
   uint8_t *seq_pool;
-  uint64_t lit_pool_bytes, seq_pool_bytes;
-  unsigned long long *pool_heads;   // [0] literals, [1] sequences; zeroed by the launcher
+  uint64_t lit_pool_bytes, seq_pool_bytes;   // both = the pool's size
+  unsigned long long *pool_heads;   // [0] the pool's head; zeroed by the launcher
   uint32_t *slow_list;      // n entries
   uint32_t *slow_count;     // 1 entry, zeroed by the launcher
   uint32_t *group_counters; // [0] literal kernel, [1] sequence kernel work queues; zeroed by the launcher

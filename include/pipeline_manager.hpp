@@ -9,8 +9,10 @@
 // What differs is behind it.  The reference calls the blocking single-buffer compress() per batch
 // from the host loop (src/pipeline_manager.cu), so its three streams never hold more than one
 // stage.  This build enqueues H2D -> compress_async_no_sync -> D2H of the 16-byte result on three
-// streams chained by events, fills the next pinned slot while the GPU works, and only then waits
-// for the previous batch's size to issue a D2H of exactly the bytes produced.  Every batch becomes
+// streams chained by events (every slot compresses on its own stream, so small batches, which fill
+// only a fraction of the GPU, overlap each other as well), fills the next pinned slot while the
+// GPU works, and waits for a batch's size only when it is there or when the ring would stall,
+// to issue a D2H of exactly the bytes produced.  Every batch becomes
 // one Zstandard frame (blocks of 128 KB encoded side by side), so the output is a concatenation of
 // frames that `zstd -d` / ZSTD_decompress-in-a-loop reads back.
 #ifndef CUDA_ZSTD_PIPELINE_MANAGER_HPP
@@ -62,7 +64,7 @@ private:
   size_t batch_size_;
   int num_slots_;
   std::vector<RingBufferSlot> ring_buffer_;
-  std::vector<cudaStream_t> streams_;       // [0] upload, [1] compress, [2] download
+  std::vector<cudaStream_t> streams_;       // [0] upload, [1] compress (slot 0), [2] download, [3..] compress of slots 1..
 
   Status init_resources();
   void cleanup_resources();

@@ -71,6 +71,44 @@ def test_ragged_sizes_and_unaligned_frames(oracle, libzstd, gpu_codec_factory):
         assert int(osz[i]) == x.size and np.array_equal(out[i * cap: i * cap + x.size], x), i
 
 
+def test_raw_and_rle_blocks_at_every_alignment(oracle, libzstd, pkg, gpu_codec_factory):
+    """Raw and RLE blocks are copied / filled with realigned 16-byte vectors: every source offset mod 16, every
+    destination offset mod 16, sizes around the vector boundaries, the last frame flush with the end of the allocation."""
+    codec = gpu_codec_factory()
+    sizes_in = [1, 3, 15, 16, 17, 31, 32, 33, 47, 100, 4096, 4099, 65535, 65536, 131072]
+    frames, datas = [], []
+    for i, n in enumerate(sizes_in):
+        rnd = oracle.gen_batch(n, 1, 1, 0, first_idx=100 + i)                  # uniform random -> one raw block
+        rle = np.full(n, 7 + i, np.uint8)                                      # one byte repeated -> RLE block (or RLE literals)
+        for x in (rnd, rle):
+            datas.append(x); frames.append(libzstd.compress(x, 3, checksum=(i % 2 == 0)))
+    blob, offs = [], []
+    pos = 0
+    for k, f in enumerate(frames):
+        pad = (k * 5 + 1) % 17                                                # walks through all source alignments
+        blob.append(np.zeros(pad, np.uint8)); pos += pad
+        offs.append(pos); blob.append(f); pos += f.size
+    blob = np.concatenate(blob)                                               # ends with the last frame's last byte
+    n = len(frames)
+    comp = to_dev(blob)
+    stride = 131072 + 48
+    out = torch.zeros(n * stride + 16, dtype=torch.uint8, device="cuda")
+    idx = np.arange(n, dtype=np.uint64)
+    dst_off = idx * np.uint64(stride) + (idx * np.uint64(3)) % np.uint64(16)    # every destination alignment
+    in_ptrs = (np.uint64(comp.data_ptr()) + np.asarray(offs, np.uint64)).astype(np.uint64)
+    out_ptrs = (np.uint64(out.data_ptr()) + dst_off).astype(np.uint64)
+    szs = np.asarray([f.size for f in frames], np.uint64)
+    out_sizes = np.asarray([x.size for x in datas], np.uint64)                 # exact capacities: nothing may be written past them
+    ws = torch.empty(codec.decompress_temp_size(n, szs), dtype=torch.uint8, device="cuda")
+    rc = codec.decompress_tables(in_ptrs, szs, n, out_ptrs, out_sizes, ws)
+    assert rc == 0
+    host = out.cpu().numpy()
+    for i, x in enumerate(datas):
+        o = int(dst_off[i])
+        assert int(out_sizes[i]) == x.size and np.array_equal(host[o:o + x.size], x), i
+        assert not host[o + x.size:o + x.size + 16].any(), f"frame {i} wrote past its output"
+
+
 def test_multiblock_repeat_treeless_and_checksum(oracle, libzstd, pkg):
     codec = pkg.ZstdBatchCodec(level=3, checksum=True)          # COMPUTE_AND_VERIFY: checksums are verified
     big = [oracle.gen_batch(700000, 1, 0, 30000), oracle.gen_textlike(1 << 20), np.zeros(500000, np.uint8),
