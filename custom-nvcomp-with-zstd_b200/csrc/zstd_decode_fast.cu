@@ -22,6 +22,8 @@
 // emit for <= 128 KB chunks) -- or, in bare-block mode, one block of a multi-block frame that launch_split_frame cut into
 // units.  Anything else (several blocks or frames, skippable frames, more than FAST_SEQ_CAP sequences) is appended to a
 // device-side list and decoded by the general kernel in the same call.  Same reference functions replaced as zstd_decode.cu.
+#include <cstdio>
+#include <cstdlib>
 #include "zstd_common.cuh"
 #include "zstd_decode_tables.cuh"
 #include "zstd_device_api.h"
@@ -1034,13 +1036,21 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   }
   FastDecodeArgs F = F0;
   F.lo = 0; F.hi = n; F.sub = 0;
+  // CUDA_ZSTD_TRACE=1: events after every launch, printed as "kernel@ms since the call began" once the call has drained
+  // (a debugging aid: it synchronises the stream; this is how the KB / KC overlap in DESIGN.md 4.1 was timed)
+  static const bool trace = getenv("CUDA_ZSTD_TRACE") != nullptr;
+  cudaEvent_t te[24]; const char *tn[24]; int tc = 0;
+  auto mark = [&](const char *name, cudaStream_t st) { if (trace && tc < 24 && cudaEventCreate(&te[tc]) == cudaSuccess) { cudaEventRecord(te[tc], st); tn[tc++] = name; } };
+  mark("start", stream);
   // one memset zeroes every counter of the pipeline: general work queue, slow count, pool heads, group counters
   if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
   const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
   const uint32_t kp_blocks = (n + KP_WARPS - 1) / KP_WARPS;
   zstd_fast_prep_kernel<<<kp_blocks < 5 * sms ? kp_blocks : 5 * sms, KP_WARPS * 32, 0, stream>>>(F);
+  mark("KP", stream);
   const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
   zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
+  mark("KA", stream);
   int count = 2;
   // KB (SMEM-bound: one CTA and two busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
   // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1
@@ -1057,9 +1067,11 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
       F.lo = k * sub_chunks; F.hi = F.lo + sub_chunks < n ? F.lo + sub_chunks : n; F.sub = k;
       const uint32_t m = F.hi - F.lo, kb_groups = (m + KB_GROUP - 1) / KB_GROUP;
       zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
+      mark("KB", stream);
       if ((e = cudaEventRecord(ov->ev[k], stream)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(ov->side, ov->ev[k], 0)) != cudaSuccess) return e;
       zstd_fast_exec_kernel<<<exec_grid(m, sms), EXEC_WARPS * 32, 0, ov->side>>>(F);
+      mark("KC", ov->side);
       count += 2;
     }
     if ((e = cudaEventRecord(ov->done, ov->side)) != cudaSuccess) return e;
@@ -1071,6 +1083,13 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   G.list = F.slow_list;
   G.list_count = F.slow_count;
   e = launch_decode_batch_nomemset(G, F.general_grid, stream);
+  if (trace) {
+    mark("end", stream);
+    cudaStreamSynchronize(stream);
+    for (int i = 1; i < tc; i++) { float ms = 0; cudaEventElapsedTime(&ms, te[0], te[i]); fprintf(stderr, "%s@%.3f ", tn[i], ms); }
+    fprintf(stderr, "\n");
+    for (int i = 0; i < tc; i++) cudaEventDestroy(te[i]);
+  }
   if (launches) *launches = count + 1;
   return e;
 }
