@@ -10,6 +10,7 @@ from .binding import (  # noqa: F401
     LIB_PATH,
     Status,
     ZstdBatchCodec,
+    ZstdHybrid,
     ZstdPipeline,
     ZstdSingle,
     load_library,

@@ -52,7 +52,22 @@ EXPORTS = [
     "nvcomp_zstd_decompress_async_v5", "nvcomp_zstd_get_compress_temp_size_v5", "nvcomp_zstd_get_decompress_temp_size_v5",
     "nvcomp_zstd_get_metadata_v5",
     "cuda_zstd_pipeline_create", "cuda_zstd_pipeline_destroy", "cuda_zstd_pipeline_compress",
+    "cuda_zstd_hybrid_create", "cuda_zstd_hybrid_create_default", "cuda_zstd_hybrid_destroy", "cuda_zstd_hybrid_compress",
+    "cuda_zstd_hybrid_decompress", "cuda_zstd_hybrid_max_compressed_size", "cuda_zstd_hybrid_query_routing",
 ]
+
+
+class HybridConfigC(C.Structure):       # cuda_zstd_hybrid_config_t (include/cuda_zstd_hybrid.h)
+    _fields_ = [("mode", C.c_uint), ("cpu_size_threshold", C.c_size_t), ("gpu_device_threshold", C.c_size_t),
+                ("compression_level", C.c_int), ("enable_profiling", C.c_int), ("cpu_thread_count", C.c_uint)]
+
+
+class HybridResultC(C.Structure):       # cuda_zstd_hybrid_result_t
+    _fields_ = [("backend_used", C.c_uint), ("input_location", C.c_uint), ("output_location", C.c_uint),
+                ("total_time_ms", C.c_double), ("transfer_time_ms", C.c_double), ("compute_time_ms", C.c_double),
+                ("throughput_mbps", C.c_double), ("input_bytes", C.c_size_t), ("output_bytes", C.c_size_t),
+                ("compression_ratio", C.c_float)]
+
 
 # callbacks of include/pipeline_manager.hpp
 PIPELINE_INPUT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t))
@@ -116,6 +131,18 @@ def load_library() -> C.CDLL:
     lib.cuda_zstd_pipeline_destroy.argtypes = [vp]
     lib.cuda_zstd_pipeline_compress.restype = i32
     lib.cuda_zstd_pipeline_compress.argtypes = [vp, PIPELINE_INPUT_FN, PIPELINE_OUTPUT_FN, vp]
+    lib.cuda_zstd_hybrid_create.restype = vp
+    lib.cuda_zstd_hybrid_create.argtypes = [C.POINTER(HybridConfigC)]
+    lib.cuda_zstd_hybrid_create_default.restype = vp
+    lib.cuda_zstd_hybrid_create_default.argtypes = []
+    lib.cuda_zstd_hybrid_destroy.argtypes = [vp]
+    for f in (lib.cuda_zstd_hybrid_compress, lib.cuda_zstd_hybrid_decompress):
+        f.restype = i32
+        f.argtypes = [vp, vp, sz, vp, C.POINTER(sz), C.c_uint, C.c_uint, C.POINTER(HybridResultC), vp]
+    lib.cuda_zstd_hybrid_max_compressed_size.restype = sz
+    lib.cuda_zstd_hybrid_max_compressed_size.argtypes = [vp, sz]
+    lib.cuda_zstd_hybrid_query_routing.restype = C.c_uint
+    lib.cuda_zstd_hybrid_query_routing.argtypes = [vp, sz, C.c_uint, C.c_uint, i32]
     _LIB = lib
     return lib
 
@@ -345,3 +372,43 @@ class ZstdPipeline:
         if state["ovf"]:
             raise RuntimeError("pipeline output buffer too small")
         return out[: state["wr"]], state["sizes"]
+
+
+class ZstdHybrid:
+    """HybridEngine C API (include/cuda_zstd_hybrid.h): host or device buffers in, host or device buffers out, always on the
+    GPU.  Locations: 0 host, 1 device, 3 detect."""
+    HOST, DEVICE, UNKNOWN = 0, 1, 3
+
+    def __init__(self, level: int = 3, mode: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ZstdHybrid needs a CUDA device (there is no CPU path in this library)")
+        self.lib = load_library()
+        cfg = HybridConfigC(mode, 1 << 20, 64 << 10, level, 0, 0)
+        self.h = self.lib.cuda_zstd_hybrid_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("cuda_zstd_hybrid_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cuda_zstd_hybrid_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def max_compressed_size(self, n: int) -> int:
+        return self.lib.cuda_zstd_hybrid_max_compressed_size(self.h, n)
+
+    def query_routing(self, n: int, in_loc: int = 0, out_loc: int = 0, compress: bool = True) -> int:
+        return self.lib.cuda_zstd_hybrid_query_routing(self.h, n, in_loc, out_loc, int(compress))
+
+    def _call(self, fn, src, n, dst, cap, in_loc, out_loc, stream):
+        size = C.c_size_t(cap)
+        res = HybridResultC()
+        rc = fn(self.h, _addr(src), n, _addr(dst), C.byref(size), in_loc, out_loc, C.byref(res), _stream_handle(stream))
+        return rc, size.value, res
+
+    def compress(self, src, n, dst, cap, in_loc=3, out_loc=3, stream=None):
+        return self._call(self.lib.cuda_zstd_hybrid_compress, src, n, dst, cap, in_loc, out_loc, stream)
+
+    def decompress(self, src, n, dst, cap, in_loc=3, out_loc=3, stream=None):
+        return self._call(self.lib.cuda_zstd_hybrid_decompress, src, n, dst, cap, in_loc, out_loc, stream)

@@ -171,12 +171,14 @@ HeaderInfo peek_header(const unsigned char *p, size_t n) {
 }
 } // namespace
 
-Status get_decompressed_size(const void *data, size_t size, size_t *out) {
+namespace {
+// strict form: a frame without a content size is an error (what the metadata helpers below want)
+Status frame_content_size(const void *data, size_t size, size_t *out) {
   if (!data || !out) return Status::ERROR_INVALID_PARAMETER;
   unsigned char head[18];
   size_t n = std::min<size_t>(size, sizeof head);
   cudaPointerAttributes at{};
-  if (cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+  if (cudaPointerGetAttributes(&at, data) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
     if (cudaMemcpy(head, data, n, cudaMemcpyDeviceToHost) != cudaSuccess) return Status::ERROR_CUDA_ERROR;
   } else { (void)cudaGetLastError(); std::memcpy(head, data, n); }
   HeaderInfo h = peek_header(head, n);
@@ -185,14 +187,33 @@ Status get_decompressed_size(const void *data, size_t size, size_t *out) {
   *out = (size_t)h.content_size;
   return Status::SUCCESS;
 }
+} // namespace
+// Public form, host or device pointer (reference src/cuda_zstd_types.cpp:1058-1106): a frame that does not declare its size
+// answers SUCCESS with 0 -- the reference's Python binding then falls back to an estimate (python/src/binding.cpp:247-250).
+Status get_decompressed_size(const void *data, size_t size, size_t *out) {
+  if (!data || !out || size < 4) return Status::ERROR_INVALID_PARAMETER;
+  *out = 0;
+  const Status s = frame_content_size(data, size, out);
+  if (s == Status::ERROR_CORRUPT_DATA) { *out = 0; return Status::SUCCESS; }
+  return s;
+}
+// Header-level check only, like the reference (src/cuda_zstd_types.cpp:1108-1170: magic, then "the header parses");
+// check_checksum is accepted and, as there, does not decode the frame.
+Status validate_compressed_data(const void *data, size_t size, bool) {
+  if (!data) return Status::ERROR_INVALID_PARAMETER;
+  if (size < 4) return Status::ERROR_CORRUPT_DATA;
+  size_t s = 0;
+  const Status st = frame_content_size(data, size, &s);
+  return st == Status::ERROR_CORRUPT_DATA ? Status::SUCCESS : st;
+}
 bool is_nvcomp_zstd_format(const void *data, size_t size) {
   size_t s = 0;
-  Status st = get_decompressed_size(data, size, &s);
+  Status st = frame_content_size(data, size, &s);
   return st == Status::SUCCESS || st == Status::ERROR_CORRUPT_DATA;
 }
 Status extract_metadata(const void *data, size_t size, NvcompMetadata &m) {
   size_t s = 0;
-  Status st = get_decompressed_size(data, size, &s);
+  Status st = frame_content_size(data, size, &s);
   if (st != Status::SUCCESS) return st;
   m = NvcompMetadata();
   m.format_version = get_format_version();

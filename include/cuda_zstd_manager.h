@@ -117,8 +117,11 @@ Status compress_simple(const void *uncompressed_data, size_t uncompressed_size, 
 Status decompress_simple(const void *compressed_data, size_t compressed_size, void *uncompressed_data,
                          size_t *uncompressed_size, cudaStream_t stream = 0);
 
-// Host helpers on a HOST copy of (the head of) a frame.
+// Frame-header helpers; the pointer may be host or device memory (reference src/cuda_zstd_types.cpp:1058-1170).
+// get_decompressed_size: a frame that declares no content size answers SUCCESS with *decompressed_size = 0.
 Status get_decompressed_size(const void *compressed_data, size_t compressed_size, size_t *decompressed_size);
+// magic + header check only (the reference does not decode either); check_checksum is accepted and unused
+Status validate_compressed_data(const void *compressed_data, size_t compressed_size, bool check_checksum = true);
 size_t estimate_compressed_size(size_t uncompressed_size, int compression_level);
 Status validate_config(const CompressionConfig &config);
 void apply_level_parameters(CompressionConfig &config);

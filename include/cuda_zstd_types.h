@@ -169,6 +169,49 @@ struct NvcompMetadata {
   ChecksumPolicy checksum_policy = ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
 };
 
+// ---- types of the HybridEngine surface (reference include/cuda_zstd_types.h:323-437) ----------------------------------
+// The reference's engine routes between host libzstd and its kernels.  This build has no host codec: every mode runs the
+// CUDA path, the mode / thresholds are kept for get_config() round trips, and results always name a GPU backend
+// (include/cuda_zstd_hybrid.h).  Enumerator values and field names are the reference's, since callers (its Python
+// binding, python/src/binding.cpp:689-751) spell them out.
+enum class HybridMode : u32 { AUTO = 0, PREFER_CPU = 1, PREFER_GPU = 2, FORCE_CPU = 3, FORCE_GPU = 4, ADAPTIVE = 5 };
+enum class DataLocation : u32 { HOST = 0, DEVICE = 1, MANAGED = 2, UNKNOWN = 3 };
+enum class ExecutionBackend : u32 { CPU_LIBZSTD = 0, GPU_KERNELS = 1, CPU_PARALLEL = 2, GPU_BATCH = 3 };
+
+struct HybridConfig {
+  HybridMode mode = HybridMode::AUTO;
+  size_t cpu_size_threshold = 1024 * 1024;      // kept, never consulted
+  size_t gpu_device_threshold = 64 * 1024;      // kept, never consulted
+  bool enable_profiling = false;
+  int compression_level = 3;
+  u32 cpu_thread_count = 0;
+  bool use_pinned_memory = true;
+  bool overlap_transfers = true;
+};
+
+struct HybridResult {
+  ExecutionBackend backend_used = ExecutionBackend::GPU_KERNELS;
+  DataLocation input_location = DataLocation::HOST;
+  DataLocation output_location = DataLocation::HOST;
+  double total_time_ms = 0.0;
+  double transfer_time_ms = 0.0;
+  double compute_time_ms = 0.0;
+  double throughput_mbps = 0.0;
+  size_t input_bytes = 0;
+  size_t output_bytes = 0;
+  float compression_ratio = 1.0f;
+  const char *routing_reason = nullptr;
+};
+
+struct BatchRoutingResult {
+  size_t item_index = 0;
+  ExecutionBackend backend_used = ExecutionBackend::GPU_BATCH;
+  Status status = Status::SUCCESS;
+  size_t input_bytes = 0;
+  size_t output_bytes = 0;
+  double compute_time_ms = 0.0;
+};
+
 constexpr u32 ZSTD_MAGIC = 0xFD2FB528;
 constexpr u32 MIN_COMPRESSION_LEVEL = 1;
 constexpr u32 MAX_COMPRESSION_LEVEL = 22;

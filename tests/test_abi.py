@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("cuda_zstd_batch_c.h", "cuda_zstd_manager.h", "cuda_zstd_nvcomp.h", "pipeline_manager.hpp"):
+    for h in ("cuda_zstd_batch_c.h", "cuda_zstd_manager.h", "cuda_zstd_nvcomp.h", "pipeline_manager.hpp", "cuda_zstd_hybrid.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         for block in re.findall(r'extern "C" \{(.*?)\n\}', text, flags=re.S):
             names.update(re.findall(r"\b((?:cuda_zstd|nvcomp_zstd)_[a-z0-9_]+)\s*\(", block))
@@ -21,7 +21,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol(pkg):
     lib = pkg.load_library()
     syms = declared_symbols()
-    assert len(syms) >= 34
+    assert len(syms) >= 41
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(pkg.binding.EXPORTS) == syms
