@@ -784,9 +784,14 @@ __device__ __forceinline__ void warp_copy_match(uint8_t *out, uint32_t d, uint32
 }
 
 // (9 CTAs per SM by registers = 56 per thread: eight resident KC CTAs then leave room for KB's CTA beside them)
+constexpr uint32_t EXEC_OWN = 256;      // pieces of a group whose owning sequence is looked up in shared memory (a group rarely has more)
 __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(FastDecodeArgs F) {
+  __shared__ uint8_t s_own[EXEC_WARPS][EXEC_OWN];
   const DecodeArgs &A = F.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t *const own = s_own[warp];
+  for (uint32_t k = lane; k < EXEC_OWN; k += 32) own[k] = 0;      // stale entries are only ever read for empty pieces, but must name a lane
+  __syncwarp();
   const uint32_t stride = gridDim.x * EXEC_WARPS;
   for (uint32_t chunk = F.lo + blockIdx.x * EXEC_WARPS + warp; chunk < F.hi; chunk += stride) {
     ChunkSlot slot = slot_of(F, chunk);
@@ -838,13 +843,20 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const uint32_t excl = incl - (ca + cb), total = __shfl_sync(0xffffffffu, incl, 31);
+        // piece -> owning sequence: every lane writes its own index over its range of pieces (a few stores), so that a piece
+        // finds its sequence with one shared load instead of a five-round shuffle search; pieces past EXEC_OWN still search
+        for (uint32_t k = excl, e = min(incl, EXEC_OWN); k < e; k++) own[k] = (uint8_t)lane;
+        __syncwarp();
         struct Piece { uint8_t *dp; uint32_t nb, sh, w0, w1, w2, w3, w4; };
-        // all 32 lanes call (shuffles inside); q >= total yields an empty piece
+        // all 32 lanes call (shuffles inside); q >= total yields an empty piece.  q - lane is warp-uniform.
         auto fetch = [&](uint32_t q) -> Piece {
           Piece P{nullptr, 0, 0, 0, 0, 0, 0, 0};
           uint32_t j = 0;
+          if (q - (uint32_t)lane + 32 <= EXEC_OWN) j = own[q];
+          else {
 #pragma unroll
-          for (int st = 16; st; st >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, excl, (j + st) & 31); if (j + st < 32 && pj <= q) j += st; }
+            for (int st = 16; st; st >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, excl, (j + st) & 31); if (j + st < 32 && pj <= q) j += st; }
+          }
           const uint32_t jx = __shfl_sync(0xffffffffu, r.x, j), jy = __shfl_sync(0xffffffffu, r.y, j), jz = __shfl_sync(0xffffffffu, r.z, j);
           const uint32_t jll = __shfl_sync(0xffffffffu, ll, j), jml = __shfl_sync(0xffffffffu, mlen, j);
           const uint32_t jca = __shfl_sync(0xffffffffu, ca, j), jex = __shfl_sync(0xffffffffu, excl, j);
@@ -894,11 +906,16 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
             }
           }
         };
-        for (uint32_t q0 = 0; q0 < total; q0 += 64) {
-          const Piece pa = fetch(q0 + (uint32_t)lane);
-          const Piece pb = fetch(q0 + 32 + (uint32_t)lane);
-          store(pa);
-          store(pb);
+        // software pipeline in units of 32 pieces: the loads of round k+1 are issued before the stores of round k, so two
+        // pieces per lane are in flight as before, but a group pays for ceil(total / 32) rounds instead of 2 * ceil(total / 64)
+        if (total) {
+          Piece cur = fetch((uint32_t)lane);
+          for (uint32_t q0 = 32; q0 < total; q0 += 32) {
+            const Piece nxt = fetch(q0 + (uint32_t)lane);
+            store(cur);
+            cur = nxt;
+          }
+          store(cur);
         }
         __syncwarp();
         // ---- matches that read this group's own output: in sequence order, the whole warp on each ----
