@@ -918,6 +918,18 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
           store(cur);
         }
         __syncwarp();
+        // ---- the next group's sources: its records have arrived by now (requested at the top of this iteration), so every lane
+        // asks for the line its own next sequence will read -- literal run and match source -- one group before the piece loads
+        // need them (the resident chunks' output and literals exceed the L2: without this those loads wait on HBM)
+        if (g0 + 32 < nseq) {
+          const uint32_t ny = __shfl_down_sync(0xffffffffu, r_nxt.y, 1);
+          const uint32_t nll = lane < 31 ? ny - r_nxt.y : 0u;
+          if (i + 32 < nseq) {
+            if (r_nxt.y < lit_size) { bool cg; asm volatile("prefetch.global.L1 [%0];" ::"l"(L.run(r_nxt.y, 1, &cg))); }
+            const uint32_t nd = r_nxt.x + nll;
+            if (r_nxt.z != 0 && r_nxt.z <= nd && nd < cap) asm volatile("prefetch.global.L1 [%0];" ::"l"(out + nd - r_nxt.z));
+          }
+        }
         // ---- matches that read this group's own output: in sequence order, the whole warp on each ----
         uint32_t dep = __ballot_sync(0xffffffffu, valid && !indep);
         while (dep) {
