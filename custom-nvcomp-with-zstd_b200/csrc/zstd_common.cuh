@@ -102,15 +102,28 @@ struct BackBits {
   __device__ __forceinline__ uint32_t read(int n) { uint32_t v = peek(n); skip(n); return v; }
 };
 
-// Forward little-endian bit reader for FSE table descriptions (byte loads; these headers are tiny).
+// Forward little-endian bit reader for FSE table descriptions.  Refills four bytes at a time from the aligned words under
+// the read position (the byte-by-byte loop this replaces was a seventh of the prepare kernel's instructions); bytes past
+// the end of the buffer read as zero, and no word that lies wholly outside [p, p + n) is touched.
 struct FwdBits {
   const uint8_t *p;
   uint32_t n, ip;
   uint64_t acc;
   int have;
   __device__ __forceinline__ void init(const uint8_t *src, uint32_t len) { p = src; n = len; ip = 0; acc = 0; have = 0; }
-  __device__ __forceinline__ void need(int k) {
-    while (have < k) { uint64_t b = (ip < n) ? p[ip] : 0; ip++; acc |= b << have; have += 8; }
+  __device__ __forceinline__ void need(int k) {          // k <= 32
+    if (have < k) {
+      uint32_t w = 0;
+      if (ip < n) {
+        const uintptr_t a = (uintptr_t)(p + ip);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const uint32_t mis = (uint32_t)(a & 3), valid = min(n - ip, 4u);
+        const uint32_t lo = wp[0], hi = (mis + valid > 4) ? wp[1] : 0u;
+        w = __funnelshift_r(lo, hi, mis * 8);
+        if (valid < 4) w &= (1u << (8 * valid)) - 1u;
+      }
+      acc |= (uint64_t)w << have; have += 32; ip += 4;
+    }
   }
   __device__ __forceinline__ uint32_t peek(int k) { need(k); return (uint32_t)(acc & ((1ull << k) - 1)); }
   __device__ __forceinline__ void drop(int k) { acc >>= k; have -= k; }

@@ -7,6 +7,7 @@
 #include "cuda_zstd_manager.h"
 #include "cuda_zstd_nvcomp.h"
 #include "cuda_zstd_batch_c.h"
+#include "cuda_zstd_hybrid.h"
 
 #include <cstdio>
 #include <cstring>
@@ -265,6 +266,74 @@ static void test_status_maps_and_config() {
   CHECK(get_last_error().status == Status::ERROR_INVALID_PARAMETER);
 }
 
+static void test_hybrid_engine_cpp() {
+  // HybridEngine C++ surface (reference include/cuda_zstd_hybrid.h:88-263; shape of tests/test_hybrid.cu's round trips), GPU-only here
+  HybridConfig cfg;
+  cfg.mode = HybridMode::FORCE_CPU;                         // accepted, stored, and still served by the GPU
+  cfg.compression_level = 5;
+  cfg.enable_profiling = true;
+  HybridEngine eng(cfg);
+  CHECK(eng.get_config().mode == HybridMode::FORCE_CPU && eng.get_config().compression_level == 5);
+  CHECK(eng.query_routing(100, DataLocation::HOST, DataLocation::HOST, true) == ExecutionBackend::GPU_KERNELS);
+  HybridConfig bad = cfg;
+  bad.compression_level = 0;
+  CHECK(eng.configure(bad) == Status::ERROR_INVALID_PARAMETER && eng.get_config().compression_level == 5);
+  CHECK(eng.set_compression_level(23) == Status::ERROR_INVALID_PARAMETER);
+  CHECK(eng.set_compression_level(3) == Status::SUCCESS && eng.get_config().compression_level == 3);
+  // single buffer, host to host, 300 KB (a multi-block frame)
+  std::vector<unsigned char> h(300 * 1024 + 17), c(eng.get_max_compressed_size(h.size())), back(h.size());
+  fill(h, 21);
+  size_t csz = c.size();
+  HybridResult res;
+  CHECK(eng.compress(h.data(), h.size(), c.data(), &csz, DataLocation::HOST, DataLocation::HOST, &res) == Status::SUCCESS);
+  CHECK(csz > 0 && csz < h.size() / 2 && res.backend_used == ExecutionBackend::GPU_KERNELS && res.output_bytes == csz);
+  CHECK(c[0] == 0x28 && c[1] == 0xB5 && c[2] == 0x2F && c[3] == 0xFD);
+  size_t bsz = back.size();
+  CHECK(eng.decompress(c.data(), csz, back.data(), &bsz, DataLocation::UNKNOWN, DataLocation::UNKNOWN, &res) == Status::SUCCESS);
+  CHECK(bsz == h.size() && std::memcmp(back.data(), h.data(), h.size()) == 0);
+  CHECK(res.input_location == DataLocation::HOST && res.output_location == DataLocation::HOST);
+  CHECK(eng.get_observed_throughput(ExecutionBackend::GPU_KERNELS, true) > 0 && eng.get_observed_throughput(ExecutionBackend::CPU_LIBZSTD, true) == 0);
+  size_t tiny = 10;
+  CHECK(eng.decompress(c.data(), csz, back.data(), &tiny) == Status::ERROR_BUFFER_TOO_SMALL);
+  CHECK(eng.compress(nullptr, 10, c.data(), &csz) == Status::ERROR_INVALID_PARAMETER);
+  CHECK(eng.compress(h.data(), 0, c.data(), &csz) == Status::ERROR_INVALID_PARAMETER);
+  // batch: 6 host items of different sizes in ONE launch, one of them with too little room
+  const size_t n = 6;
+  const size_t sizes[n] = {1, 100, 4096, 65536, 100000, 131072};
+  std::vector<std::vector<unsigned char>> in(n), comp(n), out(n);
+  std::vector<const void *> ip(n);
+  std::vector<void *> cp(n), op(n);
+  std::vector<size_t> isz(n), csz2(n), osz(n);
+  for (size_t i = 0; i < n; ++i) {
+    in[i].resize(sizes[i]); fill(in[i], 30 + (unsigned)i);
+    comp[i].resize(eng.get_max_compressed_size(sizes[i])); out[i].resize(sizes[i]);
+    ip[i] = in[i].data(); cp[i] = comp[i].data(); op[i] = out[i].data(); isz[i] = sizes[i]; csz2[i] = comp[i].size(); osz[i] = sizes[i];
+  }
+  std::vector<BatchRoutingResult> rr(n);
+  CHECK(eng.compress_batch(ip.data(), isz.data(), cp.data(), csz2.data(), n, DataLocation::HOST, DataLocation::HOST, rr.data()) == Status::SUCCESS);
+  for (size_t i = 0; i < n; ++i) CHECK(rr[i].status == Status::SUCCESS && rr[i].backend_used == ExecutionBackend::GPU_BATCH && csz2[i] > 0 && rr[i].output_bytes == csz2[i]);
+  std::vector<const void *> cip(cp.begin(), cp.end());
+  CHECK(eng.decompress_batch(cip.data(), csz2.data(), op.data(), osz.data(), n, DataLocation::HOST, DataLocation::HOST, rr.data()) == Status::SUCCESS);
+  for (size_t i = 0; i < n; ++i) CHECK(osz[i] == sizes[i] && std::memcmp(out[i].data(), in[i].data(), sizes[i]) == 0);
+  osz[3] = 1000;                                            // capacity too small for item 3 only
+  CHECK(eng.decompress_batch(cip.data(), csz2.data(), op.data(), osz.data(), n, DataLocation::HOST, DataLocation::HOST, rr.data()) == Status::ERROR_DECOMPRESSION);
+  CHECK(rr[3].status == Status::ERROR_BUFFER_TOO_SMALL && osz[3] == 0 && rr[2].status == Status::SUCCESS && osz[2] == sizes[2]);
+  CHECK(eng.compress_batch(ip.data(), isz.data(), cp.data(), csz2.data(), 0) == Status::ERROR_INVALID_PARAMETER);   // hybrid.cu:920
+  CompressionStats st = eng.get_stats();
+  CHECK(st.input_bytes > 0 && st.output_bytes > 0 && st.bytes_decompressed > 0);
+  eng.reset_stats();
+  CHECK(eng.get_stats().input_bytes == 0);
+  // free functions and factories
+  csz = c.size();
+  CHECK(hybrid_compress(h.data(), 5000, c.data(), &csz, DataLocation::HOST, DataLocation::HOST, 7) == Status::SUCCESS);
+  bsz = back.size();
+  CHECK(hybrid_decompress(c.data(), csz, back.data(), &bsz) == Status::SUCCESS && bsz == 5000 && std::memcmp(back.data(), h.data(), 5000) == 0);
+  CHECK(create_hybrid_engine(4)->get_config().compression_level == 4);
+  size_t vs = 0;
+  CHECK(validate_compressed_data(c.data(), csz) == Status::SUCCESS && validate_compressed_data(h.data(), 100) == Status::ERROR_INVALID_MAGIC);
+  CHECK(get_decompressed_size(c.data(), csz, &vs) == Status::SUCCESS && vs == 5000);
+}
+
 int main() {
   int dev = 0;
   if (cudaGetDeviceCount(&dev) != cudaSuccess || dev == 0) { std::printf("SKIP: no CUDA device\n"); return 77; }
@@ -272,6 +341,7 @@ int main() {
   test_batch_manager_roundtrip();
   test_single_buffer_and_inference_api();
   test_nvcomp_facade_device_tables();
+  test_hybrid_engine_cpp();
   std::printf(g_fail ? "FAILED (%d)\n" : "ALL PASSED\n", g_fail);
   return g_fail ? 1 : 0;
 }
