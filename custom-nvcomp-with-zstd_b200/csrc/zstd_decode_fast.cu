@@ -478,15 +478,42 @@ __device__ inline void fse_build_warp_packed(const SeqTab &T, uint32_t off, cons
   const int size = 1 << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
   uint8_t *cell = T.t8 + off;                       // the byte plane doubles as the symbol-of-cell scratch
   uint8_t *item_sym = (uint8_t *)(T.t16 + off);     // and the 16-bit plane, not written before the last pass, holds the sorted symbols
-  int high = size - 1, acc = 0;
-  for (int s = 0; s <= max_sym; s++) {
-    const int c = norm[s];
-    if (c == -1) { if (lane == 0) { cell[high] = (uint8_t)s; sym_next[s] = 1; } high--; }
-    else {
-      if (lane == 0) sym_next[s] = (uint16_t)c;
-      for (int k = lane; k < c; k += 32) item_sym[acc + k] = (uint8_t)s;
-      acc += c;
-    }
+  // symbols sorted by value with multiplicity (item_sym), low-probability symbols parked at the top cells.  Lane l owns symbols
+  // l and l + 32: two warp scans give every symbol its first item, the symbol is written there, and a running maximum over
+  // the item array (symbols ascend) fills the rest -- ~200 warp instructions where a loop over the symbols took ~900
+  const int s0 = lane, s1 = lane + 32;
+  const int c0 = s0 <= max_sym ? norm[s0] : 0, c1 = s1 <= max_sym ? norm[s1] : 0;
+  const uint32_t neg0 = __ballot_sync(0xffffffffu, c0 == -1), neg1 = __ballot_sync(0xffffffffu, c1 == -1);
+  const int p0 = c0 > 0 ? c0 : 0, p1 = c1 > 0 ? c1 : 0;
+  int i0 = p0, i1 = p1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+    if (lane >= o) { i0 += t0; i1 += t1; }
+  }
+  const int st0 = i0 - p0, st1 = __shfl_sync(0xffffffffu, i0, 31) + i1 - p1;
+  for (int k = lane * 4; k < size; k += 128) *reinterpret_cast<uint32_t *>(item_sym + k) = 0u;
+  __syncwarp();
+  if (s0 <= max_sym) {
+    if (c0 == -1) { cell[size - 1 - __popc(neg0 & lanemask_lt())] = (uint8_t)s0; sym_next[s0] = 1; }
+    else { sym_next[s0] = (uint16_t)c0; if (c0 > 0) item_sym[st0] = (uint8_t)s0; }
+  }
+  if (s1 <= max_sym) {
+    if (c1 == -1) { cell[size - 1 - __popc(neg0) - __popc(neg1 & lanemask_lt())] = (uint8_t)s1; sym_next[s1] = 1; }
+    else { sym_next[s1] = (uint16_t)c1; if (c1 > 0) item_sym[st1] = (uint8_t)s1; }
+  }
+  const int high = size - 1 - __popc(neg0) - __popc(neg1);
+  __syncwarp();
+  {
+    const int seg = size >> 5, base = lane * seg;              // size >= 32: sequence tables have accuracy log >= 5
+    uint32_t m = 0;
+    for (int k = 0; k < seg; k++) m = max(m, (uint32_t)item_sym[base + k]);
+    uint32_t pm = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pm, o); if (lane >= o) pm = max(pm, t); }
+    uint32_t v = __shfl_up_sync(0xffffffffu, pm, 1);
+    if (lane == 0) v = 0;
+    for (int k = 0; k < seg; k++) { v = max(v, (uint32_t)item_sym[base + k]); item_sym[base + k] = (uint8_t)v; }
   }
   __syncwarp();
   int run = 0;
