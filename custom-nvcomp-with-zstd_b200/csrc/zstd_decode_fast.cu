@@ -819,8 +819,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
   uint8_t *const own = s_own[warp];
   for (uint32_t k = lane; k < EXEC_OWN; k += 32) own[k] = 0;      // stale entries are only ever read for empty pieces, but must name a lane
   __syncwarp();
-  const uint32_t stride = gridDim.x * EXEC_WARPS;
-  for (uint32_t chunk = F.lo + blockIdx.x * EXEC_WARPS + warp; chunk < F.hi; chunk += stride) {
+  // chunks are handed out through a work counter (one per sub-wave, zeroed with the workspace header): in a mixed batch a warp
+  // that draws raw / RLE chunks (finished by KP) or short ones simply takes more of them
+  uint32_t *const queue = F.base.counter + 2 + F.sub;
+  for (;;) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = F.lo + atomicAdd(queue, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= F.hi) break;
     ChunkSlot slot = slot_of(F, chunk);
     const FastDesc *D = slot.desc();
     if (D->state != 0) continue;
