@@ -54,7 +54,10 @@ struct __align__(16) FastDesc {
   uint32_t lit_status[4];                     // written by the Huffman threads
   uint32_t lit_slot, seq_slot;                // pool offsets in 16-byte units
 };
-static_assert(sizeof(FastDesc) <= FAST_DESC_BYTES, "descriptor slot too small");
+// The tail of the descriptor area holds KC's per-chunk hand-over words: [0] parts of the chunk executed so far, [1] the status
+// the finished parts arrived at (zeroed by KP; see zstd_fast_exec_kernel).
+constexpr uint32_t FAST_PROG_OFF = 160;
+static_assert(sizeof(FastDesc) <= FAST_PROG_OFF && FAST_PROG_OFF + 8 <= FAST_DESC_BYTES, "descriptor slot too small");
 
 struct ChunkSlot {
   uint8_t *base, *lit_pool, *seq_pool;
@@ -657,7 +660,7 @@ __global__ void __launch_bounds__(KP_WARPS * 32) zstd_fast_prep_kernel(FastDecod
     ChunkSlot slot = slot_of(F, chunk);
     FastDesc *D = slot.desc();
     SeqInfo *const info = reinterpret_cast<SeqInfo *>(slot.seq_info());
-    if (lane == 0) info->ready = 0;
+    if (lane == 0) { info->ready = 0; *reinterpret_cast<uint2 *>(slot.base + FAST_PROG_OFF) = make_uint2(0, 0); }
     if (D->state != 0) continue;                                                              // uniform per warp
     const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
     const uint32_t nseq = D->nseq;
@@ -767,6 +770,7 @@ __global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecode
 // KC: sequence execution, one warp per chunk, one lane per sequence
 // =================================================================================================
 constexpr int EXEC_WARPS = 4;
+constexpr uint32_t EXEC_PARTS = 4;     // work items per chunk (see the queue in zstd_fast_exec_kernel)
 
 struct LitSrc {
   const uint8_t *base;
@@ -821,19 +825,43 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
   __syncwarp();
   // chunks are handed out through a work counter (one per sub-wave, zeroed with the workspace header): in a mixed batch a warp
   // that draws raw / RLE chunks (finished by KP) or short ones simply takes more of them
+  // A chunk is executed in EXEC_PARTS consecutive parts (quarters of its groups), each a work item of its own: items are
+  // numbered part-major, so part p of a chunk is always drawn after part p - 1, by whichever warp is free.  With one item
+  // per chunk a sub-wave of 8,192 chunks gave the 4,736 resident warps 1.73 items each -- two rounds, the second with a
+  // quarter of the warps idle; quarters make that 6.9 -> 7 rounds of a quarter's length.  A part waits for its predecessor
+  // on the chunk's hand-over word (release / acquire at gpu scope: its matches read what the predecessor wrote, possibly
+  // on another SM); the predecessor is always held by a running warp, and part 0 waits for nobody.
   uint32_t *const queue = F.base.counter + 2 + F.sub;
+  const uint32_t span = F.hi - F.lo;
   for (;;) {
-    uint32_t chunk = 0;
-    if (lane == 0) chunk = F.lo + atomicAdd(queue, 1u);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (chunk >= F.hi) break;
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= span * EXEC_PARTS) break;
+    const uint32_t part = item / span, chunk = F.lo + (item - part * span);
     ChunkSlot slot = slot_of(F, chunk);
     const FastDesc *D = slot.desc();
     if (D->state != 0) continue;
+    uint32_t *const prog = reinterpret_cast<uint32_t *>(slot.base + FAST_PROG_OFF);
     const uint8_t *const src = (const uint8_t *)A.in_ptrs[chunk];
     uint8_t *const out = (uint8_t *)A.out_ptrs[chunk];
-    uint32_t status = D->seq_status;
-    for (uint32_t k = 0; k < D->n_streams; k++) if (status == ST_OK) status = D->lit_status[k];
+    uint32_t status;
+    if (part == 0) {
+      status = D->seq_status;
+      for (uint32_t k = 0; k < D->n_streams; k++) if (status == ST_OK) status = D->lit_status[k];
+    } else {
+      uint32_t seen = 0;
+      if (lane == 0) {
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prog) : "memory");
+          if (seen >= part) break;
+          __nanosleep(100);
+        }
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prog + 1) : "memory");
+      }
+      __syncwarp();
+      status = __shfl_sync(0xffffffffu, seen, 0);
+    }
     uint32_t total = 0;
     if (status == ST_OK) {
       const uint32_t nseq = D->nseq, lit_size = D->lit_size, cap = D->cap;
@@ -843,9 +871,11 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
       const uint4 *__restrict__ seqs = slot.seqs();
       const uintptr_t out_addr = (uintptr_t)out;
       // records of the first group (the sentinel at index nseq is fetched like a record: it ends the last literal run)
+      const uint32_t groups = (nseq + 31) >> 5;
+      const uint32_t g_lo = (groups * part / EXEC_PARTS) << 5, g_hi = min(nseq, (groups * (part + 1) / EXEC_PARTS) << 5);
       uint4 r_nxt = make_uint4(0, 0, 0, 0);
-      if ((uint32_t)lane <= nseq) r_nxt = __ldcs(seqs + lane);
-      for (uint32_t g0 = 0; g0 < nseq; g0 += 32) {
+      if (g_lo + (uint32_t)lane <= nseq) r_nxt = __ldcs(seqs + g_lo + lane);
+      for (uint32_t g0 = g_lo; g0 < g_hi; g0 += 32) {
         const uint32_t i = g0 + (uint32_t)lane;
         const bool valid = i < nseq;
         const uint4 r = r_nxt;
@@ -973,6 +1003,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
           __syncwarp();
         }
       }
+      if (part + 1 < EXEC_PARTS) {                          // hand the chunk over: everything this warp wrote, then the word
+        __syncwarp();
+        if (lane == 0) {
+          prog[1] = status;
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog), "r"(part + 1) : "memory");
+        }
+        continue;
+      }
       // trailing literals
       const uint32_t out_end = D->out_end, lit_end = D->lit_end, rest = lit_size - lit_end;
       if (status != ST_OK) {}
@@ -1001,6 +1040,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
         const uint64_t hs = xxh64_warp(out, total, lane);
         if ((uint32_t)hs != ld_le32(src + D->ck_off)) status = ST_CHECKSUM;
       }
+    }
+    if (part + 1 < EXEC_PARTS) {                            // (only reached with a failed status: pass it on)
+      __syncwarp();
+      if (lane == 0) {
+        prog[1] = status;
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog), "r"(part + 1) : "memory");
+      }
+      continue;
     }
     if (lane == 0) {
       A.out_sizes[chunk] = status == ST_OK ? total : 0;
