@@ -1127,9 +1127,12 @@ cudaError_t launch_verify_checksum(const void *d_data, size_t n, const void *d_e
 // KC grid: a bounded number of resident CTAs per SM, each striding over chunks.  Fewer chunks in flight keep the
 // recently written output (the match sources) inside the 126 MB L2 instead of re-reading it from HBM.
 static int g_exec_ctas_per_sm = 8;    // = what 64 registers x 128 threads leave resident: every CTA of the grid runs at once
+static int g_exec_ctas_last = 0;      // KC of the last sub-wave runs alone (0 = same as the others)
 extern "C" void cuda_zstd_b200_tune_exec_ctas(int v) { if (v > 0) g_exec_ctas_per_sm = v; }
-static uint32_t exec_grid(uint32_t chunks, uint32_t sms) {
-  const uint32_t blocks = (chunks + EXEC_WARPS - 1) / EXEC_WARPS, cap = sms * (uint32_t)g_exec_ctas_per_sm;
+extern "C" void cuda_zstd_b200_tune_exec_ctas_last(int v) { g_exec_ctas_last = v > 0 ? v : 0; }
+static uint32_t exec_grid(uint32_t chunks, uint32_t sms, bool last = false) {
+  const int per_sm = last && g_exec_ctas_last ? g_exec_ctas_last : g_exec_ctas_per_sm;
+  const uint32_t blocks = (chunks + EXEC_WARPS - 1) / EXEC_WARPS, cap = sms * (uint32_t)per_sm;
   return blocks < cap ? blocks : cap;
 }
 
@@ -1180,7 +1183,7 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
       mark("KB", stream);
       if ((e = cudaEventRecord(ov->ev[k], stream)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(ov->side, ov->ev[k], 0)) != cudaSuccess) return e;
-      zstd_fast_exec_kernel<<<exec_grid(m, sms), EXEC_WARPS * 32, 0, ov->side>>>(F);
+      zstd_fast_exec_kernel<<<exec_grid(m, sms, k + 1 == nsub), EXEC_WARPS * 32, 0, ov->side>>>(F);
       mark("KC", ov->side);
       count += 2;
     }
