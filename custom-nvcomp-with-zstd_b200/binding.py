@@ -14,7 +14,8 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcuda_zstd_b200.so")
+# CUDA_ZSTD_B200_LIB selects an instrumented build of the same library (tools/esd_prof.py); there is no other fallback
+LIB_PATH = os.environ.get("CUDA_ZSTD_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcuda_zstd_b200.so")
 _LIB: Optional[C.CDLL] = None
 
 

@@ -277,6 +277,35 @@ public:
     return (int)std::min<size_t>(n, (size_t)sm_count * per);
   }
   static size_t table_bytes(size_t n) { return align_up(n * 40, 256); }
+  // ---- encoder placement: levels 1-4 run the decoupled pipeline (zstd_encode_esd.cu), the chain levels and items of
+  // more than one block the general kernel (zstd_encode.cu) ----
+  bool use_esd() const { return b200zstd::esd_level(std::max(cfg.level, 1)); }
+  static size_t lists_bytes(size_t n) { return align_up(n * 8, 256); }
+  size_t enc_scratch_bytes(size_t n) const {
+    const size_t general = b200zstd::encode_cta_scratch_bytes(enc_params());
+    if (use_esd()) {
+      const size_t a = std::min<size_t>(n, (size_t)sm_count * b200zstd::esd_ctas_per_sm(0)) * b200zstd::esd_cta_scratch_bytes(0);
+      const size_t b = std::min<size_t>(n, (size_t)sm_count * b200zstd::esd_ctas_per_sm(1)) * b200zstd::esd_cta_scratch_bytes(1);
+      return std::max(std::max(a, b), general);
+    }
+    return (size_t)enc_grid(n) * general;
+  }
+  // a.counter / a.scratch are set here; w = workspace base (counters live in its header), lists = 2 n words
+  cudaError_t enqueue_encode(b200zstd::EncodeArgs &a, unsigned char *w, unsigned char *lists, unsigned char *scratch, size_t min_item,
+                             size_t max_item, cudaStream_t stream, int *launches) {
+    a.scratch = scratch;
+    if (use_esd()) {
+      b200zstd::EsdLaunch L{};
+      L.counters = reinterpret_cast<u32 *>(w + 128);
+      L.lists = reinterpret_cast<u32 *>(lists);
+      L.scratch = scratch; L.scratch_bytes = enc_scratch_bytes(a.n);
+      L.sm_count = sm_count; L.min_item_bytes = min_item; L.max_item_bytes = max_item;
+      return b200zstd::launch_encode_esd(a, L, stream, launches);
+    }
+    a.counter = reinterpret_cast<u32 *>(w);
+    *launches = 1;
+    return b200zstd::launch_encode_batch(a, enc_grid(a.n), stream);
+  }
   // decode workspace: header | staged tables | slow list | general-kernel literal scratch | fast-path slots
   static size_t wave_of(size_t n) { return std::min<size_t>(n, b200zstd::FAST_WAVE); }
   static size_t slow_list_bytes(size_t n) { return align_up(wave_of(n) * 4, 256); }
@@ -304,7 +333,7 @@ public:
   }
   size_t enc_temp(size_t n, const size_t *sizes = nullptr) const {
     if (n == 0) return 0;
-    size_t e = b200zstd::WS_HEADER_BYTES + table_bytes(n) + (size_t)enc_grid(n) * b200zstd::encode_cta_scratch_bytes(enc_params());
+    size_t e = b200zstd::WS_HEADER_BYTES + table_bytes(n) + lists_bytes(n) + enc_scratch_bytes(n);
     // a compress workspace can always be reused for decompress (reference tests/test_c_api.cpp:62-64):
     // the decoder needs dec_fixed(); pool space beyond that only decides how many chunks take the fast path
     (void)sizes;
@@ -321,7 +350,7 @@ public:
   static size_t big_tables(size_t B) { return align_up(B * 44 + (B + 1) * 8, 256); }
   size_t big_temp(size_t n) const {
     const size_t B = big_blocks(n);
-    return b200zstd::WS_HEADER_BYTES + big_tables(B) + (size_t)enc_grid(B) * b200zstd::encode_cta_scratch_bytes(enc_params()) + B * big_slot();
+    return b200zstd::WS_HEADER_BYTES + big_tables(B) + lists_bytes(B) + enc_scratch_bytes(B) + B * big_slot();
   }
   // Enqueue only: nothing is synchronised.  The outcome {frame bytes, first failing block status} lands in the 16-byte
   // device mailbox at ws + 64 and, when h_result is given (pinned host memory), is copied there on the same stream.
@@ -341,9 +370,9 @@ public:
     u32 *counter = reinterpret_cast<u32 *>(w);
     u64 *d_result = reinterpret_cast<u64 *>(w + 64);
     unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
-    unsigned char *scratch = tab + big_tables(B);
-    const int grid = enc_grid(B);
-    unsigned char *slots = scratch + (size_t)grid * b200zstd::encode_cta_scratch_bytes(enc_params());
+    unsigned char *lists = tab + big_tables(B);
+    unsigned char *scratch = lists + lists_bytes(B);
+    unsigned char *slots = scratch + enc_scratch_bytes(B);
     std::vector<u64> host(4 * B);
     for (size_t i = 0; i < B; ++i) {
       host[i] = (u64)(uintptr_t)(static_cast<const unsigned char *>(d_src) + i * BIG_BLOCK);
@@ -360,15 +389,16 @@ public:
     b200zstd::EncodeArgs a{};
     a.in_ptrs = reinterpret_cast<const void *const *>(tab); a.in_sizes = reinterpret_cast<const size_t *>(tab + B * 8);
     a.out_ptrs = reinterpret_cast<void *const *>(tab + 2 * B * 8); a.out_sizes = reinterpret_cast<size_t *>(tab + 3 * B * 8);
-    a.statuses = d_status; a.counter = counter; a.scratch = scratch; a.n = (uint32_t)B; a.block_mode = 1; a.prm = enc_params();
+    a.statuses = d_status; a.counter = counter; a.n = (uint32_t)B; a.block_mode = 1; a.prm = enc_params();
     a.prm.checksum = 0;
-    if ((e = b200zstd::launch_encode_batch(a, grid, stream)) != cudaSuccess) return cuda_fail(e, fn);
+    int enc_launches = 0;
+    if ((e = enqueue_encode(a, w, lists, scratch, n - (B - 1) * BIG_BLOCK, std::min(n, BIG_BLOCK), stream, &enc_launches)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = b200zstd::launch_scan_sizes(a.out_sizes, B, sizeof hdr, reinterpret_cast<uint64_t *>(d_offsets), stream)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = b200zstd::launch_pack(a.out_ptrs, a.out_sizes, reinterpret_cast<const uint64_t *>(d_offsets), B, d_dst, stream)) != cudaSuccess) return cuda_fail(e, fn);
-    last_launches = 4;
+    last_launches = 3 + enc_launches;
     if (ck) {
       if ((e = b200zstd::launch_frame_checksum(d_src, n, d_dst, reinterpret_cast<const uint64_t *>(d_offsets + B), stream)) != cudaSuccess) return cuda_fail(e, fn);
-      last_launches = 5;
+      last_launches++;
     }
     if ((e = b200zstd::launch_big_result(d_status, B, reinterpret_cast<const uint64_t *>(d_offsets + B), ck ? 4 : 0, d_result, stream)) != cudaSuccess) return cuda_fail(e, fn);
     if (h_result && (e = cudaMemcpyAsync(h_result, d_result, 16, cudaMemcpyDefault, stream)) != cudaSuccess) return cuda_fail(e, fn);
@@ -451,6 +481,12 @@ public:
     u32 *counter = reinterpret_cast<u32 *>(w);
     unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
     unsigned char *scratch = tab + table_bytes(n);
+    size_t min_item = 0, max_item = 0;              // 0 / 0 = unknown (device-resident size table)
+    if (compress && !tables_on_device) {
+      min_item = ~(size_t)0;
+      for (size_t i = 0; i < n; ++i) { min_item = std::min(min_item, in_sizes[i]); max_item = std::max(max_item, in_sizes[i]); }
+      if (max_item == 0) max_item = 1;              // all-empty batch: every item is an error, any kernel reports it
+    }
     const void *const *d_in = in_ptrs;
     const size_t *d_in_sz = in_sizes;
     void *const *d_out = out_ptrs;
@@ -473,9 +509,8 @@ public:
     if (compress) {
       b200zstd::EncodeArgs a{};
       a.in_ptrs = d_in; a.in_sizes = d_in_sz; a.out_ptrs = d_out; a.out_sizes = d_out_sz; a.statuses = d_status;
-      a.counter = counter; a.scratch = scratch; a.n = (uint32_t)n; a.prm = enc_params();
-      e = b200zstd::launch_encode_batch(a, enc_grid(n), stream);
-      last_launches = 1;
+      a.counter = counter; a.n = (uint32_t)n; a.prm = enc_params();
+      e = enqueue_encode(a, w, scratch, scratch + lists_bytes(n), min_item, max_item, stream, &last_launches);
     } else {
       // fast path in waves of FAST_WAVE chunks (bounds the scratch); each wave is 4 launches:
       // prep, entropy, execute, and the general kernel for whatever the fast path declined
@@ -755,12 +790,14 @@ Status ZstdBatchManager::compress_async_no_sync(const void *src, size_t n, void 
   b200zstd::EncodeArgs a{};
   a.in_ptrs = reinterpret_cast<const void *const *>(tab); a.in_sizes = reinterpret_cast<const size_t *>(tab + 8);
   a.out_ptrs = reinterpret_cast<void *const *>(tab + 16); a.out_sizes = reinterpret_cast<size_t *>(tab + 24);
-  a.statuses = reinterpret_cast<u32 *>(tab + 32); a.counter = reinterpret_cast<u32 *>(w); a.scratch = tab + Impl::table_bytes(1);
+  a.statuses = reinterpret_cast<u32 *>(tab + 32); a.counter = reinterpret_cast<u32 *>(w);
   a.n = 1; a.prm = I.enc_params();
-  if ((e = b200zstd::launch_encode_batch(a, 1, stream)) != cudaSuccess) return cuda_fail(e, fn);
+  int enc_launches = 0;
+  unsigned char *lists = tab + Impl::table_bytes(1);
+  if ((e = I.enqueue_encode(a, w, lists, lists + Impl::lists_bytes(1), n, n, stream, &enc_launches)) != cudaSuccess) return cuda_fail(e, fn);
   if ((e = b200zstd::launch_big_result(a.statuses, 1, reinterpret_cast<const uint64_t *>(tab + 24), 0, d_result, stream)) != cudaSuccess) return cuda_fail(e, fn);
   if ((e = cudaMemcpyAsync(result16, d_result, 16, cudaMemcpyDefault, stream)) != cudaSuccess) return cuda_fail(e, fn);
-  I.last_launches = 2;
+  I.last_launches = 1 + enc_launches;
   return Status::SUCCESS;
 }
 // both sizes are known here, so the block-parallel path for multi-block frames is provisioned exactly

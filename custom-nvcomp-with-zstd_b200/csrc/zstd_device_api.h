@@ -88,9 +88,25 @@ struct EncodeArgs {
   uint32_t n;
   uint32_t block_mode;      // 1: items are the consecutive <= 128 KB blocks of one frame (no frame header / checksum, see kernel)
   EncodeParams prm;
+  const uint32_t *list;        // optional: item indices to process instead of 0 .. n-1 (device memory) ...
+  const uint32_t *list_count;  // ... and how many of them
 };
 size_t encode_cta_scratch_bytes(const EncodeParams &prm);
 cudaError_t launch_encode_batch(const EncodeArgs &args, int grid, cudaStream_t stream);
+cudaError_t launch_encode_batch_nomemset(const EncodeArgs &args, int grid, cudaStream_t stream);   // counter already zero
+
+// ---- levels 1-4: the decoupled pipeline (zstd_encode_esd.cu) ----
+struct EsdLaunch {
+  uint32_t *counters;       // 8 words, zeroed by the launcher: work heads of the three kernels, list counts
+  uint32_t *lists;          // 2 * n words: items handed to the 128 KB-block kernel | to the general kernel
+  uint8_t *scratch;         // encode_esd_scratch_bytes()
+  size_t scratch_bytes;
+  int sm_count;
+  size_t min_item_bytes, max_item_bytes;    // 0 / 0: unknown (size table lives on the device)
+};
+size_t esd_cta_scratch_bytes(int big);
+int esd_ctas_per_sm(int big);
+cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaStream_t stream, int *launches);
 int encode_ctas_per_sm(const EncodeParams &prm);
 
 // low 32 bits of XXH64(src[0..n)) written at dst + *d_where (n < 4 GiB)

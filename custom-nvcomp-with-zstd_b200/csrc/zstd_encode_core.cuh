@@ -15,7 +15,7 @@
 
 #if defined(__CUDACC__)
 #define ZHD __host__ __device__ __forceinline__
-#define ZHDN __host__ __device__
+#define ZHDN __host__ __device__ inline
 #else
 #define ZHD inline
 #define ZHDN inline

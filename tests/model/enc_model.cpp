@@ -169,6 +169,117 @@ void parse_block(const uint8_t *chunk, uint32_t blk_off, uint32_t bn, const Enco
   (void)ip;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Levels 1-4, blocks <= 128 KB: the decoupled parse of zstd_encode_esd.cu, stage by stage.
+//   hash stage   : fixed windows of 32 positions; every position looks its candidate(s) up in the table state left by
+//                  the windows before it, or takes the nearest lower position of its own window that has the same hash
+//                  and was inserted; then the window is inserted (a position whose hash equals its predecessor's is
+//                  not: runs keep their first position).  uint16 entries, zero = "position 0" (never-written buckets).
+//   verify stage : long candidate needs 8 equal bytes, the short one ESD_MIN_MATCH; an 8-byte match is measured up to
+//                  ESD_LCAP bytes.
+//   select stage : windows of 32 positions from the parse position: repeat-offset matches (>= 4 bytes, byte-exact
+//                  inside the window) and measured table matches; first candidate wins (optionally displaced by its
+//                  right neighbour), open matches are finished, then extended backwards into pending literals.
+// ------------------------------------------------------------------------------------------------
+void parse_block_esd(const uint8_t *b, uint32_t bn, const EsdParams &E, uint32_t rep[3], BlockOut &out) {
+  const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
+  std::vector<uint32_t> Roff((size_t)bn + 64, 0), Rlen((size_t)bn + 64, 0);
+  std::vector<uint16_t> tab1((size_t)1 << E.hash_log, 0), tab2(E.dfast ? (size_t)1 << E.long_log : 0, 0);
+  auto recon = [](uint32_t pos, uint16_t e) -> int64_t {
+    int64_t c = (int64_t)((pos & ~0xFFFFu) | e);
+    if (c >= (int64_t)pos) c -= 0x10000;
+    return c;
+  };
+  uint32_t prev_h1 = 0xFFFFFFFFu, prev_h2 = 0xFFFFFFFFu;
+  for (uint32_t p0 = 0; p0 < ilimit; p0 += 32) {
+    uint32_t h1[32], h2[32];
+    int64_t c1[32], c2[32];
+    bool act[32], ins1[32], ins2[32];
+    for (int l = 0; l < 32; l++) {
+      const uint32_t p = p0 + l;
+      act[l] = p < ilimit; ins1[l] = ins2[l] = false; h1[l] = h2[l] = 0; c1[l] = c2[l] = -1;
+      if (!act[l]) continue;
+      const uint64_t v = read64(b, p, bn);
+      h1[l] = hash_short(v, E.hash_bytes, E.hash_log);
+      c1[l] = recon(p, tab1[h1[l]]);
+      ins1[l] = (l > 0 ? h1[l - 1] : prev_h1) != h1[l];
+      for (int m = l - 1; m >= 0; m--) if (ins1[m] && h1[m] == h1[l]) { c1[l] = (int64_t)(p0 + m); break; }
+      if (E.dfast) {
+        h2[l] = hash_long(v, E.long_log);
+        c2[l] = recon(p, tab2[h2[l]]);
+        ins2[l] = (l > 0 ? h2[l - 1] : prev_h2) != h2[l];
+        for (int m = l - 1; m >= 0; m--) if (ins2[m] && h2[m] == h2[l]) { c2[l] = (int64_t)(p0 + m); break; }
+      }
+    }
+    // (inactive lanes only exist in the last window; lane 31's hash of a full window feeds the next window's lane 0)
+    prev_h1 = h1[31]; prev_h2 = h2[31];
+    for (int l = 0; l < 32; l++) if (act[l]) {
+      const uint32_t p = p0 + l;
+      if (ins1[l]) tab1[h1[l]] = (uint16_t)p;
+      if (ins2[l]) tab2[h2[l]] = (uint16_t)p;
+    }
+    for (int l = 0; l < 32; l++) if (act[l]) {
+      const uint32_t p = p0 + l;
+      const uint64_t v = read64(b, p, bn);
+      uint32_t off = 0, len = 0;
+      if (c2[l] >= 0 && read64(b, (uint32_t)c2[l], bn) == v) { off = p - (uint32_t)c2[l]; len = 8; }
+      else if (c1[l] >= 0) {
+        const uint32_t c = common8(v, read64(b, (uint32_t)c1[l], bn));
+        if (c >= ESD_MIN_MATCH) { off = p - (uint32_t)c1[l]; len = c; }
+      }
+      if (len == 8) {
+        while (len < ESD_LCAP && p + len < bn) {
+          uint32_t c = common8(read64(b, p + len, bn), read64(b, p + len - off, bn));
+          const uint32_t room = bn - (p + len);
+          if (c > room) c = room;
+          len += c;
+          if (c < 8) break;
+        }
+        if (len > ESD_LCAP) len = ESD_LCAP;
+      }
+      Roff[p] = off; Rlen[p] = len;
+    }
+  }
+  uint32_t ip = 0, anchor = 0, rep0 = rep[0];
+  while (ip < ilimit) {
+    uint32_t eq = 0, ok = 0, inb = 0;
+    for (int l = 0; l < 32; l++) {
+      const uint32_t p = ip + l;
+      if (rep0 && p >= rep0 && p < bn && b[p] == b[p - rep0]) eq |= 1u << l;
+      if (p < ilimit) { inb |= 1u << l; if (Roff[p]) ok |= 1u << l; }
+    }
+    const uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & inb;
+    const uint32_t cand = ok | rp;
+    if (!cand) { ip += 32; continue; }
+    int f = __builtin_ctz(cand);
+    auto replen = [&](int j) { const uint32_t m = ~(eq >> j); return m ? (uint32_t)__builtin_ctz(m) : 32u; };
+    bool use_rep = false;
+    if ((rp >> f) & 1) {
+      const uint32_t rl = replen(f);
+      if (!((ok >> f) & 1) || f + rl == 32 || rl + ESD_REP_BONUS >= Rlen[ip + f]) use_rep = true;
+    } else if (f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
+      const uint32_t rl = replen(f + 1);
+      if (f + 1 + rl == 32 || rl + ESD_REP_BONUS >= Rlen[ip + f]) { f = f + 1; use_rep = true; }
+    }
+    if (!use_rep && E.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && Rlen[ip + f + 1] > Rlen[ip + f]) f = f + 1;
+    uint32_t s = ip + f, off, len;
+    bool open;
+    if (use_rep) { len = replen(f); off = rep0; open = f + len == 32; }
+    else { off = Roff[s]; len = Rlen[s]; open = len == ESD_LCAP; }
+    if (open) while (s + len < bn && b[s + len] == b[s + len - off]) len++;
+    uint32_t nb = 0;
+    while (nb < 32 && s - nb > anchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
+    s -= nb; len += nb;
+    const uint32_t llen = s - anchor;
+    out.lits.insert(out.lits.end(), b + anchor, b + s);
+    out.ll.push_back(llen); out.ml.push_back(len);
+    out.ofv.push_back(offset_to_code(off, llen, rep));
+    ip = anchor = s + len; rep0 = off;
+  }
+  out.lits.insert(out.lits.end(), b + anchor, b + bn);
+}
+
 } // namespace
 
 extern "C" {
@@ -199,7 +310,8 @@ size_t model_compress(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, in
     }
     BlockOut B;
     uint32_t rep_save[3] = {rep[0], rep[1], rep[2]};
-    parse_block(src, (uint32_t)ip, bn, P, rep, B, MAX_SEQ_PER_BLOCK);
+    if (esd_level(P.level) && n <= BLOCK_BYTES) parse_block_esd(src, bn, esd_params_for_level(P.level), rep, B);
+    else parse_block(src, (uint32_t)ip, bn, P, rep, B, MAX_SEQ_PER_BLOCK);
     uint32_t payload = B.ll.size() >= MAX_SEQ_PER_BLOCK ? 0 : encode_block_payload(W, B.lits.data(), (uint32_t)B.lits.size(), B.ll.data(), B.ml.data(), B.ofv.data(), (uint32_t)B.ll.size(), tmp.data(), bn - 1);
     if (payload == 0 || payload >= bn) {
       rep[0] = rep_save[0]; rep[1] = rep_save[1]; rep[2] = rep_save[2];
