@@ -280,26 +280,26 @@ public:
   // ---- encoder placement: levels 1-4 run the decoupled pipeline (zstd_encode_esd.cu), the chain levels and items of
   // more than one block the general kernel (zstd_encode.cu) ----
   bool use_esd() const { return b200zstd::esd_level(std::max(cfg.level, 1)); }
-  static size_t lists_bytes(size_t n) { return align_up(n * 8, 256); }
-  size_t enc_scratch_bytes(size_t n) const {
+  // slot geometry of the levels 1-4 pipeline: 64 KB blocks when every item is known to fit, else 128 KB
+  static uint32_t esd_block_max(size_t max_item) { return (max_item == 0 || max_item > 65536) ? 131072u : 65536u; }
+  size_t lists_bytes(size_t n) const { return align_up(n * 8 + (use_esd() ? b200zstd::esd_counter_words(n, 131072u) * 4 : 0), 256); }
+  size_t enc_scratch_bytes(size_t n, uint32_t bm) const {
     const size_t general = b200zstd::encode_cta_scratch_bytes(enc_params());
-    if (use_esd()) {
-      const size_t a = std::min<size_t>(n, (size_t)sm_count * b200zstd::esd_ctas_per_sm(0)) * b200zstd::esd_cta_scratch_bytes(0);
-      const size_t b = std::min<size_t>(n, (size_t)sm_count * b200zstd::esd_ctas_per_sm(1)) * b200zstd::esd_cta_scratch_bytes(1);
-      return std::max(std::max(a, b), general);
-    }
+    if (use_esd()) return std::max(b200zstd::esd_scratch_bytes(n, bm, sm_count), general);
     return (size_t)enc_grid(n) * general;
   }
-  // a.counter / a.scratch are set here; w = workspace base (counters live in its header), lists = 2 n words
-  cudaError_t enqueue_encode(b200zstd::EncodeArgs &a, unsigned char *w, unsigned char *lists, unsigned char *scratch, size_t min_item,
-                             size_t max_item, cudaStream_t stream, int *launches) {
+  size_t enc_need(size_t n, uint32_t bm) const { return b200zstd::WS_HEADER_BYTES + table_bytes(n) + lists_bytes(n) + enc_scratch_bytes(n, bm); }
+  // a.counter / a.scratch are set here; w = workspace base, lists = 2 n words followed by the pipeline's counters
+  cudaError_t enqueue_encode(b200zstd::EncodeArgs &a, unsigned char *w, unsigned char *lists, unsigned char *scratch, size_t scratch_bytes,
+                             uint32_t bm, size_t min_item, size_t max_item, cudaStream_t stream, int *launches) {
     a.scratch = scratch;
     if (use_esd()) {
       b200zstd::EsdLaunch L{};
-      L.counters = reinterpret_cast<u32 *>(w + 128);
       L.lists = reinterpret_cast<u32 *>(lists);
-      L.scratch = scratch; L.scratch_bytes = enc_scratch_bytes(a.n);
-      L.sm_count = sm_count; L.min_item_bytes = min_item; L.max_item_bytes = max_item;
+      L.counters = L.lists + 2 * (size_t)a.n;
+      L.counter_words = b200zstd::esd_counter_words(a.n, 131072u);
+      L.scratch = scratch; L.scratch_bytes = scratch_bytes;
+      L.sm_count = sm_count; L.block_max = bm; L.min_item_bytes = min_item; L.max_item_bytes = max_item;
       return b200zstd::launch_encode_esd(a, L, stream, launches);
     }
     a.counter = reinterpret_cast<u32 *>(w);
@@ -333,10 +333,11 @@ public:
   }
   size_t enc_temp(size_t n, const size_t *sizes = nullptr) const {
     if (n == 0) return 0;
-    size_t e = b200zstd::WS_HEADER_BYTES + table_bytes(n) + lists_bytes(n) + enc_scratch_bytes(n);
+    size_t max_item = 0;
+    if (sizes) for (size_t i = 0; i < n; ++i) max_item = std::max(max_item, sizes[i]);
+    size_t e = enc_need(n, esd_block_max(max_item));
     // a compress workspace can always be reused for decompress (reference tests/test_c_api.cpp:62-64):
     // the decoder needs dec_fixed(); pool space beyond that only decides how many chunks take the fast path
-    (void)sizes;
     return std::max(e, dec_fixed(n) + wave_of(n) * (size_t)(64 * 1024));
   }
 
@@ -350,7 +351,7 @@ public:
   static size_t big_tables(size_t B) { return align_up(B * 44 + (B + 1) * 8, 256); }
   size_t big_temp(size_t n) const {
     const size_t B = big_blocks(n);
-    return b200zstd::WS_HEADER_BYTES + big_tables(B) + lists_bytes(B) + enc_scratch_bytes(B) + B * big_slot();
+    return b200zstd::WS_HEADER_BYTES + big_tables(B) + lists_bytes(B) + enc_scratch_bytes(B, 131072u) + B * big_slot();
   }
   // Enqueue only: nothing is synchronised.  The outcome {frame bytes, first failing block status} lands in the 16-byte
   // device mailbox at ws + 64 and, when h_result is given (pinned host memory), is copied there on the same stream.
@@ -372,7 +373,7 @@ public:
     unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
     unsigned char *lists = tab + big_tables(B);
     unsigned char *scratch = lists + lists_bytes(B);
-    unsigned char *slots = scratch + enc_scratch_bytes(B);
+    unsigned char *slots = scratch + enc_scratch_bytes(B, 131072u);
     std::vector<u64> host(4 * B);
     for (size_t i = 0; i < B; ++i) {
       host[i] = (u64)(uintptr_t)(static_cast<const unsigned char *>(d_src) + i * BIG_BLOCK);
@@ -392,7 +393,8 @@ public:
     a.statuses = d_status; a.counter = counter; a.n = (uint32_t)B; a.block_mode = 1; a.prm = enc_params();
     a.prm.checksum = 0;
     int enc_launches = 0;
-    if ((e = enqueue_encode(a, w, lists, scratch, n - (B - 1) * BIG_BLOCK, std::min(n, BIG_BLOCK), stream, &enc_launches)) != cudaSuccess) return cuda_fail(e, fn);
+    if ((e = enqueue_encode(a, w, lists, scratch, enc_scratch_bytes(B, 131072u), 131072u, n - (B - 1) * BIG_BLOCK, std::min(n, BIG_BLOCK), stream,
+                            &enc_launches)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = b200zstd::launch_scan_sizes(a.out_sizes, B, sizeof hdr, reinterpret_cast<uint64_t *>(d_offsets), stream)) != cudaSuccess) return cuda_fail(e, fn);
     if ((e = b200zstd::launch_pack(a.out_ptrs, a.out_sizes, reinterpret_cast<const uint64_t *>(d_offsets), B, d_dst, stream)) != cudaSuccess) return cuda_fail(e, fn);
     last_launches = 3 + enc_launches;
@@ -474,19 +476,23 @@ public:
     if (n == 0) return Status::SUCCESS;
     if (!in_ptrs || !in_sizes || !out_ptrs || !out_sizes) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null pointer table");
     if (n > 0xFFFFFFF0ull) return fail(Status::ERROR_INVALID_PARAMETER, fn, "too many chunks");
-    const size_t need = compress ? enc_temp(n) : dec_fixed(n);             // decode pools use whatever lies beyond the fixed part
-    if (!ws) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null workspace");
-    if (ws_bytes < need) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
-    unsigned char *w = static_cast<unsigned char *>(ws);
-    u32 *counter = reinterpret_cast<u32 *>(w);
-    unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
-    unsigned char *scratch = tab + table_bytes(n);
     size_t min_item = 0, max_item = 0;              // 0 / 0 = unknown (device-resident size table)
     if (compress && !tables_on_device) {
       min_item = ~(size_t)0;
       for (size_t i = 0; i < n; ++i) { min_item = std::min(min_item, in_sizes[i]); max_item = std::max(max_item, in_sizes[i]); }
       if (max_item == 0) max_item = 1;              // all-empty batch: every item is an error, any kernel reports it
     }
+    // levels 1-4: 128 KB slots unless every item is known to fit 64 KB -- or, with a device-resident size table, unless
+    // the workspace was sized for 64 KB chunks (anything larger then takes the general kernel)
+    uint32_t enc_bm = esd_block_max(max_item);
+    if (compress && tables_on_device && ws_bytes < enc_need(n, 131072u)) enc_bm = 65536u;
+    const size_t need = compress ? enc_need(n, enc_bm) : dec_fixed(n);     // decode pools use whatever lies beyond the fixed part
+    if (!ws) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null workspace");
+    if (ws_bytes < need) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    u32 *counter = reinterpret_cast<u32 *>(w);
+    unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
+    unsigned char *scratch = tab + table_bytes(n);
     const void *const *d_in = in_ptrs;
     const size_t *d_in_sz = in_sizes;
     void *const *d_out = out_ptrs;
@@ -510,7 +516,7 @@ public:
       b200zstd::EncodeArgs a{};
       a.in_ptrs = d_in; a.in_sizes = d_in_sz; a.out_ptrs = d_out; a.out_sizes = d_out_sz; a.statuses = d_status;
       a.counter = counter; a.n = (uint32_t)n; a.prm = enc_params();
-      e = enqueue_encode(a, w, scratch, scratch + lists_bytes(n), min_item, max_item, stream, &last_launches);
+      e = enqueue_encode(a, w, scratch, scratch + lists_bytes(n), enc_scratch_bytes(n, enc_bm), enc_bm, min_item, max_item, stream, &last_launches);
     } else {
       // fast path in waves of FAST_WAVE chunks (bounds the scratch); each wave is 4 launches:
       // prep, entropy, execute, and the general kernel for whatever the fast path declined
@@ -779,7 +785,8 @@ Status ZstdBatchManager::compress_async_no_sync(const void *src, size_t n, void 
   if (n == 0) return fail(Status::ERROR_INVALID_PARAMETER, fn, "zero-size input");
   Impl &I = *pimpl_;
   if (n > Impl::BIG_BLOCK) return I.compress_big_enqueue(src, n, dst, cap, ws, ws_bytes, stream, reinterpret_cast<u64 *>(result16));
-  if (ws_bytes < I.enc_temp(1)) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
+  const uint32_t bm = Impl::esd_block_max(n);
+  if (ws_bytes < I.enc_need(1, bm)) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace too small");
   std::lock_guard<std::mutex> lock(I.mu);
   unsigned char *w = static_cast<unsigned char *>(ws);
   unsigned char *tab = w + b200zstd::WS_HEADER_BYTES;
@@ -794,7 +801,7 @@ Status ZstdBatchManager::compress_async_no_sync(const void *src, size_t n, void 
   a.n = 1; a.prm = I.enc_params();
   int enc_launches = 0;
   unsigned char *lists = tab + Impl::table_bytes(1);
-  if ((e = I.enqueue_encode(a, w, lists, lists + Impl::lists_bytes(1), n, n, stream, &enc_launches)) != cudaSuccess) return cuda_fail(e, fn);
+  if ((e = I.enqueue_encode(a, w, lists, lists + I.lists_bytes(1), I.enc_scratch_bytes(1, bm), bm, n, n, stream, &enc_launches)) != cudaSuccess) return cuda_fail(e, fn);
   if ((e = b200zstd::launch_big_result(a.statuses, 1, reinterpret_cast<const uint64_t *>(tab + 24), 0, d_result, stream)) != cudaSuccess) return cuda_fail(e, fn);
   if ((e = cudaMemcpyAsync(result16, d_result, 16, cudaMemcpyDefault, stream)) != cudaSuccess) return cuda_fail(e, fn);
   I.last_launches = 1 + enc_launches;

@@ -97,15 +97,17 @@ cudaError_t launch_encode_batch_nomemset(const EncodeArgs &args, int grid, cudaS
 
 // ---- levels 1-4: the decoupled pipeline (zstd_encode_esd.cu) ----
 struct EsdLaunch {
-  uint32_t *counters;       // 8 words, zeroed by the launcher: work heads of the three kernels, list counts
+  uint32_t *counters;       // esd_counter_words() words, zeroed by the launcher: work heads and list counts per wave
+  size_t counter_words;
   uint32_t *lists;          // 2 * n words: items handed to the 128 KB-block kernel | to the general kernel
-  uint8_t *scratch;         // encode_esd_scratch_bytes()
+  uint8_t *scratch;         // esd_scratch_bytes(): the wave's sequence lists, then the finish kernel's per-warp buffers
   size_t scratch_bytes;
   int sm_count;
+  uint32_t block_max;       // 65536: every item above 64 KB takes the general kernel; 131072: blocks up to 128 KB are parsed here
   size_t min_item_bytes, max_item_bytes;    // 0 / 0: unknown (size table lives on the device)
 };
-size_t esd_cta_scratch_bytes(int big);
-int esd_ctas_per_sm(int big);
+size_t esd_scratch_bytes(size_t n_items, uint32_t block_max, int sm_count);
+size_t esd_counter_words(size_t n_items, uint32_t block_max);
 cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaStream_t stream, int *launches);
 int encode_ctas_per_sm(const EncodeParams &prm);
 

@@ -182,10 +182,10 @@ void parse_block(const uint8_t *chunk, uint32_t blk_off, uint32_t bn, const Enco
 //                  inside the window) and measured table matches; first candidate wins (optionally displaced by its
 //                  right neighbour), open matches are finished, then extended backwards into pending literals.
 // ------------------------------------------------------------------------------------------------
-void parse_block_esd(const uint8_t *b, uint32_t bn, const EsdParams &E, uint32_t rep[3], BlockOut &out) {
+void parse_block_esd(const uint8_t *b, uint32_t bn, const EsdParams &EP, uint32_t rep[3], BlockOut &out) {
   const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
   std::vector<uint32_t> Roff((size_t)bn + 64, 0), Rlen((size_t)bn + 64, 0);
-  std::vector<uint16_t> tab1((size_t)1 << E.hash_log, 0), tab2(E.dfast ? (size_t)1 << E.long_log : 0, 0);
+  std::vector<uint16_t> tab1((size_t)1 << EP.hash_log, 0), tab2(EP.dfast ? (size_t)1 << EP.long_log : 0, 0);
   auto recon = [](uint32_t pos, uint16_t e) -> int64_t {
     int64_t c = (int64_t)((pos & ~0xFFFFu) | e);
     if (c >= (int64_t)pos) c -= 0x10000;
@@ -201,12 +201,12 @@ void parse_block_esd(const uint8_t *b, uint32_t bn, const EsdParams &E, uint32_t
       act[l] = p < ilimit; ins1[l] = ins2[l] = false; h1[l] = h2[l] = 0; c1[l] = c2[l] = -1;
       if (!act[l]) continue;
       const uint64_t v = read64(b, p, bn);
-      h1[l] = hash_short(v, E.hash_bytes, E.hash_log);
+      h1[l] = hash_short(v, EP.hash_bytes, EP.hash_log);
       c1[l] = recon(p, tab1[h1[l]]);
       ins1[l] = (l > 0 ? h1[l - 1] : prev_h1) != h1[l];
       for (int m = l - 1; m >= 0; m--) if (ins1[m] && h1[m] == h1[l]) { c1[l] = (int64_t)(p0 + m); break; }
-      if (E.dfast) {
-        h2[l] = hash_long(v, E.long_log);
+      if (EP.dfast) {
+        h2[l] = hash_long(v, EP.long_log);
         c2[l] = recon(p, tab2[h2[l]]);
         ins2[l] = (l > 0 ? h2[l - 1] : prev_h2) != h2[l];
         for (int m = l - 1; m >= 0; m--) if (ins2[m] && h2[m] == h2[l]) { c2[l] = (int64_t)(p0 + m); break; }
@@ -241,41 +241,50 @@ void parse_block_esd(const uint8_t *b, uint32_t bn, const EsdParams &E, uint32_t
       Roff[p] = off; Rlen[p] = len;
     }
   }
-  uint32_t ip = 0, anchor = 0, rep0 = rep[0];
-  while (ip < ilimit) {
-    uint32_t eq = 0, ok = 0, inb = 0;
-    for (int l = 0; l < 32; l++) {
-      const uint32_t p = ip + l;
-      if (rep0 && p >= rep0 && p < bn && b[p] == b[p - rep0]) eq |= 1u << l;
-      if (p < ilimit) { inb |= 1u << l; if (Roff[p]) ok |= 1u << l; }
+  // select stage: independent sub-segments of ESD_SUB positions
+  uint32_t anchor = 0;                                   // end of the last match anywhere in the block
+  for (uint32_t B = 0; B < ilimit; B += ESD_SUB) {
+    const uint32_t E = std::min(B + ESD_SUB, bn), lim = std::min(E, ilimit);
+    uint32_t rs[3] = {0, 0, 0};                          // repeat-offset history as the sub-segment knows it (0 = unknown)
+    if (B == 0) { rs[0] = rep[0]; rs[1] = rep[1]; rs[2] = rep[2]; }
+    uint32_t ip = B, lanchor = B, rep0 = rs[0];
+    while (ip < lim) {
+      uint32_t eq = 0, ok = 0, inb = 0;
+      for (int l = 0; l < 32; l++) {
+        const uint32_t p = ip + l;
+        if (rep0 && p >= rep0 && p < E && b[p] == b[p - rep0]) eq |= 1u << l;
+        if (p < lim && p + 4 <= E) { inb |= 1u << l; if (Roff[p]) ok |= 1u << l; }
+      }
+      const uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & inb;
+      const uint32_t cand = ok | rp;
+      if (!cand) { ip += 32; continue; }
+      int f = __builtin_ctz(cand);
+      auto replen = [&](int j) { const uint32_t m = ~(eq >> j); return m ? (uint32_t)__builtin_ctz(m) : 32u; };
+      auto rlen = [&](int j) { return ((inb >> j) & 1) ? Rlen[ip + j] : 0u; };
+      bool use_rep = false;
+      if ((rp >> f) & 1) {
+        const uint32_t rl = replen(f);
+        if (!((ok >> f) & 1) || f + rl == 32 || rl + ESD_REP_BONUS >= rlen(f)) use_rep = true;
+      } else if (f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
+        const uint32_t rl = replen(f + 1);
+        if (f + 1 + rl == 32 || rl + ESD_REP_BONUS >= rlen(f)) { f = f + 1; use_rep = true; }
+      }
+      if (!use_rep && EP.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && rlen(f + 1) > rlen(f)) f = f + 1;
+      uint32_t s = ip + f, off, len;
+      bool open;
+      if (use_rep) { len = replen(f); off = rep0; open = f + len == 32; }
+      else { off = Roff[s]; len = Rlen[s]; open = len == ESD_LCAP; }
+      if (open) while (s + len < E && b[s + len] == b[s + len - off]) len++;
+      if (s + len > E) len = E - s;
+      uint32_t nb = 0;
+      while (nb < 32 && s - nb > lanchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
+      s -= nb; len += nb;
+      out.lits.insert(out.lits.end(), b + anchor, b + s);
+      out.ll.push_back(s - anchor); out.ml.push_back(len);
+      out.ofv.push_back(offset_to_code(off, s - lanchor, rs));     // coded with the literal run the sub-segment sees
+      ip = lanchor = anchor = s + len; rep0 = off;
     }
-    const uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & inb;
-    const uint32_t cand = ok | rp;
-    if (!cand) { ip += 32; continue; }
-    int f = __builtin_ctz(cand);
-    auto replen = [&](int j) { const uint32_t m = ~(eq >> j); return m ? (uint32_t)__builtin_ctz(m) : 32u; };
-    bool use_rep = false;
-    if ((rp >> f) & 1) {
-      const uint32_t rl = replen(f);
-      if (!((ok >> f) & 1) || f + rl == 32 || rl + ESD_REP_BONUS >= Rlen[ip + f]) use_rep = true;
-    } else if (f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
-      const uint32_t rl = replen(f + 1);
-      if (f + 1 + rl == 32 || rl + ESD_REP_BONUS >= Rlen[ip + f]) { f = f + 1; use_rep = true; }
-    }
-    if (!use_rep && E.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && Rlen[ip + f + 1] > Rlen[ip + f]) f = f + 1;
-    uint32_t s = ip + f, off, len;
-    bool open;
-    if (use_rep) { len = replen(f); off = rep0; open = f + len == 32; }
-    else { off = Roff[s]; len = Rlen[s]; open = len == ESD_LCAP; }
-    if (open) while (s + len < bn && b[s + len] == b[s + len - off]) len++;
-    uint32_t nb = 0;
-    while (nb < 32 && s - nb > anchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
-    s -= nb; len += nb;
-    const uint32_t llen = s - anchor;
-    out.lits.insert(out.lits.end(), b + anchor, b + s);
-    out.ll.push_back(llen); out.ml.push_back(len);
-    out.ofv.push_back(offset_to_code(off, llen, rep));
-    ip = anchor = s + len; rep0 = off;
+    if (B == 0) { rep[0] = rs[0]; rep[1] = rs[1]; rep[2] = rs[2]; }
   }
   out.lits.insert(out.lits.end(), b + anchor, b + bn);
 }

@@ -97,49 +97,55 @@ static void parse_esd(const uint8_t *b, uint32_t bn, const Knobs &K, uint32_t re
       Roff[p] = off; Rlen[p] = len;
     }
   }
-  // ---- S stage ----
-  uint32_t ip = 0, anchor = 0, rep0 = rep[0];
-  auto emit = [&](uint32_t s, uint32_t len, uint32_t off) {
+  // ---- S stage: independent sub-segments of SUB positions (matches truncated at their end, repeat offsets unknown at their start) ----
+  const uint32_t SUB = (uint32_t)envi("SUB", 1 << 20);
+  uint32_t anchor = 0;
+  auto emit = [&](uint32_t s, uint32_t len, uint32_t off, uint32_t *rp3) {
     uint32_t ll = s - anchor;
     out.lits.insert(out.lits.end(), b + anchor, b + s);
     out.ll.push_back(ll); out.ml.push_back(len);
-    out.ofv.push_back(offset_to_code(off, ll, rep));
+    out.ofv.push_back(offset_to_code(off, ll, rp3));
   };
-  while (ip < ilimit) {
-    uint32_t eq = 0, ok = 0;
-    for (int l = 0; l < 32; l++) {
-      uint32_t p = ip + l;
-      if (rep0 && p >= rep0 && p < bn && b[p] == b[p - rep0]) eq |= 1u << l;
-      if (p < ilimit && Roff[p]) ok |= 1u << l;
+  for (uint32_t B = 0; B < ilimit; B += SUB) {
+    const uint32_t E = std::min(B + SUB, bn), lim = std::min(E, ilimit);
+    uint32_t rs[3] = {0, 0, 0};
+    if (B == 0) { rs[0] = rep[0]; rs[1] = rep[1]; rs[2] = rep[2]; }
+    uint32_t ip = B, rep0 = rs[0], lanchor = B;
+    while (ip < lim) {
+      uint32_t eq = 0, ok = 0, inb = 0;
+      for (int l = 0; l < 32; l++) {
+        uint32_t p = ip + l;
+        if (rep0 && p >= rep0 && p < E && b[p] == b[p - rep0]) eq |= 1u << l;
+        if (p < lim && p + 4 <= E) { inb |= 1u << l; if (Roff[p]) ok |= 1u << l; }
+      }
+      uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & inb;
+      uint32_t cand = ok | rp;
+      if (!cand) { ip += 32; continue; }
+      int f = __builtin_ctz(cand);
+      uint32_t off, len;
+      bool open;
+      auto replen = [&](int j) { uint32_t m = ~(eq >> j); return m ? (uint32_t)__builtin_ctz(m) : 32u; };
+      bool use_rep = false;
+      if ((rp >> f) & 1) {
+        uint32_t rl = replen(f);
+        if (!((ok >> f) & 1) || f + rl == 32 || rl + K.rep_bonus >= Rlen[ip + f]) use_rep = true;
+      } else if (K.rep_next && f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
+        uint32_t rl = replen(f + 1);
+        if (f + 1 + rl == 32 || rl + K.rep_bonus >= Rlen[ip + f]) { f = f + 1; use_rep = true; }
+      }
+      if (!use_rep && K.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && Rlen[ip + f + 1] > Rlen[ip + f]) f = f + 1;
+      uint32_t s = ip + f;
+      if (use_rep) { len = replen(f); off = rep0; open = f + len == 32; stats[0]++; }
+      else { off = Roff[s]; len = Rlen[s]; open = len == (uint32_t)K.lcap; stats[1]++; }
+      if (open) { while (s + len < E && b[s + len] == b[s + len - off]) len++; stats[2]++; }
+      if (s + len > E) len = E - s;
+      uint32_t nb = 0;
+      while (nb < (uint32_t)envi("NBMAX", 32) && s - nb > lanchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
+      s -= nb; len += nb;
+      emit(s, len, off, rs);
+      ip = lanchor = anchor = s + len; rep0 = off;
     }
-    uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3);
-    // rep starts must also be parse positions
-    for (int l = 0; l < 32; l++) if (ip + l >= ilimit) rp &= ~(1u << l);
-    uint32_t cand = ok | rp;
-    if (!cand) { ip += 32; continue; }
-    int f = __builtin_ctz(cand);
-    uint32_t off, len;
-    bool open;
-    auto replen = [&](int j, bool *op) { uint32_t m = ~(eq >> j); uint32_t n = m ? (uint32_t)__builtin_ctz(m) : 32u; if (n > 32u - j) n = 32u - j; *op = (j + n == 32); return n; };
-    bool use_rep = false;
-    if ((rp >> f) & 1) {
-      bool op; uint32_t rl = replen(f, &op);
-      if (!((ok >> f) & 1) || op || rl + K.rep_bonus >= Rlen[ip + f]) use_rep = true;
-    } else if (K.rep_next && f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
-      bool op; uint32_t rl = replen(f + 1, &op);
-      if (op || rl + K.rep_bonus >= Rlen[ip + f]) { f = f + 1; use_rep = true; }
-    }
-    if (!use_rep && K.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && Rlen[ip + f + 1] > Rlen[ip + f]) f = f + 1;
-    uint32_t s = ip + f;
-    if (use_rep) { bool op; len = replen(f, &op); off = rep0; open = op; stats[0]++; }
-    else { off = Roff[s]; len = Rlen[s]; open = len == (uint32_t)K.lcap; stats[1]++; }
-    if (open) { while (s + len < bn && b[s + len] == b[s + len - off]) len++; stats[2]++; }
-    // backward
-    uint32_t nb = 0;
-    while (nb < 32 && s - nb > anchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
-    s -= nb; len += nb;
-    emit(s, len, off);
-    ip = anchor = s + len; rep0 = off;
+    if (B == 0 && SUB >= bn) { rep[0] = rs[0]; rep[1] = rs[1]; rep[2] = rs[2]; }
   }
   out.lits.insert(out.lits.end(), b + anchor, b + bn);
 }

@@ -35,8 +35,8 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); codec.compress_chunks(dev, chunk, ws); e1.record(); torch.cuda.synchronize()
 lib.cuda_zstd_b200_esd_prof(buf, 0)
 v = list(buf)
-names = ["S total", "S waits V", "S waits buffer", "X busy", "H total", "H waits ring", "V total", "V waits H", "blocks", "load wait", "S steps",
-         "sequences", "X waits", "open extensions"]
+names = ["S busy", "S waits V", "block total", "finish busy", "H total", "H waits ring", "V total", "V waits H", "blocks", "load wait", "S steps",
+         "sequences", "H exact-path windows", "open extensions"]
 blocks = max(v[8], 1)
 print(f"ms {e0.elapsed_time(e1):.2f}  blocks {v[8]}")
 for i, nm in enumerate(names):
