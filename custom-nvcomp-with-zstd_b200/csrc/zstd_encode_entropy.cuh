@@ -12,8 +12,8 @@ using namespace enc;
 // ---------------------------------------------------------------------------------------------------
 // Entropy stage of one block, warp-parallel.  Produces exactly the bytes of enc::encode_block_payload
 // (the serial form the host model runs): histograms by shared-memory atomics across 32 lanes, the 4
-// Huffman streams on 4 lanes at offsets known from a bit-count pre-pass, the three FSE state chains on
-// 3 lanes (state bits parked in the spare high bits of the sequence arrays), and the interleaved
+// Huffman streams cut into one piece per lane at bit offsets known from a bit-count pre-pass, the three FSE state
+// chains on 3 lanes fed by shuffles (state bits parked in the spare high bits of the sequence arrays), and the interleaved
 // sequence bitstream assembled by all lanes: each lane packs a contiguous run of sequences into
 // 32-bit words at a bit offset known from a prefix sum (atomicOr only for the two words it shares).
 // The table builders (Huffman lengths, FSE normalisation / CTable) stay on lane 0.
@@ -36,7 +36,20 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
   if (nlit >= 64) {
     for (int i = lane; i < 256; i += 32) W.count[i] = 0;
     __syncwarp();
-    for (uint32_t i = lane; i < nlit; i += 32) atomicAdd(&W.count[lits[i]], 1u);
+    {
+      // four literals per lane and step through aligned 32-bit loads (lits is 4-byte aligned: the kernels' own buffer)
+      const uint32_t head = min(nlit, (uint32_t)((4 - ((uintptr_t)lits & 3)) & 3));
+      if ((uint32_t)lane < head) atomicAdd(&W.count[lits[lane]], 1u);
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(lits + head);
+      const uint32_t words = (nlit - head) >> 2;
+      for (uint32_t i = lane; i < words; i += 32) {
+        const uint32_t x = w[i];
+        atomicAdd(&W.count[x & 0xFF], 1u); atomicAdd(&W.count[(x >> 8) & 0xFF], 1u);
+        atomicAdd(&W.count[(x >> 16) & 0xFF], 1u); atomicAdd(&W.count[x >> 24], 1u);
+      }
+      const uint32_t done4 = head + (words << 2);
+      if (done4 + (uint32_t)lane < nlit) atomicAdd(&W.count[lits[done4 + lane]], 1u);
+    }
     __syncwarp();
     uint32_t ms = 0, mc = 0;
     for (int s = lane; s < 256; s += 32) { const uint32_t c = W.count[s]; if (c) ms = (uint32_t)s; mc = max(mc, c); }
@@ -75,14 +88,27 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
         uint32_t used = t;
         if (ok) {
           const uint32_t nstreams = single ? 1 : 4, seg = (nlit + 3) / 4;
-          // bit count of every stream -> byte sizes and offsets before any stream is written
-          uint32_t sz[4] = {0, 0, 0, 0};
-          for (uint32_t k = 0; k < nstreams; k++) {
-            const uint32_t b0 = single ? 0 : k * seg, cnt = single ? nlit : (k < 3 ? seg : nlit - 3 * seg);
-            uint32_t bits = 0;
-            for (uint32_t i = lane; i < cnt; i += 32) bits += W.hufc[lits[b0 + i]] >> 16;
-            sz[k] = (warp_sum_u32(bits) + 1 + 7) >> 3;           // + end mark, rounded up to bytes
+          // Every stream is cut into pieces, one per lane (8 lanes per stream, 32 for a single stream); a piece is a
+          // contiguous run of symbols.  A stream is written from its LAST symbol to its first, so a piece starts at the
+          // bit count of the pieces behind it: pass 1 counts bits, a suffix sum inside the stream's lane group gives
+          // every piece its bit offset and every stream its size, pass 2 writes.
+          const uint32_t per = 32 / nstreams;                       // lanes per stream
+          const uint32_t k = (uint32_t)lane / per, m = (uint32_t)lane % per;
+          const uint32_t b0 = single ? 0 : k * seg, cnt = single ? nlit : (k < 3 ? seg : nlit - 3 * seg);
+          const uint32_t piece = (cnt + per - 1) / per;
+          const uint32_t lo = min(cnt, m * piece), hi = min(cnt, lo + piece);
+          uint32_t bits = 0;
+          for (uint32_t i = lo; i < hi; i++) bits += W.hufc[lits[b0 + i]] >> 16;
+          // suffix sum over the lanes of my stream that hold later symbols (higher m)
+          uint32_t after = 0, total = bits;
+          for (uint32_t o = 1; o < per; o <<= 1) {
+            const uint32_t t = __shfl_down_sync(0xffffffffu, total, o);
+            if (m + o < per) total += t;
           }
+          after = total - bits;
+          const uint32_t stream_bits = __shfl_sync(0xffffffffu, total, (int)(k * per));
+          uint32_t sz[4];
+          for (uint32_t q = 0; q < 4; q++) sz[q] = q < nstreams ? (__shfl_sync(0xffffffffu, stream_bits, (int)(q * per)) + 1 + 7) >> 3 : 0u;
           uint32_t off[4] = {0, 0, 0, 0};
           if (single) {
             if (sz[0] > budget - used) ok = false; else { off[0] = used; used += sz[0]; }
@@ -91,23 +117,54 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
             else {
               const uint32_t jt = used;
               used += 6;
-              for (int k = 0; k < 4 && ok; k++) {
-                if (sz[k] > budget - used || sz[k] > 0xFFFF) { ok = false; break; }
-                off[k] = used;
-                used += sz[k];
+              for (int q = 0; q < 4 && ok; q++) {
+                if (sz[q] > budget - used || sz[q] > 0xFFFF) { ok = false; break; }
+                off[q] = used;
+                used += sz[q];
               }
               if (ok && lane == 0)
-                for (int k = 0; k < 3; k++) { body[jt + 2 * k] = (uint8_t)sz[k]; body[jt + 2 * k + 1] = (uint8_t)(sz[k] >> 8); }
+                for (int q = 0; q < 3; q++) { body[jt + 2 * q] = (uint8_t)sz[q]; body[jt + 2 * q + 1] = (uint8_t)(sz[q] >> 8); }
             }
           }
-          if (ok && (uint32_t)lane < nstreams) {
-            const uint32_t k = (uint32_t)lane;
-            const uint32_t b0 = single ? 0 : k * seg, cnt = single ? nlit : (k < 3 ? seg : nlit - 3 * seg);
-            const uint32_t s0 = k == 0 ? sz[0] : k == 1 ? sz[1] : k == 2 ? sz[2] : sz[3];
+          if (ok) {
+            // zero the words the streams cover (not the bytes before them in the first word), then OR / store the pieces
+            uint8_t *const sp = body + off[0];
+            const uint32_t span_bytes = (single ? sz[0] : off[3] + sz[3] - off[0]);
+            uint32_t *const w32 = reinterpret_cast<uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
+            const uint32_t lead = (uint32_t)((uintptr_t)sp & 3);
+            {
+              const uint32_t last_word = (lead + span_bytes - 1) >> 2;
+              const uint32_t headb = (4 - lead) & 3;
+              if ((uint32_t)lane < min(headb, span_bytes)) sp[lane] = 0;
+              uint32_t *z = w32 + (lead ? 1 : 0);
+              const uint32_t words = lead ? last_word : last_word + 1;
+              for (uint32_t i = lane; i < words; i += 32) z[i] = 0;
+            }
+            __syncwarp();
             const uint32_t o0 = k == 0 ? off[0] : k == 1 ? off[1] : k == 2 ? off[2] : off[3];
-            huf_encode_stream(lits + b0, cnt, W.hufc, body + o0, s0);
+            uint32_t bitpos = (lead + (o0 - off[0])) * 8 + after;
+            uint32_t wi = bitpos >> 5, nacc = bitpos & 31;
+            uint64_t acc = 0;
+            bool first = true;
+            if (k < nstreams) {
+              for (uint32_t i = hi; i > lo; i--) {
+                const uint32_t c = W.hufc[lits[b0 + i - 1]];
+                acc |= (uint64_t)(c & 0xFFFF) << nacc;
+                nacc += c >> 16;
+                if (nacc >= 32) {
+                  if (first) { atomicOr(w32 + wi, (uint32_t)acc); first = false; } else w32[wi] = (uint32_t)acc;
+                  wi++; acc >>= 32; nacc -= 32;
+                }
+              }
+              if (m == 0) { acc |= 1ull << nacc; nacc++; }           // end mark behind the stream's first symbol
+              if (nacc >= 32) {
+                if (first) { atomicOr(w32 + wi, (uint32_t)acc); first = false; } else w32[wi] = (uint32_t)acc;
+                wi++; acc >>= 32; nacc -= 32;
+              }
+              if (nacc > 0 && (uint32_t)acc != 0) atomicOr(w32 + wi, (uint32_t)acc);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (ok && used < budget) {
           if (lane == 0) write_lit_header_compressed(dst, hs, single, nlit, used);
@@ -156,27 +213,48 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
   if (lane == 0) dst[modes_pos] = (uint8_t)modes;
   // ---- the three FSE state chains, one lane each: state bits parked above the 18-bit values ----
   const int log_ll = W.tab_log[0], log_of = W.tab_log[1], log_ml = W.tab_log[2];
+  // Rounds of 32 sequences, last sequence first: every lane loads one sequence and computes its three codes; the codes
+  // are handed to the chain lanes (0: LL, 1: OF, 2: ML) one sequence at a time by shuffle, so the serial part of a step is
+  // two shared-memory lookups and no global access; what a chain emits for a sequence (bits | count << 9) comes back
+  // through W.count, which is free by now.
   uint32_t fin = 0;
-  if (lane < 3) {
-    const int t = lane;
+  {
+    const int t = lane < 3 ? lane : 0;
     const int log = W.tab_log[t];
     const uint16_t *st = W.state_tab(t);
     const SymTT *tt = W.tt[t];
-    uint32_t *arr = t == 0 ? sll : t == 1 ? sofv : sml;
+    uint32_t *const park = W.count;                    // [3][32]
     uint32_t state = 0;
-    if (log) {
-      for (uint32_t i = nseq; i-- > 0;) {
-        const uint32_t v = arr[i];
-        const uint32_t code = t == 0 ? ll_code(v) : t == 1 ? (uint32_t)hb32(v) : ml_code(v);
-        if (i == nseq - 1) state = fse_init_state(st, tt, code);
-        else {
-          const uint32_t nb = (uint32_t)((int32_t)state + tt[code].delta_nb) >> 16;
-          arr[i] = v | ((state & ((1u << nb) - 1u)) << 18) | (nb << 27);
-          state = st[(int32_t)(state >> nb) + tt[code].delta_state];
+    for (uint32_t base = 0; base < nseq; base += 32) {
+      const uint32_t kk = base + (uint32_t)lane;       // stream order: k = 0 is the last sequence
+      const bool valid = kk < nseq;
+      const uint32_t i = valid ? nseq - 1 - kk : 0;
+      uint32_t a = 0, b = 0, c = 1;
+      if (valid) { a = sll[i]; b = sml[i]; c = sofv[i]; }
+      const uint32_t pk = ll_code(a) | ((uint32_t)hb32(c) << 8) | (ml_code(valid ? b : 3u) << 16);
+      const uint32_t nv = min(32u, nseq - base);
+      for (uint32_t j = 0; j < nv; j++) {
+        const uint32_t x = __shfl_sync(0xffffffffu, pk, (int)j);
+        if (lane < 3 && log) {
+          const uint32_t code = (x >> (8 * t)) & 0xFF;
+          if (base + j == 0) state = fse_init_state(st, tt, code);
+          else {
+            const SymTT e = tt[code];
+            const uint32_t nb = (uint32_t)((int32_t)state + e.delta_nb) >> 16;
+            park[t * 32 + j] = (state & ((1u << nb) - 1u)) | (nb << 9);
+            state = st[(int32_t)(state >> nb) + e.delta_state];
+          }
         }
       }
+      __syncwarp();
+      if (valid && kk > 0) {
+        if (log_ll) { const uint32_t v = park[lane]; sll[i] = a | ((v & 0x1FF) << 18) | ((v >> 9) << 27); }
+        if (log_of) { const uint32_t v = park[32 + lane]; sofv[i] = c | ((v & 0x1FF) << 18) | ((v >> 9) << 27); }
+        if (log_ml) { const uint32_t v = park[64 + lane]; sml[i] = b | ((v & 0x1FF) << 18) | ((v >> 9) << 27); }
+      }
+      __syncwarp();
     }
-    fin = state;
+    if (lane < 3) fin = state;
   }
   const uint32_t fin_ll = __shfl_sync(0xffffffffu, fin, 0), fin_of = __shfl_sync(0xffffffffu, fin, 1), fin_ml = __shfl_sync(0xffffffffu, fin, 2);
   __syncwarp();

@@ -5,88 +5,56 @@
 // build_sequences_gpu_kernel (src/lz77_parallel.cu:26-268), compress_literals / compress_sequences
 // (manager.cu:4406-4484, 4864-4974), write_frame_header / write_block (:3998-4106, 4227-4286).
 //
-// Two kernels per wave of blocks.
+// Three kernels per wave of blocks, each of them data-parallel over the whole wave (zstd_encode_lz.cuh holds the
+// arithmetic of the first two, shared with the host-side model tests/model/enc_model.cpp; the bytes must agree):
 //
-// PARSE (zstd_encode_esd_kernel): one CTA per <= 128 KB block, the block resident in shared memory, specialised warps
-// running as a pipeline:
-//   load     the block arrives HBM -> shared memory by cp.async.bulk (TMA) copies completing on an mbarrier
-//   H warp   walks the block in fixed windows of 32 positions: hashes, reads the candidate position(s) from the
-//            shared-memory table(s), resolves equal hashes inside the window (match_any) and inserts -- the table
-//            state never depends on the parse, so this warp only waits for ring room
-//   V warps  take windows in turn: compare each position with its candidate(s) and measure the match up to 32 bytes
-//   S warps  the serial greedy parse, one SUB-SEGMENT of 1024 positions per warp at a time: 32 positions from the
-//            parse position per step, repeat-offset matches by a byte compare + ballot (exact lengths as a bit mask),
-//            measured table matches from the V warps, cooperative extension of the rare longer match, backward
-//            extension, repeat-offset coding.  Sub-segments are independent (a match ends at the sub-segment's end, the
-//            repeat-offset history is "unknown" at its start, which only ever costs a full offset code), so several S
-//            warps work on one block; all of them read candidates that H / V computed once, in block order.
-//   output   per sub-segment a list of {literal run, match length, offset code} in the wave's scratch in HBM
-// FINISH (zstd_encode_finish_kernel): one warp per block, many resident per SM: joins the lists (a sub-segment's
-// trailing literals go to the next sequence), gathers the literals from the input, runs the entropy stage
-// (zstd_encode_entropy.cuh) and writes the frame.
-//
-// A lone warp issues a dependent instruction every 5-10 cycles, so the per-sequence chain is kept short (no literal
-// copies) and four of them run per block; everything that can be computed per position is computed by the other
-// warps.  tests/model/enc_model.cpp (parse_block_esd) restates the stages on the host; the bytes must agree.
+// MATCH  (zstd_lz_match_kernel)   one CTA of 256 threads per <= 128 KB block.  The block arrives HBM -> shared memory by
+//        cp.async.bulk (TMA) copies completing on an mbarrier; the hash tables live in shared memory.  The block is
+//        walked in windows of 256 positions, one per thread: hash, look the candidates up in the state the windows
+//        before left behind, note "first position of this window with my hash" in a small side table (atomicMin on a
+//        window-tagged key), barrier, insert (highest position wins a bucket), barrier, verify the candidate against
+//        the staged block and measure the match up to 16 bytes.  R[p] = offset | length << 17 goes to the wave's scratch.
+//        Nothing in this kernel depends on the parse, so every position of every block is independent work.
+// SELECT (zstd_lz_select_kernel)  one warp per block, one lane per 1/32 of it: each lane walks its sub-segment greedily
+//        over R (repeat offsets, one-step lazy, extension of long matches), first speculatively from its first
+//        position, then again from the state the lane before it really ended in until the two walks meet; the rounds
+//        repeat until no lane's exit state changes.  The joined lists are exactly the serial walk of the whole block,
+//        repeat-offset codes included.
+// FINISH (zstd_lz_finish_kernel)  one warp per block: joins the lists, gathers the literals, runs the entropy stage
+//        (zstd_encode_entropy.cuh) and writes the frame (or the bare block in block mode).
 #include "zstd_common.cuh"
 #include "zstd_device_api.h"
 #include "zstd_encode_core.cuh"
 #include "zstd_encode_entropy.cuh"
+#include "zstd_encode_lz.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace b200zstd {
 
 using namespace enc;
+using namespace lz;
 
 namespace {
 
-constexpr int ESD_NV = 8;                       // verify warps (power of two)
-constexpr int ESD_NS = 4;                       // select warps
-constexpr int ESD_NSLOT = 5;                    // ring capacity in sub-segments: NS being parsed + one being filled
-// Warp roles by warp id.  The SM's schedulers favour the highest warp id among the eligible warps, so the serial chains
-// sit on top and the warps with slack at the bottom.
-constexpr int ESD_W_V0 = 0;
-constexpr int ESD_W_S0 = ESD_NV;
-constexpr int ESD_W_H = ESD_NV + ESD_NS;        // every other warp waits for these two (one per table): top priority
-constexpr int ESD_WARPS = ESD_NV + ESD_NS + 2;
-constexpr int ESD_THREADS = 32 * ESD_WARPS;
-constexpr uint32_t ESD_SUB_WINDOWS = ESD_SUB / 32;
-constexpr uint32_t ESD_SUB_SEQ = ESD_SUB / 4;   // every sequence covers >= 4 positions of its sub-segment
-constexpr uint32_t ESD_RING_POS = ESD_NSLOT * ESD_SUB;
-constexpr uint32_t ESD_IN_PAD = 64;             // 16 bytes of alignment slack in front, read-ahead room behind
-constexpr uint32_t ESD_KIND_PARSED = 0, ESD_KIND_RLE = 1, ESD_KIND_SKIP = 2;
+constexpr int MATCH_THREADS = (int)LZ_WIN;
+constexpr uint32_t LZ_IN_PAD = 64;               // 16 bytes of alignment slack in front, read-ahead room behind
+constexpr uint32_t KIND_PARSED = 0, KIND_RLE = 1, KIND_SKIP = 2;
 
-// ---- optional cycle accounting per warp role (build with -DESD_PROF; tools/esd_prof.py reads it) ----
-#ifdef ESD_PROF
-__device__ unsigned long long g_esd_prof[16];
-#define PROF_T0(v) const long long v = clock64()
-#define PROF_ADD(slot, v) do { if (lane == 0) atomicAdd(&g_esd_prof[slot], (unsigned long long)(v)); } while (0)
-#define PROF_SINCE(slot, v) PROF_ADD(slot, clock64() - (v))
-#else
-#define PROF_T0(v) do { } while (0)
-#define PROF_ADD(slot, v) do { } while (0)
-#define PROF_SINCE(slot, v) do { } while (0)
-#endif
-// slots: 0 S busy (summed over sub-segments), 1 S waits for V, 2 block total (CTA), 3 finish busy, 4 H total, 5 H waits for ring room,
-//        6 V total, 7 V waits for H, 8 blocks, 9 load wait, 10 S steps, 11 sequences, 13 S open extensions
+// ---- scratch slot of one block: [BlockHdr 16 B | 32 x LaneHdr | R: uint32 x block_max | spec lists | prefix lists] ----
+struct BlockHdr { uint32_t kind, pad0, pad1, pad2; };
+struct LaneHdr { uint16_t spec_cnt, sync_k, pre_cnt, pad; };
+__host__ __device__ constexpr size_t slot_r_off() { return 16 + LZ_LANES * sizeof(LaneHdr); }
+__host__ __device__ constexpr size_t slot_spec_off(uint32_t bm) { return slot_r_off() + (size_t)bm * 4; }
+__host__ __device__ constexpr size_t slot_lists_bytes(uint32_t bm) { return (size_t)LZ_LANES * ((bm / LZ_LANES + 4) / 4 + 8) * sizeof(Seq); }
+__host__ __device__ constexpr size_t slot_pre_off(uint32_t bm) { return slot_spec_off(bm) + slot_lists_bytes(bm); }
+__host__ __device__ constexpr size_t slot_bytes_of(uint32_t bm) { return (slot_pre_off(bm) + slot_lists_bytes(bm) + 255) & ~(size_t)255; }
 
-// per-block record in the wave's scratch: header, then the sub-segment lists
-struct EsdBlockHdr { uint32_t kind, nsub, pad0, pad1; };
-// scratch slot of one block: [EsdBlockHdr | nsub_max x {uint16 count, uint16 tail} | nsub_max x ESD_SUB_SEQ x uint2]
-__host__ __device__ constexpr uint32_t esd_nsub_max(uint32_t block_max) { return block_max / ESD_SUB; }
-__host__ __device__ constexpr size_t esd_slot_bytes(uint32_t block_max) {
-  return 16 + (size_t)esd_nsub_max(block_max) * 4 + (size_t)esd_nsub_max(block_max) * ESD_SUB_SEQ * 8;
-}
-
-struct EsdCtl {
+struct MatchCtl {
   unsigned long long mbar;
-  volatile uint32_t h_done[2];              // windows hashed, per table
-  uint32_t item;                            // broadcast of the work-queue draw
+  uint32_t item;
   uint32_t pad;
-  volatile uint32_t v_done[ESD_NV];         // per V warp: the next window it will publish
-  volatile uint32_t s_done[ESD_NS];         // per S warp: sub-segments finished
-  uint32_t flag;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,7 +76,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void cc_barrier() { asm volatile("" ::: "memory"); }
 
 // 8 bytes at byte offset `at` of the staged block (three aligned shared-memory words and two funnel shifts)
 __device__ __forceinline__ uint64_t lds64(const uint8_t *base16, uint32_t at) {
@@ -117,16 +84,17 @@ __device__ __forceinline__ uint64_t lds64(const uint8_t *base16, uint32_t at) {
   const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
   return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 }
-__device__ __forceinline__ uint32_t common8(uint64_t a, uint64_t b) {
-  const uint32_t xl = (uint32_t)a ^ (uint32_t)b, xh = (uint32_t)(a >> 32) ^ (uint32_t)(b >> 32);
-  if (xl) return (uint32_t)(__ffs((int)xl) - 1) >> 3;
-  if (xh) return 4u + ((uint32_t)(__ffs((int)xh) - 1) >> 3);
-  return 8u;
+
+// "highest position wins": uint16 buckets (blocks <= 64 KB) take a compare-and-swap loop, uint32 buckets atomicMax
+__device__ __forceinline__ void bucket_max(uint16_t *b, uint32_t p) {
+  uint16_t old = *b;
+  while (old < p) {
+    const uint16_t seen = atomicCAS(b, old, (uint16_t)p);
+    if (seen == old) break;
+    old = seen;
+  }
 }
-__device__ __forceinline__ uint32_t ones_from(uint32_t m, uint32_t j) {          // length of the run of 1 bits of m starting at bit j
-  const uint32_t z = ~(m >> j);
-  return z ? (uint32_t)(__ffs((int)z) - 1) : 32u;
-}
+__device__ __forceinline__ void bucket_max(uint32_t *b, uint32_t p) { atomicMax(b, p); }
 
 struct EsdArgs {
   EncodeArgs A;
@@ -141,23 +109,24 @@ struct EsdArgs {
   uint8_t *slots;                // wave_n x slot_bytes
   uint32_t slot_bytes, slot_block_max;
   uint32_t wave_base, wave_n;
-  uint32_t dbg;                  // ESD_PROF builds: 1 = V warps publish without working, 2 = S warps skip their sub-segments
 };
 
 template <int DFAST, int BIG>
-__global__ void __launch_bounds__(ESD_THREADS, BIG ? 1 : 2) zstd_encode_esd_kernel(EsdArgs K) {
+__global__ void __launch_bounds__(MATCH_THREADS, BIG ? 1 : 2) zstd_lz_match_kernel(EsdArgs K) {
+  using Bucket = typename std::conditional<BIG != 0, uint32_t, uint16_t>::type;
   constexpr uint32_t block_max = BIG ? 131072u : 65536u;
   extern __shared__ __align__(128) uint8_t smem[];
-  EsdCtl *const ctl = reinterpret_cast<EsdCtl *>(smem);
+  MatchCtl *const ctl = reinterpret_cast<MatchCtl *>(smem);
   uint8_t *const in_base = smem + 128;                                         // 16-byte aligned
-  uint16_t *const tab1 = reinterpret_cast<uint16_t *>(in_base + block_max + ESD_IN_PAD);
-  uint16_t *const tab2 = tab1 + ((size_t)1 << K.E.hash_log);
-  uint32_t *const ring = reinterpret_cast<uint32_t *>(tab2 + (DFAST ? ((size_t)1 << K.E.long_log) : 0));
+  Bucket *const tab1 = reinterpret_cast<Bucket *>(in_base + block_max + LZ_IN_PAD);
+  Bucket *const tab2 = tab1 + ((size_t)1 << K.E.hash_log);
+  uint32_t *const first1 = reinterpret_cast<uint32_t *>(tab2 + (DFAST ? ((size_t)1 << K.E.long_log) : 0));
+  uint32_t *const first2 = first1 + (1u << LZ_FIRST_LOG);
 
-  // (the warp id is broadcast from lane 0 so that the compiler treats the role branches as warp-uniform)
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int tid = threadIdx.x, lane = tid & 31;
   const EncodeArgs &A = K.A;
   const bool blocks_only = A.block_mode != 0;
+  const int hash_log = K.E.hash_log, long_log = K.E.long_log, hash_bytes = K.E.hash_bytes;
 
   if (tid == 0) mbar_init(&ctl->mbar, 1);
   __syncthreads();
@@ -174,9 +143,8 @@ __global__ void __launch_bounds__(ESD_THREADS, BIG ? 1 : 2) zstd_encode_esd_kern
     __syncthreads();
     const uint32_t item = ctl->item;
     if (item == 0xFFFFFFFFu) break;
-    PROF_T0(tb0);
     uint8_t *const slot = K.slots + (size_t)(item - K.wave_base) * K.slot_bytes;
-    EsdBlockHdr *const hdr = reinterpret_cast<EsdBlockHdr *>(slot);
+    BlockHdr *const hdr = reinterpret_cast<BlockHdr *>(slot);
     const uint8_t *const chunk = (const uint8_t *)A.in_ptrs[item];
     const size_t n = A.in_sizes[item];
     uint8_t *const dst = (uint8_t *)A.out_ptrs[item];
@@ -195,10 +163,10 @@ __global__ void __launch_bounds__(ESD_THREADS, BIG ? 1 : 2) zstd_encode_esd_kern
         if (status != ST_OK) {
           A.out_sizes[item] = 0;
           if (A.statuses) A.statuses[item] = status;
-          hdr->kind = ESD_KIND_SKIP;
+          hdr->kind = KIND_SKIP;
         } else if (n > K.slot_block_max) {
           K.big_list[atomicAdd(K.big_count, 1u)] = item;            // multi-block (or, for 64 KB slots, > 64 KB) item: the general kernel takes it
-          hdr->kind = ESD_KIND_SKIP;
+          hdr->kind = KIND_SKIP;
         } else K.defer_list[atomicAdd(K.defer_count, 1u)] = item;   // the 128 KB geometry writes this slot later
       }
       __syncthreads();
@@ -206,7 +174,6 @@ __global__ void __launch_bounds__(ESD_THREADS, BIG ? 1 : 2) zstd_encode_esd_kern
     }
     const uint32_t bn = (uint32_t)n;
     const uint32_t delta = (uint32_t)((uintptr_t)chunk & 15);
-    const uint8_t *const in = in_base + delta;                              // block byte i lives at in[i]
     // ---- load: HBM -> shared memory by bulk async copies; tables are cleared while the copy is in flight ----
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -214,19 +181,16 @@ __global__ void __launch_bounds__(ESD_THREADS, BIG ? 1 : 2) zstd_encode_esd_kern
       mbar_arrive_tx(&ctl->mbar, total);
       const uint8_t *src = chunk - delta;
       for (uint32_t o = 0; o < total; o += 16384u) bulk_g2s(in_base + o, src + o, min(16384u, total - o), &ctl->mbar);
-      ctl->h_done[0] = 0; ctl->h_done[1] = 0;
-      for (int j = 0; j < ESD_NV; j++) ctl->v_done[j] = (uint32_t)j;
-      for (int j = 0; j < ESD_NS; j++) ctl->s_done[j] = 0;
     }
     {
       uint4 *z = reinterpret_cast<uint4 *>(tab1);
-      const uint32_t vecs = (uint32_t)((((size_t)2 << K.E.hash_log) + (DFAST ? ((size_t)2 << K.E.long_log) : 0)) >> 4);
-      for (uint32_t i = tid; i < vecs; i += ESD_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      const uint32_t vecs = (uint32_t)((sizeof(Bucket) << hash_log) + (DFAST ? (sizeof(Bucket) << long_log) : 0)) >> 4;
+      for (uint32_t i = tid; i < vecs; i += MATCH_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = tid; i < (2u << LZ_FIRST_LOG); i += MATCH_THREADS) first1[i] = 0xFFFFFFFFu;
     }
-    PROF_T0(tl0);
     mbar_wait(&ctl->mbar, phase);
     phase ^= 1;
-    if (warp == 0) PROF_SINCE(9, tl0);
+    const uint8_t *const in = in_base + delta;                              // block byte i lives at in[i]
     // ---- RLE block? (decided on the first 32 bytes in the common case) ----
     bool rle = false;
     {
@@ -234,237 +198,121 @@ __global__ void __launch_bounds__(ESD_THREADS, BIG ? 1 : 2) zstd_encode_esd_kern
       bool same = true;
       if ((uint32_t)tid < min(bn, 32u)) same = in[tid] == b0;
       if (__syncthreads_and(same)) {
-        for (uint32_t i = tid; i < bn && same; i += ESD_THREADS) same = in[i] == b0;
+        for (uint32_t i = tid; i < bn && same; i += MATCH_THREADS) same = in[i] == b0;
         rle = __syncthreads_and(same) && bn > 1;
       }
     }
-    __syncthreads();                                                       // tables cleared, control words set
-    const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
-    const uint32_t nwin = rle ? 0 : (ilimit + 31) >> 5;
-    const uint32_t nsub = rle ? 0 : (ilimit + ESD_SUB - 1) / ESD_SUB;
-    if (tid == 0) { hdr->kind = rle ? ESD_KIND_RLE : ESD_KIND_PARSED; hdr->nsub = nsub; }
-    uint16_t *const sub_hdr = reinterpret_cast<uint16_t *>(slot + 16);
-    uint2 *const lists = reinterpret_cast<uint2 *>(slot + 16 + (size_t)esd_nsub_max(K.slot_block_max) * 4);
-
-    if (warp >= ESD_W_H) {
-      // ============================ H warps: one per table (the second only for DFAST) ============================
-      // Sequential semantics inside a window ("nearest lower inserting lane with my hash", "highest inserting lane
-      // writes") need to know which lanes share a hash.  MATCH.ANY answers that but takes ~300 cycles on this part, so:
-      // the inserting lanes store, every lane reads its bucket back, and a lane that does not find what it expects (its
-      // own position if it inserted, the old entry if not) has met another lane of the window in its bucket.  Each
-      // such bucket is then settled by one broadcast of its hash and a ballot.
-      const int T = warp - ESD_W_H;                                       // 0: primary table, 1: long table
-      if (T == 0 || DFAST) {
-        uint16_t *const tab = T ? tab2 : tab1;
-        uint16_t *const ring16 = reinterpret_cast<uint16_t *>(ring) + T;
-        uint32_t prev = 0xFFFFFFFFu;
-        const uint32_t lt = lanemask_lt();
-        PROF_T0(th0);
-        uint32_t slot_base = 0;
-        uint64_t v = (uint32_t)lane < ilimit ? lds64(in_base, delta + (uint32_t)lane) : 0ull;
-        for (uint32_t k = 0; k < nwin; k++) {
-          if ((k & (ESD_SUB_WINDOWS - 1)) == 0) {
-            const uint32_t j = k / ESD_SUB_WINDOWS;
-            slot_base = (j % ESD_NSLOT) * ESD_SUB;
-            if (j >= ESD_NSLOT) {                           // ring room: the sub-segment that held this slot must be parsed
-              const uint32_t o = j - ESD_NSLOT;
-              PROF_T0(th1);
-              while (ctl->s_done[o % ESD_NS] <= o / ESD_NS) __nanosleep(64);
-              if (T == 0) PROF_SINCE(5, th1);
-            }
-            cc_barrier();
-          }
-          const uint32_t p0 = k << 5, p = p0 + (uint32_t)lane;
-          const bool act = p < ilimit;
-          const uint32_t h = T ? hash_long(v, K.E.long_log) : hash_short(v, K.E.hash_bytes, K.E.hash_log);
-          v = p + 32 < ilimit ? lds64(in_base, delta + p + 32) : 0ull;     // next window's bytes, in flight during the table work
-          uint32_t e = act ? tab[h] : 0u;
-          uint32_t hp = __shfl_up_sync(0xffffffffu, h, 1);
-          if (lane == 0) hp = prev;
-          const bool ins = act && hp != h;
-          prev = __shfl_sync(0xffffffffu, h, 31);
-          __syncwarp();                                     // every lookup of the window precedes its inserts
-          if (ins) tab[h] = (uint16_t)p;
-          __syncwarp();
-          uint32_t cm = __ballot_sync(0xffffffffu, act && tab[h] != (ins ? (p & 0xFFFFu) : e));
-          if (cm) {
-            if (T == 0) PROF_ADD(12, 1);
-            const uint32_t insmask = __ballot_sync(0xffffffffu, ins);
-            do {
-              const uint32_t ht = __shfl_sync(0xffffffffu, h, __ffs((int)cm) - 1);
-              const bool mine = act && h == ht;
-              const uint32_t g = __ballot_sync(0xffffffffu, mine), gi = g & insmask;
-              if (mine) {
-                const uint32_t lower = gi & lt;
-                if (lower) e = (p0 + (uint32_t)(31 - __clz(lower))) & 0xFFFFu;
-                if (ins && (gi >> lane) == 1u) tab[h] = (uint16_t)p;
-              }
-              cm &= ~g;
-            } while (cm);
-          }
-          ring16[2 * (slot_base + (p & (ESD_SUB - 1)))] = (uint16_t)e;
-          __syncwarp();
-          cc_barrier();
-          if (lane == 0) ctl->h_done[T] = k + 1;
+    __syncthreads();                                                       // tables cleared
+    if (tid == 0) hdr->kind = rle ? KIND_RLE : KIND_PARSED;
+    if (!rle) {
+      const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
+      const uint32_t nwin = (ilimit + LZ_WIN - 1) / LZ_WIN;
+      uint32_t *const Rg = reinterpret_cast<uint32_t *>(slot + slot_r_off());
+      auto rd = [&](uint32_t q) { return lds64(in_base, delta + q); };
+      for (uint32_t w = 0; w < nwin; w++) {
+        const uint32_t p = w * LZ_WIN + (uint32_t)tid;
+        const bool act = p < ilimit;
+        const uint64_t v = act ? rd(p) : 0ull;
+        // phase 1: hashes, the state before this window, first-of-window side table
+        const uint32_t h1 = hash_short(v, hash_bytes, hash_log);
+        const uint32_t hp1 = __shfl_up_sync(0xffffffffu, h1, 1);
+        const bool ins1 = act && inserts((uint32_t)lane, h1, hp1);
+        const uint32_t e1 = act ? (uint32_t)tab1[h1] : 0u;
+        const uint32_t s1 = h1 >> (hash_log - LZ_FIRST_LOG);
+        if (ins1) atomicMin(&first1[s1], first_key(w, (uint32_t)tid, h1));
+        uint32_t h2 = 0, e2 = 0, s2 = 0;
+        bool ins2 = false;
+        if (DFAST) {
+          h2 = hash_long(v, long_log);
+          const uint32_t hp2 = __shfl_up_sync(0xffffffffu, h2, 1);
+          ins2 = act && inserts((uint32_t)lane, h2, hp2);
+          e2 = act ? (uint32_t)tab2[h2] : 0u;
+          s2 = h2 >> (long_log - LZ_FIRST_LOG);
+          if (ins2) atomicMin(&first2[s2], first_key(w, (uint32_t)tid, h2));
         }
-        if (T == 0) PROF_SINCE(4, th0);
-      }
-    } else if (warp < ESD_W_S0) {
-      // ======================================= V warps =======================================
-      const int jv = warp - ESD_W_V0;
-      PROF_T0(tv0);
-      for (uint32_t k = (uint32_t)jv; k < nwin; k += ESD_NV) {
-        PROF_T0(tv1);
-        while (ctl->h_done[0] <= k || (DFAST && ctl->h_done[1] <= k)) __nanosleep(32);
-        PROF_SINCE(7, tv1);
-        cc_barrier();
-        const uint32_t p = (k << 5) + (uint32_t)lane;
-        const uint32_t ri = ((k / ESD_SUB_WINDOWS) % ESD_NSLOT) * ESD_SUB + (p & (ESD_SUB - 1));
-        uint32_t res = 0;
-        if (p < ilimit && !(K.dbg & 1)) {
-          const uint32_t e = ring[ri];
-          const uint64_t v = lds64(in_base, delta + p);
-          int32_t c1 = (int32_t)((BIG ? (p & ~0xFFFFu) : 0u) | (e & 0xFFFFu));
-          if (c1 >= (int32_t)p) c1 -= 0x10000;
-          uint32_t off = 0, len = 0;
-          if (DFAST) {
-            int32_t c2 = (int32_t)((BIG ? (p & ~0xFFFFu) : 0u) | (e >> 16));
-            if (c2 >= (int32_t)p) c2 -= 0x10000;
-            if (c2 >= 0 && lds64(in_base, delta + (uint32_t)c2) == v) { off = p - (uint32_t)c2; len = 8; }
-          }
-          if (len == 0 && c1 >= 0) {
-            const uint32_t c = common8(v, lds64(in_base, delta + (uint32_t)c1));
-            if (c >= ESD_MIN_MATCH) { off = p - (uint32_t)c1; len = c; }
-          }
-          if (len == 8) {
-            while (len < ESD_LCAP && p + len < bn) {
-              uint32_t c = common8(lds64(in_base, delta + p + len), lds64(in_base, delta + p + len - off));
-              const uint32_t room = bn - (p + len);
-              if (c > room) c = room;
-              len += c;
-              if (c < 8) break;
-            }
-            if (len > ESD_LCAP) len = ESD_LCAP;
-          }
-          res = off | (len << 17);
+        __syncthreads();
+        // phase 2: inserts; the candidate is the first earlier position of this window with my hash, else the old entry
+        if (ins1) bucket_max(&tab1[h1], p);
+        int32_t a1 = first_candidate(first1[s1], w, (uint32_t)tid, h1), a2 = -1;
+        if (a1 < 0) a1 = e1 < p ? (int32_t)e1 : -1;
+        if (DFAST) {
+          if (ins2) bucket_max(&tab2[h2], p);
+          a2 = first_candidate(first2[s2], w, (uint32_t)tid, h2);
+          if (a2 < 0) a2 = e2 < p ? (int32_t)e2 : -1;
         }
-        ring[ri] = res;
-        __syncwarp();
-        cc_barrier();
-        if (lane == 0) ctl->v_done[jv] = k + ESD_NV;
-      }
-      PROF_SINCE(6, tv0);
-    } else {
-      // ======================================= S warps =======================================
-      const int ws = warp - ESD_W_S0;
-      for (uint32_t j = (uint32_t)ws; j < nsub; j += ESD_NS) {
-        PROF_T0(ts0);
-        long long waited = 0;
-        const uint32_t B = j * ESD_SUB, E = min(B + ESD_SUB, bn), lim = min(E, ilimit);
-        const uint32_t slot_base = (j % ESD_NSLOT) * ESD_SUB;
-        uint2 *const list = lists + (size_t)j * ESD_SUB_SEQ;
-        // a sub-segment parsed on its own does not know the repeat offsets the decoder will hold when it gets there:
-        // 0 = unknown, never matched against and never equal to a real offset, so its first sequences simply carry full
-        // offset codes (RFC 8878 3.1.1.5 lets any offset be written that way); the block's first sub-segment starts
-        // from the frame's initial history unless the block is itself encoded on its own (block mode)
-        uint32_t r0 = 0, r1 = 0, r2 = 0;
-        if (j == 0 && !(blocks_only && item != 0)) { r0 = 1; r1 = 4; r2 = 8; }
-        uint32_t ip = B, anchor = B, rep0 = r0, nseq = 0, ready_end = B;
-        while (ip < lim && !(K.dbg & 2)) {
-          const uint32_t need = min(ip + 32, lim);
-          if (ready_end < need) {
-            PROF_T0(ts2);
-            while (ready_end < need) {
-              const uint32_t kk = ready_end >> 5;
-              while (ctl->v_done[kk & (ESD_NV - 1)] <= kk) __nanosleep(20);
-              ready_end += 32;
-            }
-            cc_barrier();
-#ifdef ESD_PROF
-            waited += clock64() - ts2;
-#endif
-          }
-          PROF_ADD(10, 1);
-          const uint32_t p = ip + (uint32_t)lane;
-          const bool inb = p < lim && p + 4 <= E;
-          const uint32_t r = inb ? ring[slot_base + (p & (ESD_SUB - 1))] : 0u;
-          const bool e = rep0 != 0 && p >= rep0 && p < E && in[p] == in[p - rep0];
-          const uint32_t eq = __ballot_sync(0xffffffffu, e);
-          const uint32_t ok = __ballot_sync(0xffffffffu, r != 0);
-          const uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & __ballot_sync(0xffffffffu, inb);
-          const uint32_t cand = ok | rp;
-          if (cand == 0) { ip += 32; continue; }
-          uint32_t f = (uint32_t)__ffs((int)cand) - 1;
-          const uint32_t rlen = r >> 17;
-          const uint32_t len_f = __shfl_sync(0xffffffffu, rlen, f), len_g = __shfl_sync(0xffffffffu, rlen, (f + 1) & 31);
-          bool use_rep = false;
-          if ((rp >> f) & 1) {
-            const uint32_t rl = ones_from(eq, f);
-            if (!((ok >> f) & 1) || f + rl == 32 || rl + ESD_REP_BONUS >= len_f) use_rep = true;
-          } else if (f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
-            const uint32_t rl = ones_from(eq, f + 1);
-            if (f + 1 + rl == 32 || rl + ESD_REP_BONUS >= len_f) { f = f + 1; use_rep = true; }
-          }
-          uint32_t off, len;
-          bool open;
-          if (use_rep) { len = ones_from(eq, f); off = rep0; open = f + len == 32; }
-          else {
-            if (K.E.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && len_g > len_f) f = f + 1;
-            const uint32_t rf = __shfl_sync(0xffffffffu, r, f);
-            off = rf & 0x1FFFFu; len = rf >> 17; open = len == ESD_LCAP;
-          }
-          uint32_t s = ip + f;
-          if (open) {
-            PROF_ADD(13, 1);
-            for (;;) {
-              const uint32_t q = s + len + (uint32_t)lane;
-              const uint32_t m = __ballot_sync(0xffffffffu, q < E && in[q] == in[q - off]);
-              const uint32_t nn = ones_from(m, 0);
-              len += nn;
-              if (nn < 32) break;
-            }
-          }
-          if (s + len > E) len = E - s;
-          {
-            const uint32_t jb = (uint32_t)lane;
-            const bool mb = jb < s - anchor && s - 1 - jb >= off && in[s - 1 - jb] == in[s - 1 - jb - off];
-            const uint32_t nb = ones_from(__ballot_sync(0xffffffffu, mb), 0);
-            s -= nb; len += nb;
-          }
-          const uint32_t llen = s - anchor;
-          // repeat-offset code and history update (enc::offset_to_code, RFC 8878 3.1.2.5) without branches
-          uint32_t code;
-          {
-            const bool l0 = llen == 0;
-            const uint32_t ca = l0 ? r1 : r0, cb = l0 ? r2 : r1, cc = l0 ? (r0 > 1 ? r0 - 1 : 0u) : r2;
-            code = off == ca ? 1u : off == cb ? 2u : off == cc ? 3u : off + 3u;
-            const bool same = !l0 && off == r0;
-            const uint32_t n2 = same ? r2 : (off == r1 ? r2 : r1), n1 = same ? r1 : r0;
-            r2 = n2; r1 = n1; r0 = off;
-          }
-          if (lane == 0) list[nseq] = make_uint2(llen | (len << 12), code);
-          nseq++;
-          ip = anchor = s + len; rep0 = off;
-        }
-        if (lane == 0) { sub_hdr[2 * j] = (uint16_t)nseq; sub_hdr[2 * j + 1] = (uint16_t)(E - anchor); }
-        __syncwarp();
-        cc_barrier();
-        if (lane == 0) ctl->s_done[ws] = j / ESD_NS + 1;
-#ifdef ESD_PROF
-        PROF_ADD(0, clock64() - ts0 - waited);
-        PROF_ADD(1, waited);
-        PROF_ADD(11, nseq);
-#endif
+        __syncthreads();
+        if (act) Rg[p] = match_verify(rd, p, v, a2, a1, bn);
       }
     }
     __syncthreads();                              // every warp is done with the staged block and the tables
-    if (warp == 0) { PROF_SINCE(2, tb0); PROF_ADD(8, 1); }
   }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// FINISH: one warp per block.  Joins the sub-segment lists into the three sequence arrays, gathers the literals from
-// the input, codes the block and writes the frame (or the bare block in block mode).
+// SELECT: one warp per block, lane j walks sub-segment j.
+// -----------------------------------------------------------------------------------------------------------------
+constexpr int SEL_WARPS = 4;
+struct SelArgs {
+  EncodeArgs A;
+  uint8_t *slots;
+  uint32_t slot_bytes, slot_block_max;
+  uint32_t wave_base, wave_n;
+  int lazy;
+};
+__device__ __forceinline__ State shfl_up_state(const State &s) {
+  State r;
+  r.ip = __shfl_up_sync(0xffffffffu, s.ip, 1); r.anchor = __shfl_up_sync(0xffffffffu, s.anchor, 1);
+  r.r0 = __shfl_up_sync(0xffffffffu, s.r0, 1); r.r1 = __shfl_up_sync(0xffffffffu, s.r1, 1); r.r2 = __shfl_up_sync(0xffffffffu, s.r2, 1);
+  return r;
+}
+
+__global__ void __launch_bounds__(32 * SEL_WARPS) zstd_lz_select_kernel(SelArgs S) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t idx = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
+  if (idx >= S.wave_n) return;
+  const uint32_t item = S.wave_base + idx;
+  uint8_t *const slot = S.slots + (size_t)idx * S.slot_bytes;
+  if (reinterpret_cast<const BlockHdr *>(slot)->kind != KIND_PARSED) return;
+  const uint8_t *const in = (const uint8_t *)S.A.in_ptrs[item];
+  const uint32_t bn = (uint32_t)S.A.in_sizes[item];
+  const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
+  const uint32_t *const R = reinterpret_cast<const uint32_t *>(slot + slot_r_off());
+  const uint32_t cap = lane_list_cap(S.slot_block_max);
+  Seq *const spec = reinterpret_cast<Seq *>(slot + slot_spec_off(S.slot_block_max)) + (size_t)lane * cap;
+  Seq *const prefix = reinterpret_cast<Seq *>(slot + slot_pre_off(S.slot_block_max)) + (size_t)lane * cap;
+  const SelectParams SP{S.lazy};
+  const uint32_t span = lane_span(ilimit);
+  const uint32_t B = lane_begin((uint32_t)lane, span, ilimit), E = lane_begin((uint32_t)lane + 1, span, ilimit);
+  // the history a decoder holds at the start of the block: the format's initial one, unless the block is coded on its
+  // own inside a larger frame (block mode), where it is unknown (0 never matches and is never written as a repeat code)
+  State st{B, B, 0, 0, 0};
+  if (lane == 0 && !(S.A.block_mode != 0 && item != 0)) { st.r0 = 1; st.r1 = 4; st.r2 = 8; }
+  const State spec0 = st;
+  const uint32_t spec_cnt = select_walk(in, bn, R, E, SP, st, spec);
+  const State spec_exit = st;
+  State exit_state = st, entry_used = spec0;
+  uint32_t pre_cnt = 0, sync_k = 0;
+  __syncwarp();
+  for (;;) {
+    const State entry = shfl_up_state(exit_state);
+    bool changed = false;
+    if (lane > 0 && !entry.same(entry_used)) {
+      entry_used = entry;
+      State s2 = entry;
+      pre_cnt = select_rewalk(in, bn, R, E, SP, s2, spec, spec_cnt, spec0, spec_exit, prefix, &sync_k);
+      if (!s2.same(exit_state)) { exit_state = s2; changed = true; }
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, changed)) break;
+  }
+  LaneHdr h;
+  h.spec_cnt = (uint16_t)spec_cnt; h.sync_k = (uint16_t)sync_k; h.pre_cnt = (uint16_t)pre_cnt; h.pad = 0;
+  reinterpret_cast<LaneHdr *>(slot + 16)[lane] = h;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// FINISH: one warp per block.  Joins the lane lists into the three sequence arrays, gathers the literals from the
+// input, codes the block and writes the frame (or the bare block in block mode).
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int FIN_WARPS = 4;                     // warps per CTA (each with its own entropy workspace)
 struct FinArgs {
@@ -477,7 +325,12 @@ struct FinArgs {
 };
 __host__ __device__ constexpr size_t fin_warp_scratch(uint32_t block_max) { return ((size_t)block_max + 64 + (size_t)3 * (block_max / 4 + 64) * 4 + 255) & ~(size_t)255; }
 
-__global__ void __launch_bounds__(32 * FIN_WARPS) zstd_encode_finish_kernel(FinArgs F) {
+// copies n bytes src -> dst with the whole warp (dst and src are unrelated in alignment)
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+  for (uint32_t i = (uint32_t)lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(32 * FIN_WARPS, 8) zstd_lz_finish_kernel(FinArgs F) {
   __shared__ EntropyWs s_ws[FIN_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   EntropyWs &W = s_ws[warp];
@@ -490,7 +343,7 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) zstd_encode_finish_kernel(FinA
   uint32_t *const s_ll = reinterpret_cast<uint32_t *>(buf + F.slot_block_max + 64);
   uint32_t *const s_ml = s_ll + max_seq;
   uint32_t *const s_of = s_ml + max_seq;
-  const uint32_t nsub_max = esd_nsub_max(F.slot_block_max);
+  const uint32_t cap = lane_list_cap(F.slot_block_max);
   for (;;) {
     uint32_t idx = 0;
     if (lane == 0) idx = atomicAdd(F.work_head, 1u);
@@ -498,9 +351,8 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) zstd_encode_finish_kernel(FinA
     if (idx >= F.wave_n) break;
     const uint32_t item = F.wave_base + idx;
     const uint8_t *const slot = F.slots + (size_t)idx * F.slot_bytes;
-    const EsdBlockHdr H = *reinterpret_cast<const EsdBlockHdr *>(slot);
-    if (H.kind == ESD_KIND_SKIP) continue;
-    PROF_T0(tf0);
+    const uint32_t kind = reinterpret_cast<const BlockHdr *>(slot)->kind;
+    if (kind == KIND_SKIP) continue;
     const uint8_t *const chunk = (const uint8_t *)A.in_ptrs[item];
     const uint32_t bn = (uint32_t)A.in_sizes[item];
     uint8_t *const dst = (uint8_t *)A.out_ptrs[item];
@@ -510,45 +362,53 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) zstd_encode_finish_kernel(FinA
       if (lane == 0) op = write_frame_header(dst, bn, P.checksum != 0);
       op = __shfl_sync(0xffffffffu, (unsigned long long)op, 0);
     }
-    if (H.kind == ESD_KIND_RLE) {
+    if (kind == KIND_RLE) {
       if (lane == 0) { write_block_header(dst + op, last, 1, bn); dst[op + 3] = chunk[0]; }
       op += 4;
     } else {
-      // ---- join the lists; every sequence learns where its literal run starts in the block and in the literal buffer ----
-      const uint16_t *const sub_hdr = reinterpret_cast<const uint16_t *>(slot + 16);
-      const uint2 *const lists = reinterpret_cast<const uint2 *>(slot + 16 + (size_t)nsub_max * 4);
-      uint32_t nseq = 0, nlit = 0, pos = 0, carry = 0;          // pos: block position where the pending literal run starts
-      for (uint32_t j = 0; j < H.nsub; j++) {
-        const uint32_t cnt = sub_hdr[2 * j], tail = sub_hdr[2 * j + 1];
-        const uint2 *const list = lists + (size_t)j * ESD_SUB_SEQ;
+      // ---- join the lists: lane j contributed prefix[0 .. pre_cnt) then spec[sync_k .. spec_cnt) ----
+      const LaneHdr mine = reinterpret_cast<const LaneHdr *>(slot + 16)[lane];
+      const Seq *const spec_all = reinterpret_cast<const Seq *>(slot + slot_spec_off(F.slot_block_max));
+      const Seq *const pre_all = reinterpret_cast<const Seq *>(slot + slot_pre_off(F.slot_block_max));
+      uint32_t nseq = 0, nlit = 0, prev_end = 0;
+      for (int j = 0; j < 32; j++) {
+        const uint32_t pc = __shfl_sync(0xffffffffu, (uint32_t)mine.pre_cnt, j), sk = __shfl_sync(0xffffffffu, (uint32_t)mine.sync_k, j),
+                       sc = __shfl_sync(0xffffffffu, (uint32_t)mine.spec_cnt, j);
+        const uint32_t cnt = pc + (sc - sk);
+        const Seq *const pl = pre_all + (size_t)j * cap, *const sl = spec_all + (size_t)j * cap + sk;
         for (uint32_t b = 0; b < cnt; b += 32) {
           const uint32_t k = b + (uint32_t)lane;
-          uint32_t ll = 0, ml = 0, code = 0;
-          if (k < cnt) {
-            const uint2 q = list[k];
-            ll = q.x & 0xFFFu; ml = q.x >> 12; code = q.y;
-            if (k == 0) ll += carry;
+          const bool valid = k < cnt;
+          uint32_t s = 0, ml = 0, code = 0;
+          if (valid) {
+            const Seq q = k < pc ? pl[k] : sl[k - pc];
+            s = seq_start(q); ml = seq_len(q); code = seq_code(q);
           }
-          // inclusive prefix sums of ll and ll + ml over the 32 sequences of this round
-          uint32_t sl = ll, sb = ll + ml;
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t tl = __shfl_up_sync(0xffffffffu, sl, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-            if (lane >= o) { sl += tl; sb += tb; }
+          const uint32_t e = s + ml;
+          uint32_t pe = __shfl_up_sync(0xffffffffu, e, 1);
+          if (lane == 0) pe = prev_end;
+          const uint32_t ll = valid ? s - pe : 0u;
+          uint32_t sl_incl = ll;                       // inclusive prefix sum of the literal runs of this round
+          for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, sl_incl, o); if (lane >= o) sl_incl += t; }
+          const uint32_t my_lit = nlit + sl_incl - ll;
+          if (valid) { s_ll[nseq + lane] = ll; s_ml[nseq + lane] = ml; s_of[nseq + lane] = code; }
+          // literal runs: short ones by their own lane, long ones by the whole warp
+          if (valid && ll <= 8) for (uint32_t i = 0; i < ll; i++) lits[my_lit + i] = chunk[pe + i];
+          uint32_t big = __ballot_sync(0xffffffffu, valid && ll > 8);
+          while (big) {
+            const int src = __ffs((int)big) - 1;
+            big &= big - 1;
+            warp_copy_bytes(lits + __shfl_sync(0xffffffffu, my_lit, src), chunk + __shfl_sync(0xffffffffu, pe, src), __shfl_sync(0xffffffffu, ll, src), lane);
           }
-          const uint32_t my_lit = nlit + sl - ll, my_pos = pos + sb - (ll + ml);
-          if (k < cnt) {
-            s_ll[nseq + lane] = ll; s_ml[nseq + lane] = ml; s_of[nseq + lane] = code;
-            for (uint32_t i = 0; i < ll; i++) lits[my_lit + i] = chunk[my_pos + i];
-          }
-          nlit += __shfl_sync(0xffffffffu, sl, 31);
-          pos += __shfl_sync(0xffffffffu, sb, 31);
-          nseq += min(32u, cnt - b);
+          const uint32_t nv = min(32u, cnt - b);
+          nlit += __shfl_sync(0xffffffffu, sl_incl, 31);
+          prev_end = __shfl_sync(0xffffffffu, e, (int)nv - 1);
+          nseq += nv;
         }
-        carry = (cnt ? 0u : carry) + tail;
       }
       // literals after the last sequence (the whole block when nothing was parsed)
-      for (uint32_t i = pos + lane; i < bn; i += 32) lits[nlit + i - pos] = chunk[i];
-      nlit += bn - pos;
+      warp_copy_bytes(lits + nlit, chunk + prev_end, bn - prev_end, lane);
+      nlit += bn - prev_end;
       __syncwarp();
       const uint32_t payload = entropy_stage_warp(W, lits, nlit, s_ll, s_ml, s_of, nseq, dst + op + 3, bn - 1, lane);
       if (payload == 0 || payload >= bn) {
@@ -571,41 +431,33 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) zstd_encode_finish_kernel(FinA
       if (A.statuses) A.statuses[item] = ST_OK;
     }
     __syncwarp();
-    PROF_SINCE(3, tf0);
   }
 }
 
-size_t esd_smem_bytes(const EsdParams &e, int big) {
-  const size_t in = (big ? 131072u : 65536u) + ESD_IN_PAD;
-  const size_t tabs = ((size_t)2 << e.hash_log) + (e.dfast ? ((size_t)2 << e.long_log) : 0);
-  return 128 + in + tabs + (size_t)ESD_RING_POS * 4 + 16;
+size_t match_smem_bytes(const EsdParams &e, int big) {
+  const size_t in = (big ? 131072u : 65536u) + LZ_IN_PAD;
+  const size_t entry = big ? 4 : 2;
+  const size_t tabs = (entry << e.hash_log) + (e.dfast ? (entry << e.long_log) : 0);
+  return 128 + in + tabs + ((size_t)8 << LZ_FIRST_LOG);
 }
 
-template <int DFAST, int BIG> cudaError_t esd_launch_one(const EsdArgs &k, int grid, cudaStream_t stream) {
-  const size_t smem = esd_smem_bytes(k.E, BIG);
-  cudaError_t e = cudaFuncSetAttribute(zstd_encode_esd_kernel<DFAST, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int DFAST, int BIG> cudaError_t match_launch_one(const EsdArgs &k, int grid, cudaStream_t stream) {
+  const size_t smem = match_smem_bytes(k.E, BIG);
+  cudaError_t e = cudaFuncSetAttribute(zstd_lz_match_kernel<DFAST, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  zstd_encode_esd_kernel<DFAST, BIG><<<grid, ESD_THREADS, smem, stream>>>(k);
+  zstd_lz_match_kernel<DFAST, BIG><<<grid, MATCH_THREADS, smem, stream>>>(k);
   return cudaGetLastError();
 }
 
-constexpr int FIN_CTAS_PER_SM = 6;               // 24 finish warps per SM
+constexpr int FIN_CTAS_PER_SM = 8;               // 32 finish warps per SM
 
-// blocks per wave: bounds the list scratch (2 bytes per input byte of the wave)
-uint32_t esd_wave(size_t n, uint32_t block_max) { return (uint32_t)min(n, (size_t)(block_max > 65536 ? 8192 : 16384)); }
-size_t esd_slot_stride(uint32_t bm) { return (esd_slot_bytes(bm) + 255) & ~(size_t)255; }
+// blocks per wave: bounds the scratch (8 bytes per input byte of the wave)
+uint32_t esd_wave(size_t n, uint32_t block_max) { return (uint32_t)min(n, (size_t)(block_max > 65536 ? 4096 : 8192)); }
 
 } // namespace
 
-#ifdef ESD_PROF
-extern "C" void cuda_zstd_b200_esd_prof(unsigned long long *out16, int reset) {
-  cudaMemcpyFromSymbol(out16, g_esd_prof, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_esd_prof, z, sizeof z); }
-}
-#endif
-
 size_t esd_scratch_bytes(size_t n_items, uint32_t bm, int sm_count) {
-  const size_t lists = (size_t)esd_wave(n_items, bm) * esd_slot_stride(bm);
+  const size_t lists = (size_t)esd_wave(n_items, bm) * slot_bytes_of(bm);
   const size_t fin_warps = min((size_t)sm_count * FIN_CTAS_PER_SM * FIN_WARPS, ((n_items + FIN_WARPS - 1) / FIN_WARPS) * FIN_WARPS);
   return lists + fin_warps * fin_warp_scratch(bm);
 }
@@ -614,9 +466,9 @@ size_t esd_counter_words(size_t n_items, uint32_t bm) {
   return 4 * ((n_items + wave - 1) / wave) + 2;
 }
 
-// Levels 1-4.  Per wave: the 64 KB-block parse kernel (two CTAs per SM), the 128 KB-block parse kernel (one CTA per SM)
-// over what the first handed on, the finish kernel; after the last wave the general kernel (zstd_encode.cu) for
-// multi-block items.  max_item_bytes != 0 (the host knows the sizes) skips the launches that cannot have work.
+// Levels 1-4.  Per wave: the 64 KB-block match kernel (two CTAs per SM), the 128 KB-block match kernel (one CTA per SM)
+// over what the first handed on, the select kernel, the finish kernel; after the last wave the general kernel
+// (zstd_encode.cu) for multi-block items.  max_item_bytes != 0 (the host knows the sizes) skips the launches that cannot have work.
 cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaStream_t stream, int *launches) {
   if (launches) *launches = 0;
   if (args.n == 0) return cudaSuccess;
@@ -627,11 +479,11 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
   const bool any_big = !known || L.max_item_bytes > bm;
   const bool only_big = known && L.min_item_bytes > bm;
   const uint32_t wave = esd_wave(args.n, bm);
-  const uint32_t slot_bytes = (uint32_t)esd_slot_stride(bm);
+  const uint32_t slot_bytes = (uint32_t)slot_bytes_of(bm);
   const size_t lists_bytes = (size_t)wave * slot_bytes;
   if (L.scratch_bytes < esd_scratch_bytes(args.n, bm, L.sm_count)) return cudaErrorInvalidValue;
   const size_t nwaves = only_big ? 0 : (args.n + wave - 1) / wave;
-  // counters: per wave {parse64 head, parse128 head, finish head, defer count}; then general-kernel head and big count
+  // counters: per wave {match64 head, match128 head, finish head, defer count}; then general-kernel head and big count
   const size_t ctr_words = 4 * nwaves + 2;
   if (ctr_words > L.counter_words) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(L.counters, 0, ctr_words * sizeof(uint32_t), stream);
@@ -647,15 +499,12 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
     k.slots = L.scratch; k.slot_bytes = slot_bytes; k.slot_block_max = bm;
     k.wave_base = (uint32_t)(w * wave); k.wave_n = (uint32_t)min((size_t)wave, args.n - w * wave);
     k.big_list = list_big; k.big_count = big_count;
-#ifdef ESD_PROF
-    if (const char *d = getenv("ESD_DBG")) k.dbg = (uint32_t)atoi(d);
-#endif
     if (any64) {
       k.list = nullptr; k.list_count = nullptr;
       k.work_head = c + 0;
       k.defer_list = list128 + k.wave_base; k.defer_count = c + 3;
       const int grid = (int)min((size_t)k.wave_n, (size_t)L.sm_count * 2);
-      e = k.E.dfast ? esd_launch_one<1, 0>(k, grid, stream) : esd_launch_one<0, 0>(k, grid, stream);
+      e = k.E.dfast ? match_launch_one<1, 0>(k, grid, stream) : match_launch_one<0, 0>(k, grid, stream);
       if (e != cudaSuccess) return e;
       nl++;
     }
@@ -664,10 +513,18 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
       k.work_head = c + 1;
       k.defer_list = nullptr; k.defer_count = nullptr;
       const int grid = (int)min((size_t)k.wave_n, (size_t)L.sm_count);
-      e = k.E.dfast ? esd_launch_one<1, 1>(k, grid, stream) : esd_launch_one<0, 1>(k, grid, stream);
+      e = k.E.dfast ? match_launch_one<1, 1>(k, grid, stream) : match_launch_one<0, 1>(k, grid, stream);
       if (e != cudaSuccess) return e;
       nl++;
     }
+    SelArgs s{};
+    s.A = args;
+    s.slots = L.scratch; s.slot_bytes = slot_bytes; s.slot_block_max = bm;
+    s.wave_base = k.wave_base; s.wave_n = k.wave_n;
+    s.lazy = k.E.lazy;
+    zstd_lz_select_kernel<<<(k.wave_n + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, stream>>>(s);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    nl++;
     FinArgs f{};
     f.A = args;
     f.slots = L.scratch; f.slot_bytes = slot_bytes; f.slot_block_max = bm;
@@ -675,7 +532,7 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
     f.work_head = c + 2;
     f.scratch = L.scratch + lists_bytes;
     const int fgrid = (int)min((size_t)L.sm_count * FIN_CTAS_PER_SM, ((size_t)k.wave_n + FIN_WARPS - 1) / FIN_WARPS);
-    zstd_encode_finish_kernel<<<fgrid, 32 * FIN_WARPS, 0, stream>>>(f);
+    zstd_lz_finish_kernel<<<fgrid, 32 * FIN_WARPS, 0, stream>>>(f);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     nl++;
   }

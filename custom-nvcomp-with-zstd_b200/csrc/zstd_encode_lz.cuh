@@ -1,0 +1,253 @@
+// zstd_encode_lz.cuh -- the parse of levels 1-4 (zstd_encode_esd.cu), written as __host__ __device__ code: the SELECT
+// stage a lane runs on the GPU and the restatement of the MATCH stage that the host-side model runs
+// (tests/model/enc_model.cpp) are the same functions, so the two must produce the same sequences.
+//
+// Reference counterparts (behavioural spec only): find_matches_kernel / greedy parse, src/lz77_parallel.cu:26-268;
+// repeat-offset coding as RFC 8878 3.1.1.5 / 3.1.2.5.
+//
+// MATCH   every position p < n - 8 of a block looks its candidates up in hash tables that hold, per bucket, the highest
+//         position of all WINDOWS BEFORE p's own (LZ_WIN positions per window; lookup of a window, then insert of the
+//         window: "highest position wins" makes the insert order irrelevant) or, through a small side table, the first
+//         position of its own window with the same hash; verifies them and measures the match up to LZ_LCAP bytes:
+//         R[p] = offset | length << 17  (0: nothing).
+// SELECT  the greedy walk over R.  A block is cut into LZ_LANES sub-segments; lane j first walks its sub-segment as if
+//         the parse entered it at its first position with an unknown repeat-offset history (speculation), then re-walks
+//         from the state the lane before it really left behind until it meets its own speculative walk (same match end,
+//         same history) -- after that point the two walks are identical, so the speculative tail is kept.  The result is
+//         exactly the serial walk of the whole block; a lane whose exit state changed makes the next lane re-walk.
+#pragma once
+#include <stdint.h>
+
+#include "zstd_encode_core.cuh"
+#include "zstd_encode_params.h"
+
+namespace b200zstd {
+namespace lz {
+
+constexpr uint32_t LZ_WIN = 256;          // positions per match-stage window (= threads of the match CTA)
+constexpr uint32_t LZ_LANES = 32;         // sub-segments per block (= lanes of the select warp)
+constexpr uint32_t LZ_LCAP = 16;          // the match stage measures a match up to this length; the select stage finishes longer ones
+constexpr uint32_t LZ_MIN_MATCH = 5;      // shortest table match; repeat-offset matches need 4
+constexpr uint32_t LZ_REP_BONUS = 2;      // a repeat-offset match wins when its length + bonus reaches the table match
+constexpr uint32_t LZ_BACK_MAX = 8;       // backward extension into pending literals, bytes
+constexpr uint32_t LZ_OFF_MASK = (1u << 17) - 1;
+constexpr int LZ_FIRST_LOG = 9;           // slots of the "first position of this window" side table, per hash table
+
+// The side table that lets a position see the EARLIER positions of its own window: slot = top LZ_FIRST_LOG bits of the
+// hash; key = window tag | position inside the window | low hash bits, combined by atomicMin.  Tags fall from window
+// to window, so a slot never needs clearing and the smallest key of the current window is its first inserted position.
+ZHD uint32_t first_key(uint32_t window, uint32_t t, uint32_t h) { return ((~window & 0x1FFu) << 23) | (t << 15) | (h & 0x7FFFu); }
+// candidate from the side table for thread t of `window` (hash h), or -1
+ZHD int32_t first_candidate(uint32_t key, uint32_t window, uint32_t t, uint32_t h) {
+  const bool mine = (key >> 23) == (~window & 0x1FFu) && (key & 0x7FFFu) == (h & 0x7FFFu) && ((key >> 15) & 0xFFu) < t;
+  return mine ? (int32_t)(window * LZ_WIN + ((key >> 15) & 0xFFu)) : -1;
+}
+// a position enters the tables unless its hash equals that of the position before it inside its group of 32 (runs keep
+// their first position, so that a later occurrence of the run finds the aligned candidate)
+ZHD bool inserts(uint32_t p, uint32_t h, uint32_t h_prev) { return (p & 31u) == 0 || h != h_prev; }
+
+// ---- byte access.  `in` is the block (device: global memory, any alignment).  Only bytes [0, n) are ever read. ----
+ZHD uint32_t rd8(const uint8_t *in, uint32_t p) { return in[p]; }
+// 8 little-endian bytes at p; requires p + 8 <= n
+ZHD uint64_t rd64(const uint8_t *in, uint32_t p) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t a = (uintptr_t)(in + p);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3) * 8;
+  const uint32_t w0 = w[0], w1 = w[1];
+  if (sh == 0) return ((uint64_t)w1 << 32) | w0;
+  const uint32_t w2 = w[2];                  // holds byte p + 7, which is inside the block
+  return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+#else
+  uint64_t v = 0;
+  for (int k = 0; k < 8; k++) v |= (uint64_t)in[p + k] << (8 * k);
+  return v;
+#endif
+}
+ZHD uint32_t common8(uint64_t a, uint64_t b) {
+  const uint32_t xl = (uint32_t)a ^ (uint32_t)b, xh = (uint32_t)(a >> 32) ^ (uint32_t)(b >> 32);
+#if defined(__CUDA_ARCH__)
+  if (xl) return (uint32_t)(__ffs((int)xl) - 1) >> 3;
+  if (xh) return 4u + ((uint32_t)(__ffs((int)xh) - 1) >> 3);
+#else
+  if (xl) return (uint32_t)__builtin_ctz(xl) >> 3;
+  if (xh) return 4u + ((uint32_t)__builtin_ctz(xh) >> 3);
+#endif
+  return 8u;
+}
+// number of equal bytes of in[a ..] and in[a - off ..], a + result <= n
+ZHD uint32_t count_fwd(const uint8_t *in, uint32_t a, uint32_t off, uint32_t n) {
+  uint32_t len = 0;
+  while (a + len + 8 <= n) {
+    const uint32_t c = common8(rd64(in, a + len), rd64(in, a + len - off));
+    len += c;
+    if (c < 8) return len;
+  }
+  while (a + len < n && rd8(in, a + len) == rd8(in, a + len - off)) len++;
+  return len;
+}
+
+// ---- MATCH stage, per position (the kernel runs the same arithmetic on the block staged in shared memory) ----
+// c_long / c_short: candidate positions (< p) or -1.  v = rd64(p).  Returns R[p].
+template <typename Rd64>
+ZHD uint32_t match_verify(const Rd64 &rd, uint32_t p, uint64_t v, int32_t c_long, int32_t c_short, uint32_t n) {
+  uint32_t off = 0, len = 0;
+  if (c_long >= 0 && rd((uint32_t)c_long) == v) { off = p - (uint32_t)c_long; len = 8; }
+  else if (c_short >= 0) {
+    const uint32_t c = common8(v, rd((uint32_t)c_short));
+    if (c >= LZ_MIN_MATCH) { off = p - (uint32_t)c_short; len = c; }
+  }
+  if (len == 8) {
+    while (len < LZ_LCAP && p + len + 8 <= n) {
+      const uint32_t c = common8(rd(p + len), rd(p + len - off));
+      len += c;
+      if (c < 8) break;
+    }
+    if (len > LZ_LCAP) len = LZ_LCAP;
+  }
+  return len ? (off | (len << 17)) : 0u;
+}
+
+// ---- SELECT stage ----
+struct State {
+  uint32_t ip, anchor;        // next decision position; end of the last match (start of the pending literals)
+  uint32_t r0, r1, r2;        // repeat-offset history as the decoder will hold it (0 = unknown)
+  ZHD bool same(const State &o) const { return ip == o.ip && anchor == o.anchor && r0 == o.r0 && r1 == o.r1 && r2 == o.r2; }
+};
+
+// repeat-offset coding of one sequence on a three-word history (enc::offset_to_code without the array)
+ZHD uint32_t code_offset(uint32_t off, bool ll0, uint32_t &r0, uint32_t &r1, uint32_t &r2) {
+  uint32_t code;
+  if (!ll0) {
+    if (off == r0) return 1;
+    if (off == r1) { r1 = r0; r0 = off; return 2; }
+    code = off == r2 ? 3u : off + 3u;
+  } else {
+    if (off == r1) { r1 = r0; r0 = off; return 1; }
+    if (off == r2) code = 2;
+    else if (r0 > 1 && off == r0 - 1) code = 3;
+    else code = off + 3;
+  }
+  r2 = r1; r1 = r0; r0 = off;
+  return code;
+}
+// the decoder's side of the same rule: offset code -> offset, history updated (RFC 8878 3.1.1.5); used to replay a list
+ZHD uint32_t decode_offset(uint32_t code, bool ll0, uint32_t &r0, uint32_t &r1, uint32_t &r2) {
+  uint32_t off;
+  if (code > 3) { off = code - 3; r2 = r1; r1 = r0; r0 = off; return off; }
+  const uint32_t idx = code - 1 + (ll0 ? 1u : 0u);
+  if (idx == 0) return r0;
+  if (idx == 1) { off = r1; r1 = r0; r0 = off; return off; }
+  off = idx == 2 ? r2 : r0 - 1;
+  r2 = r1; r1 = r0; r0 = off;
+  return off;
+}
+
+// list entry: start | (length & 0x7FFF) << 17 ,  offset code | (length >> 15) << 18
+struct Seq { uint32_t x, y; };
+ZHD Seq pack_seq(uint32_t s, uint32_t len, uint32_t code) { return Seq{s | ((len & 0x7FFFu) << 17), code | ((len >> 15) << 18)}; }
+ZHD uint32_t seq_start(const Seq &q) { return q.x & LZ_OFF_MASK; }
+ZHD uint32_t seq_len(const Seq &q) { return (q.x >> 17) | ((q.y >> 18) << 15); }
+ZHD uint32_t seq_code(const Seq &q) { return q.y & ((1u << 18) - 1); }
+
+struct SelectParams { int lazy; };
+
+// One decision of the walk at st.ip (< lim).  Either emits one sequence (returns true, *out filled) or skips literals.
+// n: block bytes; lim: first position this lane does not decide.
+ZHD bool select_step(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t lim, const SelectParams &P, State &st, Seq *out) {
+  const uint32_t ip = st.ip;
+  uint32_t s, off, len;
+  bool found = false;
+  // (a) right behind a match: the second repeat offset with no literals in between (libzstd does the same after every match)
+  if (ip == st.anchor && st.r1 != 0 && ip >= st.r1) {
+    const uint64_t a = rd64(in, ip), b = rd64(in, ip - st.r1);
+    const uint32_t c = common8(a, b);
+    if (c >= 4 && (c == 8 || c + LZ_REP_BONUS >= (R[ip] >> 17))) { s = ip; off = st.r1; len = c == 8 ? 8 + count_fwd(in, ip + 8, off, n) : c; found = true; }
+  }
+  if (!found) {
+    const uint32_t e0 = R[ip], e1 = ip + 1 < lim ? R[ip + 1] : 0u;
+    const uint32_t lt0 = e0 >> 17;
+    uint32_t rl0 = 0, rl1 = 0;
+    if (st.r0 != 0) {
+      if (ip >= st.r0 && ip != st.anchor) rl0 = common8(rd64(in, ip), rd64(in, ip - st.r0));
+      if (ip + 1 >= st.r0 && ip + 1 < lim) rl1 = common8(rd64(in, ip + 1), rd64(in, ip + 1 - st.r0));
+    }
+    const bool t0 = e0 != 0, r0ok = rl0 >= 4, r1ok = rl1 >= 4;
+    if (!t0 && !r0ok && !r1ok) {
+      uint32_t q = ip + 1;
+      while (q < lim && R[q] == 0) q++;
+      st.ip = q;
+      return false;
+    }
+    bool open;
+    if (r0ok && (!t0 || rl0 == 8 || rl0 + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r0; len = rl0; open = rl0 == 8; }
+    else if (r1ok && (!t0 || rl1 == 8 || rl1 + LZ_REP_BONUS >= lt0)) { s = ip + 1; off = st.r0; len = rl1; open = rl1 == 8; }
+    else {
+      uint32_t e = e0;
+      s = ip;
+      if (P.lazy && (e1 >> 17) > lt0) { e = e1; s = ip + 1; }
+      off = e & LZ_OFF_MASK; len = e >> 17; open = len == LZ_LCAP;
+    }
+    if (open) len += count_fwd(in, s + len, off, n);
+    uint32_t nb = 0;
+    while (nb < LZ_BACK_MAX && s - nb > st.anchor && s - nb - 1 >= off && rd8(in, s - nb - 1) == rd8(in, s - nb - 1 - off)) nb++;
+    s -= nb; len += nb;
+  }
+  const uint32_t code = code_offset(off, s == st.anchor, st.r0, st.r1, st.r2);
+  *out = pack_seq(s, len, code);
+  st.ip = st.anchor = s + len;
+  return true;
+}
+
+// Speculative walk of one lane: from st until st.ip >= lim.  Returns the number of sequences written to list.
+ZHD uint32_t select_walk(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t lim, const SelectParams &P, State &st, Seq *list) {
+  uint32_t cnt = 0;
+  while (st.ip < lim) {
+    Seq q;
+    if (select_step(in, n, R, lim, P, st, &q)) list[cnt++] = q;
+  }
+  return cnt;
+}
+
+// Re-walk of a lane from its true entry state until it meets the speculative walk `spec` (spec_cnt sequences that
+// started from spec0 and ended in spec_exit).  prefix receives the sequences of the re-walk.  On return:
+//   *sync_k   index of the first speculative sequence that is kept (spec_cnt: none)
+//   st        the lane's true exit state
+// returns the number of prefix sequences.
+ZHD uint32_t select_rewalk(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t lim, const SelectParams &P, State &st, const Seq *spec,
+                           uint32_t spec_cnt, const State &spec0, const State &spec_exit, Seq *prefix, uint32_t *sync_k) {
+  uint32_t cnt = 0, k = 0;
+  State sp = spec0;                       // speculative walk replayed up to (not including) sequence k
+  while (st.ip < lim) {
+    Seq q;
+    if (!select_step(in, n, R, lim, P, st, &q)) continue;
+    prefix[cnt++] = q;
+    // advance the replay to the first speculative sequence that ends at or beyond this one
+    while (k < spec_cnt) {
+      const Seq e = spec[k];
+      const uint32_t es = seq_start(e), ee = es + seq_len(e);
+      if (ee > st.anchor) break;
+      decode_offset(seq_code(e), es == sp.anchor, sp.r0, sp.r1, sp.r2);
+      sp.ip = sp.anchor = ee;
+      k++;
+      if (ee == st.anchor) break;
+    }
+    if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && sp.r2 == st.r2 && k > 0) {
+      // same position, same history: the rest of the speculative walk is the rest of the true walk
+      *sync_k = k;
+      st = spec_exit;
+      return cnt;
+    }
+  }
+  *sync_k = spec_cnt;
+  return cnt;
+}
+
+// sub-segment geometry: lane j decides positions [lane_begin(j), lane_begin(j + 1)) of [0, ilimit)
+ZHD uint32_t lane_span(uint32_t ilimit) { return ((ilimit + LZ_LANES - 1) / LZ_LANES + 3u) & ~3u; }
+ZHD uint32_t lane_begin(uint32_t j, uint32_t span, uint32_t ilimit) { const uint32_t b = j * span; return b < ilimit ? b : ilimit; }
+// sequences a lane can emit: they start inside its span (+ the backward extension) and cover >= 4 bytes each
+ZHD uint32_t lane_list_cap(uint32_t block_max) { return (block_max / LZ_LANES + 4) / 4 + 8; }
+
+} // namespace lz
+} // namespace b200zstd

@@ -64,28 +64,24 @@ ZP_HD EncodeParams encode_params_for_level(int level, int checksum) {
   return p;
 }
 
-// ---- levels 1-4, blocks <= 128 KB: the decoupled pipeline of zstd_encode_esd.cu ---------------------------------
-// One CTA per block, the block resident in shared memory.  A hash warp walks the block in fixed windows of 32
-// positions (lookup, then insert: the table state is independent of the parse), verify warps measure every
-// position's candidate, select warps run the serial greedy parse on the measured candidates, one sub-segment of
-// ESD_SUB positions each; a second kernel joins the sub-segments and codes the block.  libzstd's <= 128 KB rows for these levels are fast (L1-2, 6- then 5-byte
-// hash) and dfast (L3-4); sizes land within +-2 % of them (tools/esd_experiment.cpp, tests/test_gpu_encode.py).
+// ---- levels 1-4, blocks <= 128 KB: the match / select / finish pipeline of zstd_encode_esd.cu ------------------------
+// One CTA per block finds, for EVERY position, its best table candidate (block and hash tables in shared memory, all
+// positions in parallel, window by window); one warp per block then walks the result (lanes walk sub-segments
+// speculatively and are stitched together exactly), and a third kernel codes the block.  libzstd's <= 128 KB rows for
+// these levels are fast (L1-2) and dfast (L3-4); sizes land within +-2 % of them or below (tools/model_ratio.cpp,
+// tests/test_gpu_encode.py).  The parse arithmetic lives in zstd_encode_lz.cuh.
 struct EsdParams {
   int dfast;          // 0: one table (FAST), 1: 5-byte table + 8-byte "long" table (DFAST)
-  int hash_log;       // primary table: 1 << hash_log uint16 entries
+  int hash_log;       // primary table: 1 << hash_log entries (uint16 for blocks <= 64 KB, uint32 above)
   int hash_bytes;     // bytes hashed for the primary table
   int long_log;       // 8-byte-hash table; 0 = absent
   int lazy;           // 1: the position after the first candidate may replace it when its match is longer
 };
-constexpr uint32_t ESD_SUB = 1024;       // positions per independently parsed sub-segment of a block
-constexpr uint32_t ESD_LCAP = 32;        // verify warps measure a match up to this length; longer ones are finished by the select warp
-constexpr uint32_t ESD_MIN_MATCH = 5;    // shortest table match; repeat-offset matches need 4
-constexpr uint32_t ESD_REP_BONUS = 2;    // a repeat-offset match wins when its length + bonus reaches the table match
 ZP_HD bool esd_level(int level) { return level <= 4; }
 ZP_HD EsdParams esd_params_for_level(int level) {
   EsdParams e{};
-  if (level <= 2) { e.dfast = 0; e.hash_log = 13; e.hash_bytes = level <= 1 ? 6 : 5; e.long_log = 0; e.lazy = level >= 2 ? 1 : 0; }
-  else { e.dfast = 1; e.hash_log = 12; e.hash_bytes = 5; e.long_log = 13; e.lazy = 1; }
+  if (level <= 2) { e.dfast = 0; e.hash_log = 14; e.hash_bytes = level <= 1 ? 6 : 5; e.long_log = 0; e.lazy = level >= 2 ? 1 : 0; }
+  else { e.dfast = 1; e.hash_log = 13; e.hash_bytes = 5; e.long_log = 13; e.lazy = 1; }
   return e;
 }
 

@@ -7,6 +7,7 @@
 // bit for bit.  It is never linked into the product library.
 #include "../../custom-nvcomp-with-zstd_b200/csrc/zstd_encode_core.cuh"
 #include "../../custom-nvcomp-with-zstd_b200/csrc/zstd_encode_params.h"
+#include "../../custom-nvcomp-with-zstd_b200/csrc/zstd_encode_lz.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -171,120 +172,94 @@ void parse_block(const uint8_t *chunk, uint32_t blk_off, uint32_t bn, const Enco
 
 
 // ------------------------------------------------------------------------------------------------
-// Levels 1-4, blocks <= 128 KB: the decoupled parse of zstd_encode_esd.cu, stage by stage.
-//   hash stage   : fixed windows of 32 positions; every position looks its candidate(s) up in the table state left by
-//                  the windows before it, or takes the nearest lower position of its own window that has the same hash
-//                  and was inserted; then the window is inserted (a position whose hash equals its predecessor's is
-//                  not: runs keep their first position).  uint16 entries, zero = "position 0" (never-written buckets).
-//   verify stage : long candidate needs 8 equal bytes, the short one ESD_MIN_MATCH; an 8-byte match is measured up to
-//                  ESD_LCAP bytes.
-//   select stage : windows of 32 positions from the parse position: repeat-offset matches (>= 4 bytes, byte-exact
-//                  inside the window) and measured table matches; first candidate wins (optionally displaced by its
-//                  right neighbour), open matches are finished, then extended backwards into pending literals.
+// Levels 1-4, blocks <= 128 KB: the match / select parse of zstd_encode_esd.cu, stage by stage (zstd_encode_lz.cuh
+// holds the per-position and per-lane arithmetic, shared with the kernels).
+//   match stage  : windows of LZ_WIN positions; a position's candidates are the table state left by the windows before
+//                  its own; after the lookups the window is inserted, the highest position winning a bucket.
+//   select stage : LZ_LANES lanes walk their sub-segments speculatively, then re-walk from the true entry state until
+//                  they meet their speculative walk; repeated until no lane's exit state changes.
 // ------------------------------------------------------------------------------------------------
-void parse_block_esd(const uint8_t *b, uint32_t bn, const EsdParams &EP, uint32_t rep[3], BlockOut &out) {
+void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP, bool known_history, BlockOut &out) {
+  using namespace b200zstd::lz;
   const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
-  std::vector<uint32_t> Roff((size_t)bn + 64, 0), Rlen((size_t)bn + 64, 0);
-  std::vector<uint16_t> tab1((size_t)1 << EP.hash_log, 0), tab2(EP.dfast ? (size_t)1 << EP.long_log : 0, 0);
-  auto recon = [](uint32_t pos, uint16_t e) -> int64_t {
-    int64_t c = (int64_t)((pos & ~0xFFFFu) | e);
-    if (c >= (int64_t)pos) c -= 0x10000;
-    return c;
-  };
-  uint32_t prev_h1 = 0xFFFFFFFFu, prev_h2 = 0xFFFFFFFFu;
-  for (uint32_t p0 = 0; p0 < ilimit; p0 += 32) {
-    uint32_t h1[32], h2[32];
-    int64_t c1[32], c2[32];
-    bool act[32], ins1[32], ins2[32];
-    for (int l = 0; l < 32; l++) {
-      const uint32_t p = p0 + l;
-      act[l] = p < ilimit; ins1[l] = ins2[l] = false; h1[l] = h2[l] = 0; c1[l] = c2[l] = -1;
-      if (!act[l]) continue;
-      const uint64_t v = read64(b, p, bn);
-      h1[l] = hash_short(v, EP.hash_bytes, EP.hash_log);
-      c1[l] = recon(p, tab1[h1[l]]);
-      ins1[l] = (l > 0 ? h1[l - 1] : prev_h1) != h1[l];
-      for (int m = l - 1; m >= 0; m--) if (ins1[m] && h1[m] == h1[l]) { c1[l] = (int64_t)(p0 + m); break; }
-      if (EP.dfast) {
-        h2[l] = hash_long(v, EP.long_log);
-        c2[l] = recon(p, tab2[h2[l]]);
-        ins2[l] = (l > 0 ? h2[l - 1] : prev_h2) != h2[l];
-        for (int m = l - 1; m >= 0; m--) if (ins2[m] && h2[m] == h2[l]) { c2[l] = (int64_t)(p0 + m); break; }
+  std::vector<uint32_t> R((size_t)bn + 8, 0);
+  {
+    // table entries are positions; a never-written bucket reads as position 0 (a candidate like any other: the bytes decide)
+    std::vector<uint32_t> tab1((size_t)1 << EP.hash_log, 0), tab2(EP.dfast ? (size_t)1 << EP.long_log : 0, 0);
+    std::vector<uint32_t> first1((size_t)1 << LZ_FIRST_LOG, 0xFFFFFFFFu), first2((size_t)1 << LZ_FIRST_LOG, 0xFFFFFFFFu);
+    auto rd = [&](uint32_t p) { return rd64(b, p); };
+    std::vector<uint32_t> h1(LZ_WIN + 1, 0), h2(LZ_WIN + 1, 0);      // [0] = hash of the position before the window
+    std::vector<int32_t> c1(LZ_WIN), c2(LZ_WIN);
+    for (uint32_t w = 0; w * LZ_WIN < ilimit; w++) {
+      const uint32_t w0 = w * LZ_WIN, w1 = std::min(w0 + LZ_WIN, ilimit);
+      // phase 1: hashes, lookups of the state before the window, first-of-window side table
+      for (uint32_t p = w0; p < w1; p++) {
+        const uint32_t t = p - w0;
+        const uint64_t v = rd64(b, p);
+        h1[t + 1] = hash_short(v, EP.hash_bytes, EP.hash_log);
+        c1[t] = (int32_t)tab1[h1[t + 1]];
+        if (inserts(p, h1[t + 1], h1[t])) { uint32_t &f = first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)]; f = std::min(f, first_key(w, t, h1[t + 1])); }
+        if (EP.dfast) {
+          h2[t + 1] = hash_long(v, EP.long_log);
+          c2[t] = (int32_t)tab2[h2[t + 1]];
+          if (inserts(p, h2[t + 1], h2[t])) { uint32_t &f = first2[h2[t + 1] >> (EP.long_log - LZ_FIRST_LOG)]; f = std::min(f, first_key(w, t, h2[t + 1])); }
+        } else c2[t] = -1;
       }
-    }
-    // (inactive lanes only exist in the last window; lane 31's hash of a full window feeds the next window's lane 0)
-    prev_h1 = h1[31]; prev_h2 = h2[31];
-    for (int l = 0; l < 32; l++) if (act[l]) {
-      const uint32_t p = p0 + l;
-      if (ins1[l]) tab1[h1[l]] = (uint16_t)p;
-      if (ins2[l]) tab2[h2[l]] = (uint16_t)p;
-    }
-    for (int l = 0; l < 32; l++) if (act[l]) {
-      const uint32_t p = p0 + l;
-      const uint64_t v = read64(b, p, bn);
-      uint32_t off = 0, len = 0;
-      if (c2[l] >= 0 && read64(b, (uint32_t)c2[l], bn) == v) { off = p - (uint32_t)c2[l]; len = 8; }
-      else if (c1[l] >= 0) {
-        const uint32_t c = common8(v, read64(b, (uint32_t)c1[l], bn));
-        if (c >= ESD_MIN_MATCH) { off = p - (uint32_t)c1[l]; len = c; }
-      }
-      if (len == 8) {
-        while (len < ESD_LCAP && p + len < bn) {
-          uint32_t c = common8(read64(b, p + len, bn), read64(b, p + len - off, bn));
-          const uint32_t room = bn - (p + len);
-          if (c > room) c = room;
-          len += c;
-          if (c < 8) break;
+      // phase 2: inserts (highest position wins), candidates, verification
+      for (uint32_t p = w0; p < w1; p++) {
+        const uint32_t t = p - w0;
+        if (inserts(p, h1[t + 1], h1[t])) tab1[h1[t + 1]] = std::max(tab1[h1[t + 1]], p);
+        if (EP.dfast && inserts(p, h2[t + 1], h2[t])) tab2[h2[t + 1]] = std::max(tab2[h2[t + 1]], p);
+        int32_t a1 = first_candidate(first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)], w, t, h1[t + 1]);
+        if (a1 < 0) a1 = c1[t] < (int32_t)p ? c1[t] : -1;
+        int32_t a2 = -1;
+        if (EP.dfast) {
+          a2 = first_candidate(first2[h2[t + 1] >> (EP.long_log - LZ_FIRST_LOG)], w, t, h2[t + 1]);
+          if (a2 < 0) a2 = c2[t] < (int32_t)p ? c2[t] : -1;
         }
-        if (len > ESD_LCAP) len = ESD_LCAP;
+        R[p] = match_verify(rd, p, rd64(b, p), a2, a1, bn);
       }
-      Roff[p] = off; Rlen[p] = len;
+      h1[0] = h1[w1 - w0]; h2[0] = h2[w1 - w0];
     }
   }
-  // select stage: independent sub-segments of ESD_SUB positions
-  uint32_t anchor = 0;                                   // end of the last match anywhere in the block
-  for (uint32_t B = 0; B < ilimit; B += ESD_SUB) {
-    const uint32_t E = std::min(B + ESD_SUB, bn), lim = std::min(E, ilimit);
-    uint32_t rs[3] = {0, 0, 0};                          // repeat-offset history as the sub-segment knows it (0 = unknown)
-    if (B == 0) { rs[0] = rep[0]; rs[1] = rep[1]; rs[2] = rep[2]; }
-    uint32_t ip = B, lanchor = B, rep0 = rs[0];
-    while (ip < lim) {
-      uint32_t eq = 0, ok = 0, inb = 0;
-      for (int l = 0; l < 32; l++) {
-        const uint32_t p = ip + l;
-        if (rep0 && p >= rep0 && p < E && b[p] == b[p - rep0]) eq |= 1u << l;
-        if (p < lim && p + 4 <= E) { inb |= 1u << l; if (Roff[p]) ok |= 1u << l; }
-      }
-      const uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & inb;
-      const uint32_t cand = ok | rp;
-      if (!cand) { ip += 32; continue; }
-      int f = __builtin_ctz(cand);
-      auto replen = [&](int j) { const uint32_t m = ~(eq >> j); return m ? (uint32_t)__builtin_ctz(m) : 32u; };
-      auto rlen = [&](int j) { return ((inb >> j) & 1) ? Rlen[ip + j] : 0u; };
-      bool use_rep = false;
-      if ((rp >> f) & 1) {
-        const uint32_t rl = replen(f);
-        if (!((ok >> f) & 1) || f + rl == 32 || rl + ESD_REP_BONUS >= rlen(f)) use_rep = true;
-      } else if (f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
-        const uint32_t rl = replen(f + 1);
-        if (f + 1 + rl == 32 || rl + ESD_REP_BONUS >= rlen(f)) { f = f + 1; use_rep = true; }
-      }
-      if (!use_rep && EP.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && rlen(f + 1) > rlen(f)) f = f + 1;
-      uint32_t s = ip + f, off, len;
-      bool open;
-      if (use_rep) { len = replen(f); off = rep0; open = f + len == 32; }
-      else { off = Roff[s]; len = Rlen[s]; open = len == ESD_LCAP; }
-      if (open) while (s + len < E && b[s + len] == b[s + len - off]) len++;
-      if (s + len > E) len = E - s;
-      uint32_t nb = 0;
-      while (nb < 32 && s - nb > lanchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
-      s -= nb; len += nb;
-      out.lits.insert(out.lits.end(), b + anchor, b + s);
-      out.ll.push_back(s - anchor); out.ml.push_back(len);
-      out.ofv.push_back(offset_to_code(off, s - lanchor, rs));     // coded with the literal run the sub-segment sees
-      ip = lanchor = anchor = s + len; rep0 = off;
+  SelectParams SP{EP.lazy};
+  const uint32_t span = lane_span(ilimit), cap = lane_list_cap(BLOCK_BYTES);
+  std::vector<Seq> spec((size_t)LZ_LANES * cap), prefix((size_t)LZ_LANES * cap);
+  State spec0[LZ_LANES], spec_exit[LZ_LANES], exit_[LZ_LANES], entry_used[LZ_LANES];
+  uint32_t spec_cnt[LZ_LANES], pre_cnt[LZ_LANES], sync_k[LZ_LANES];
+  for (uint32_t j = 0; j < LZ_LANES; j++) {
+    const uint32_t B = lane_begin(j, span, ilimit), E = lane_begin(j + 1, span, ilimit);
+    State st{B, B, 0, 0, 0};
+    if (j == 0 && known_history) { st.r0 = 1; st.r1 = 4; st.r2 = 8; }
+    spec0[j] = entry_used[j] = st;
+    spec_cnt[j] = select_walk(b, bn, R.data(), E, SP, st, &spec[(size_t)j * cap]);
+    spec_exit[j] = exit_[j] = st;
+    pre_cnt[j] = 0; sync_k[j] = 0;
+  }
+  for (;;) {
+    bool changed = false;
+    State entry[LZ_LANES];
+    for (uint32_t j = 1; j < LZ_LANES; j++) entry[j] = exit_[j - 1];          // (a shuffle on the GPU: all lanes see the same round)
+    for (uint32_t j = 1; j < LZ_LANES; j++) {
+      if (entry[j].same(entry_used[j])) continue;
+      entry_used[j] = entry[j];
+      const uint32_t E = lane_begin(j + 1, span, ilimit);
+      State st = entry[j];
+      pre_cnt[j] = select_rewalk(b, bn, R.data(), E, SP, st, &spec[(size_t)j * cap], spec_cnt[j], spec0[j], spec_exit[j], &prefix[(size_t)j * cap], &sync_k[j]);
+      if (!st.same(exit_[j])) { exit_[j] = st; changed = true; }
     }
-    if (B == 0) { rep[0] = rs[0]; rep[1] = rs[1]; rep[2] = rs[2]; }
+    if (!changed) break;
+  }
+  uint32_t anchor = 0;
+  auto take = [&](const Seq &q) {
+    const uint32_t s = seq_start(q), len = seq_len(q);
+    out.lits.insert(out.lits.end(), b + anchor, b + s);
+    out.ll.push_back(s - anchor); out.ml.push_back(len); out.ofv.push_back(seq_code(q));
+    anchor = s + len;
+  };
+  for (uint32_t j = 0; j < LZ_LANES; j++) {
+    for (uint32_t i = 0; i < pre_cnt[j]; i++) take(prefix[(size_t)j * cap + i]);
+    for (uint32_t i = sync_k[j]; i < spec_cnt[j]; i++) take(spec[(size_t)j * cap + i]);
   }
   out.lits.insert(out.lits.end(), b + anchor, b + bn);
 }
@@ -319,7 +294,7 @@ size_t model_compress(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, in
     }
     BlockOut B;
     uint32_t rep_save[3] = {rep[0], rep[1], rep[2]};
-    if (esd_level(P.level) && n <= BLOCK_BYTES) parse_block_esd(src, bn, esd_params_for_level(P.level), rep, B);
+    if (esd_level(P.level) && n <= BLOCK_BYTES) parse_block_lz(src, bn, esd_params_for_level(P.level), true, B);
     else parse_block(src, (uint32_t)ip, bn, P, rep, B, MAX_SEQ_PER_BLOCK);
     uint32_t payload = B.ll.size() >= MAX_SEQ_PER_BLOCK ? 0 : encode_block_payload(W, B.lits.data(), (uint32_t)B.lits.size(), B.ll.data(), B.ml.data(), B.ofv.data(), (uint32_t)B.ll.size(), tmp.data(), bn - 1);
     if (payload == 0 || payload >= bn) {

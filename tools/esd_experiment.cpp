@@ -97,52 +97,55 @@ static void parse_esd(const uint8_t *b, uint32_t bn, const Knobs &K, uint32_t re
       Roff[p] = off; Rlen[p] = len;
     }
   }
-  // ---- S stage: independent sub-segments of SUB positions (matches truncated at their end, repeat offsets unknown at their start) ----
-  const uint32_t SUB = (uint32_t)envi("SUB", 1 << 20);
+  // ---- S stage, lane-serial semantics: visited positions are the one after each match and the next position that has a table candidate ----
+  const uint32_t SUB = (uint32_t)envi("SUB", 1024);
+  const uint32_t NBMAX = (uint32_t)envi("NBMAX", 8);
   uint32_t anchor = 0;
-  auto emit = [&](uint32_t s, uint32_t len, uint32_t off, uint32_t *rp3) {
+  auto emit = [&](uint32_t s, uint32_t len, uint32_t off, uint32_t llc, uint32_t *rp3) {
     uint32_t ll = s - anchor;
     out.lits.insert(out.lits.end(), b + anchor, b + s);
     out.ll.push_back(ll); out.ml.push_back(len);
-    out.ofv.push_back(offset_to_code(off, ll, rp3));
+    out.ofv.push_back(offset_to_code(off, llc, rp3));
   };
   for (uint32_t B = 0; B < ilimit; B += SUB) {
     const uint32_t E = std::min(B + SUB, bn), lim = std::min(E, ilimit);
     uint32_t rs[3] = {0, 0, 0};
     if (B == 0) { rs[0] = rep[0]; rs[1] = rep[1]; rs[2] = rep[2]; }
     uint32_t ip = B, rep0 = rs[0], lanchor = B;
+    auto tab_at = [&](uint32_t p) { return p < lim && p + 4 <= E && Roff[p] != 0; };
+    auto rep_len = [&](uint32_t p, uint32_t cap) {      // equal bytes at p vs p - rep0, up to cap, inside the sub-segment
+      if (!rep0 || p < rep0) return 0u;
+      uint32_t n = 0;
+      while (n < cap && p + n < E && b[p + n] == b[p + n - rep0]) n++;
+      return n;
+    };
     while (ip < lim) {
-      uint32_t eq = 0, ok = 0, inb = 0;
-      for (int l = 0; l < 32; l++) {
-        uint32_t p = ip + l;
-        if (rep0 && p >= rep0 && p < E && b[p] == b[p - rep0]) eq |= 1u << l;
-        if (p < lim && p + 4 <= E) { inb |= 1u << l; if (Roff[p]) ok |= 1u << l; }
+      const bool t0 = tab_at(ip);
+      const uint32_t rl0 = (ip + 4 <= E) ? rep_len(ip, 8) : 0, rl1 = (ip + 1 < lim && ip + 5 <= E) ? rep_len(ip + 1, 7) : 0;
+      const bool r0ok = rl0 >= 4, r1ok = rl1 >= 4;
+      if (!t0 && !r0ok && !r1ok) {
+        uint32_t q = ip + 1;
+        while (q < lim && !tab_at(q)) q++;
+        ip = q;
+        continue;
       }
-      uint32_t rp = eq & (eq >> 1) & (eq >> 2) & (eq >> 3) & inb;
-      uint32_t cand = ok | rp;
-      if (!cand) { ip += 32; continue; }
-      int f = __builtin_ctz(cand);
-      uint32_t off, len;
-      bool open;
-      auto replen = [&](int j) { uint32_t m = ~(eq >> j); return m ? (uint32_t)__builtin_ctz(m) : 32u; };
-      bool use_rep = false;
-      if ((rp >> f) & 1) {
-        uint32_t rl = replen(f);
-        if (!((ok >> f) & 1) || f + rl == 32 || rl + K.rep_bonus >= Rlen[ip + f]) use_rep = true;
-      } else if (K.rep_next && f + 1 < 32 && ((rp >> (f + 1)) & 1)) {
-        uint32_t rl = replen(f + 1);
-        if (f + 1 + rl == 32 || rl + K.rep_bonus >= Rlen[ip + f]) { f = f + 1; use_rep = true; }
+      uint32_t f = ip, off, len;
+      bool use_rep = false, open = false;
+      const uint32_t lt0 = t0 ? Rlen[ip] : 0;
+      if (r0ok) { if (!t0 || rl0 == 8 || rl0 + K.rep_bonus >= lt0) { use_rep = true; len = rl0; open = rl0 == 8; } }
+      if (!use_rep && r1ok && K.rep_next) { if (!t0 || rl1 == 7 || rl1 + K.rep_bonus >= lt0) { use_rep = true; f = ip + 1; len = rl1; open = rl1 == 7; } }
+      if (use_rep) { off = rep0; stats[0]++; }
+      else {
+        if (K.lazy && tab_at(ip + 1) && Rlen[ip + 1] > lt0) f = ip + 1;
+        off = Roff[f]; len = Rlen[f]; open = len == (uint32_t)K.lcap; stats[1]++;
       }
-      if (!use_rep && K.lazy && f + 1 < 32 && ((ok >> (f + 1)) & 1) && Rlen[ip + f + 1] > Rlen[ip + f]) f = f + 1;
-      uint32_t s = ip + f;
-      if (use_rep) { len = replen(f); off = rep0; open = f + len == 32; stats[0]++; }
-      else { off = Roff[s]; len = Rlen[s]; open = len == (uint32_t)K.lcap; stats[1]++; }
+      uint32_t s = f;
       if (open) { while (s + len < E && b[s + len] == b[s + len - off]) len++; stats[2]++; }
       if (s + len > E) len = E - s;
       uint32_t nb = 0;
-      while (nb < (uint32_t)envi("NBMAX", 32) && s - nb > lanchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
+      while (nb < NBMAX && s - nb > lanchor && s - nb - 1 >= off && b[s - nb - 1] == b[s - nb - 1 - off]) nb++;
       s -= nb; len += nb;
-      emit(s, len, off, rs);
+      emit(s, len, off, s - lanchor, rs);
       ip = lanchor = anchor = s + len; rep0 = off;
     }
     if (B == 0 && SUB >= bn) { rep[0] = rs[0]; rep[1] = rs[1]; rep[2] = rs[2]; }
