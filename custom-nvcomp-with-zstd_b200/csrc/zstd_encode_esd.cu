@@ -8,13 +8,16 @@
 // Three kernels per wave of blocks, each of them data-parallel over the whole wave (zstd_encode_lz.cuh holds the
 // arithmetic of the first two, shared with the host-side model tests/model/enc_model.cpp; the bytes must agree):
 //
-// MATCH  (zstd_lz_match_kernel)   one CTA of 256 threads per <= 128 KB block.  The block arrives HBM -> shared memory by
-//        cp.async.bulk (TMA) copies completing on an mbarrier; the hash tables live in shared memory.  The block is
-//        walked in windows of 256 positions, one per thread: hash, look the candidates up in the state the windows
-//        before left behind, note "first position of this window with my hash" in a small side table (atomicMin on a
-//        window-tagged key), barrier, insert (highest position wins a bucket), barrier, verify the candidate against
-//        the staged block and measure the match up to 16 bytes.  R[p] = offset | length << 17 goes to the wave's scratch.
-//        Nothing in this kernel depends on the parse, so every position of every block is independent work.
+// MATCH  (zstd_lz_match_kernel)   one CTA of 1024 threads per <= 128 KB block, one CTA per SM.  The block arrives HBM ->
+//        shared memory by cp.async.bulk (TMA) copies completing on an mbarrier; the hash tables (uint32 buckets, 128 KB
+//        for a 64 KB block) live in shared memory.  The block is walked in windows of 256 positions, one per thread of
+//        a GROUP of 8 warps; the four groups take the windows in turn.  Per window: hash, look the candidates up in the
+//        state the windows before left behind, note "first position of this window with my hash" in a small side table
+//        (atomicMin on a window-tagged key), group barrier, insert (atomicMax: highest position wins a bucket), tell
+//        the next group to start its window (named barriers: arrive / sync), then -- off that chain -- verify the
+//        candidate against the staged block and measure the match up to 16 bytes.  R[p] = offset | length << 17 goes to
+//        the wave's scratch.  Nothing in this kernel depends on the parse: every position is independent work, and
+//        the only serial part is the lookup -> insert hand-over from window to window.
 // SELECT (zstd_lz_select_kernel)  one warp per block, one lane per 1/32 of it: each lane walks its sub-segment greedily
 //        over R (repeat offsets, one-step lazy, extension of long matches), first speculatively from its first
 //        position, then again from the state the lane before it really ended in until the two walks meet; the rounds
@@ -38,7 +41,8 @@ using namespace lz;
 
 namespace {
 
-constexpr int MATCH_THREADS = (int)LZ_WIN;
+constexpr int MATCH_GROUPS = 4;                  // groups of LZ_WIN threads that take the windows in turn
+constexpr int MATCH_THREADS = MATCH_GROUPS * (int)LZ_WIN;
 constexpr uint32_t LZ_IN_PAD = 64;               // 16 bytes of alignment slack in front, read-ahead room behind
 constexpr uint32_t KIND_PARSED = 0, KIND_RLE = 1, KIND_SKIP = 2;
 
@@ -85,16 +89,9 @@ __device__ __forceinline__ uint64_t lds64(const uint8_t *base16, uint32_t at) {
   return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 }
 
-// "highest position wins": uint16 buckets (blocks <= 64 KB) take a compare-and-swap loop, uint32 buckets atomicMax
-__device__ __forceinline__ void bucket_max(uint16_t *b, uint32_t p) {
-  uint16_t old = *b;
-  while (old < p) {
-    const uint16_t seen = atomicCAS(b, old, (uint16_t)p);
-    if (seen == old) break;
-    old = seen;
-  }
-}
-__device__ __forceinline__ void bucket_max(uint32_t *b, uint32_t p) { atomicMax(b, p); }
+// named barriers: 1 + g = the threads of group g among themselves; 5 + g = "the window before group g's is inserted"
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 struct EsdArgs {
   EncodeArgs A;
@@ -112,18 +109,19 @@ struct EsdArgs {
 };
 
 template <int DFAST, int BIG>
-__global__ void __launch_bounds__(MATCH_THREADS, BIG ? 1 : 2) zstd_lz_match_kernel(EsdArgs K) {
-  using Bucket = typename std::conditional<BIG != 0, uint32_t, uint16_t>::type;
+__global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_match_kernel(EsdArgs K) {
   constexpr uint32_t block_max = BIG ? 131072u : 65536u;
   extern __shared__ __align__(128) uint8_t smem[];
   MatchCtl *const ctl = reinterpret_cast<MatchCtl *>(smem);
   uint8_t *const in_base = smem + 128;                                         // 16-byte aligned
-  Bucket *const tab1 = reinterpret_cast<Bucket *>(in_base + block_max + LZ_IN_PAD);
-  Bucket *const tab2 = tab1 + ((size_t)1 << K.E.hash_log);
-  uint32_t *const first1 = reinterpret_cast<uint32_t *>(tab2 + (DFAST ? ((size_t)1 << K.E.long_log) : 0));
+  uint32_t *const tab1 = reinterpret_cast<uint32_t *>(in_base + block_max + LZ_IN_PAD);
+  uint32_t *const tab2 = tab1 + ((size_t)1 << K.E.hash_log);
+  uint32_t *const first1 = tab2 + (DFAST ? ((size_t)1 << K.E.long_log) : 0);
   uint32_t *const first2 = first1 + (1u << LZ_FIRST_LOG);
 
   const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> LZ_WIN_LOG;                     // warp-uniform
+  const uint32_t t = (uint32_t)tid & (LZ_WIN - 1u);
   const EncodeArgs &A = K.A;
   const bool blocks_only = A.block_mode != 0;
   const int hash_log = K.E.hash_log, long_log = K.E.long_log, hash_bytes = K.E.hash_bytes;
@@ -184,7 +182,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, BIG ? 1 : 2) zstd_lz_match_kern
     }
     {
       uint4 *z = reinterpret_cast<uint4 *>(tab1);
-      const uint32_t vecs = (uint32_t)((sizeof(Bucket) << hash_log) + (DFAST ? (sizeof(Bucket) << long_log) : 0)) >> 4;
+      const uint32_t vecs = (uint32_t)(((size_t)4 << hash_log) + (DFAST ? ((size_t)4 << long_log) : 0)) >> 4;
       for (uint32_t i = tid; i < vecs; i += MATCH_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       for (uint32_t i = tid; i < (2u << LZ_FIRST_LOG); i += MATCH_THREADS) first1[i] = 0xFFFFFFFFu;
     }
@@ -209,38 +207,45 @@ __global__ void __launch_bounds__(MATCH_THREADS, BIG ? 1 : 2) zstd_lz_match_kern
       const uint32_t nwin = (ilimit + LZ_WIN - 1) / LZ_WIN;
       uint32_t *const Rg = reinterpret_cast<uint32_t *>(slot + slot_r_off());
       auto rd = [&](uint32_t q) { return lds64(in_base, delta + q); };
-      for (uint32_t w = 0; w < nwin; w++) {
-        const uint32_t p = w * LZ_WIN + (uint32_t)tid;
+      const int next_grp = (grp + 1) & (MATCH_GROUPS - 1);
+      for (uint32_t w = (uint32_t)grp; w < nwin; w += MATCH_GROUPS) {
+        const uint32_t p = w * LZ_WIN + t;
         const bool act = p < ilimit;
         const uint64_t v = act ? rd(p) : 0ull;
-        // phase 1: hashes, the state before this window, first-of-window side table
         const uint32_t h1 = hash_short(v, hash_bytes, hash_log);
         const uint32_t hp1 = __shfl_up_sync(0xffffffffu, h1, 1);
         const bool ins1 = act && inserts((uint32_t)lane, h1, hp1);
-        const uint32_t e1 = act ? (uint32_t)tab1[h1] : 0u;
         const uint32_t s1 = h1 >> (hash_log - LZ_FIRST_LOG);
-        if (ins1) atomicMin(&first1[s1], first_key(w, (uint32_t)tid, h1));
-        uint32_t h2 = 0, e2 = 0, s2 = 0;
+        uint32_t h2 = 0, s2 = 0;
         bool ins2 = false;
         if (DFAST) {
           h2 = hash_long(v, long_log);
           const uint32_t hp2 = __shfl_up_sync(0xffffffffu, h2, 1);
           ins2 = act && inserts((uint32_t)lane, h2, hp2);
-          e2 = act ? (uint32_t)tab2[h2] : 0u;
           s2 = h2 >> (long_log - LZ_FIRST_LOG);
-          if (ins2) atomicMin(&first2[s2], first_key(w, (uint32_t)tid, h2));
         }
-        __syncthreads();
-        // phase 2: inserts; the candidate is the first earlier position of this window with my hash, else the old entry
-        if (ins1) bucket_max(&tab1[h1], p);
-        int32_t a1 = first_candidate(first1[s1], w, (uint32_t)tid, h1), a2 = -1;
-        if (a1 < 0) a1 = e1 < p ? (int32_t)e1 : -1;
+        // the window before this one must be in the tables
+        if (w > 0) bar_sync(5 + grp, 2 * (int)LZ_WIN);
+        // phase 1: the state before this window, first-of-window side table
+        const uint32_t e1 = act ? tab1[h1] : 0u;
+        if (ins1) atomicMin(&first1[s1], first_key(w, t, h1));
+        uint32_t e2 = 0;
         if (DFAST) {
-          if (ins2) bucket_max(&tab2[h2], p);
-          a2 = first_candidate(first2[s2], w, (uint32_t)tid, h2);
-          if (a2 < 0) a2 = e2 < p ? (int32_t)e2 : -1;
+          e2 = act ? tab2[h2] : 0u;
+          if (ins2) atomicMin(&first2[s2], first_key(w, t, h2));
         }
-        __syncthreads();
+        bar_sync(1 + grp, (int)LZ_WIN);
+        // phase 2: inserts; the candidate is the first earlier position of this window with my hash, else the old entry
+        if (ins1) atomicMax(&tab1[h1], p);
+        int32_t a1 = first_candidate(first1[s1], w, t, h1), a2 = -1;
+        if (DFAST) {
+          if (ins2) atomicMax(&tab2[h2], p);
+          a2 = first_candidate(first2[s2], w, t, h2);
+        }
+        if (w + 1 < nwin) bar_arrive(5 + next_grp, 2 * (int)LZ_WIN);
+        // off the chain: verification
+        if (a1 < 0) a1 = e1 < p ? (int32_t)e1 : -1;
+        if (DFAST && a2 < 0) a2 = e2 < p ? (int32_t)e2 : -1;
         if (act) Rg[p] = match_verify(rd, p, v, a2, a1, bn);
       }
     }
@@ -436,8 +441,7 @@ __global__ void __launch_bounds__(32 * FIN_WARPS, 8) zstd_lz_finish_kernel(FinAr
 
 size_t match_smem_bytes(const EsdParams &e, int big) {
   const size_t in = (big ? 131072u : 65536u) + LZ_IN_PAD;
-  const size_t entry = big ? 4 : 2;
-  const size_t tabs = (entry << e.hash_log) + (e.dfast ? (entry << e.long_log) : 0);
+  const size_t tabs = ((size_t)4 << e.hash_log) + (e.dfast ? ((size_t)4 << e.long_log) : 0);
   return 128 + in + tabs + ((size_t)8 << LZ_FIRST_LOG);
 }
 
@@ -466,7 +470,7 @@ size_t esd_counter_words(size_t n_items, uint32_t bm) {
   return 4 * ((n_items + wave - 1) / wave) + 2;
 }
 
-// Levels 1-4.  Per wave: the 64 KB-block match kernel (two CTAs per SM), the 128 KB-block match kernel (one CTA per SM)
+// Levels 1-4.  Per wave: the 64 KB-block match kernel, the 128 KB-block match kernel (half the table size)
 // over what the first handed on, the select kernel, the finish kernel; after the last wave the general kernel
 // (zstd_encode.cu) for multi-block items.  max_item_bytes != 0 (the host knows the sizes) skips the launches that cannot have work.
 cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaStream_t stream, int *launches) {
@@ -495,20 +499,21 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
     uint32_t *const c = L.counters + 4 * w;
     EsdArgs k{};
     k.A = args;
-    k.E = esd_params_for_level(args.prm.level);
     k.slots = L.scratch; k.slot_bytes = slot_bytes; k.slot_block_max = bm;
     k.wave_base = (uint32_t)(w * wave); k.wave_n = (uint32_t)min((size_t)wave, args.n - w * wave);
     k.big_list = list_big; k.big_count = big_count;
     if (any64) {
+      k.E = esd_params_for_level(args.prm.level, 0);
       k.list = nullptr; k.list_count = nullptr;
       k.work_head = c + 0;
       k.defer_list = list128 + k.wave_base; k.defer_count = c + 3;
-      const int grid = (int)min((size_t)k.wave_n, (size_t)L.sm_count * 2);
+      const int grid = (int)min((size_t)k.wave_n, (size_t)L.sm_count);
       e = k.E.dfast ? match_launch_one<1, 0>(k, grid, stream) : match_launch_one<0, 0>(k, grid, stream);
       if (e != cudaSuccess) return e;
       nl++;
     }
     if (any128) {
+      k.E = esd_params_for_level(args.prm.level, 1);
       if (any64) { k.list = list128 + k.wave_base; k.list_count = c + 3; } else { k.list = nullptr; k.list_count = nullptr; }
       k.work_head = c + 1;
       k.defer_list = nullptr; k.defer_count = nullptr;
@@ -521,7 +526,7 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
     s.A = args;
     s.slots = L.scratch; s.slot_bytes = slot_bytes; s.slot_block_max = bm;
     s.wave_base = k.wave_base; s.wave_n = k.wave_n;
-    s.lazy = k.E.lazy;
+    s.lazy = esd_params_for_level(args.prm.level, 0).lazy;
     zstd_lz_select_kernel<<<(k.wave_n + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, stream>>>(s);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     nl++;

@@ -24,23 +24,27 @@
 namespace b200zstd {
 namespace lz {
 
-constexpr uint32_t LZ_WIN = 256;          // positions per match-stage window (= threads of the match CTA)
+constexpr int LZ_WIN_LOG = 8;
+constexpr uint32_t LZ_WIN = 1u << LZ_WIN_LOG;   // positions per match-stage window (= threads of one group of the match CTA)
 constexpr uint32_t LZ_LANES = 32;         // sub-segments per block (= lanes of the select warp)
 constexpr uint32_t LZ_LCAP = 16;          // the match stage measures a match up to this length; the select stage finishes longer ones
 constexpr uint32_t LZ_MIN_MATCH = 5;      // shortest table match; repeat-offset matches need 4
 constexpr uint32_t LZ_REP_BONUS = 2;      // a repeat-offset match wins when its length + bonus reaches the table match
 constexpr uint32_t LZ_BACK_MAX = 8;       // backward extension into pending literals, bytes
 constexpr uint32_t LZ_OFF_MASK = (1u << 17) - 1;
-constexpr int LZ_FIRST_LOG = 9;           // slots of the "first position of this window" side table, per hash table
+constexpr int LZ_FIRST_LOG = 9;            // slots of the "first position of this window" side table, per hash table
 
 // The side table that lets a position see the EARLIER positions of its own window: slot = top LZ_FIRST_LOG bits of the
 // hash; key = window tag | position inside the window | low hash bits, combined by atomicMin.  Tags fall from window
 // to window, so a slot never needs clearing and the smallest key of the current window is its first inserted position.
-ZHD uint32_t first_key(uint32_t window, uint32_t t, uint32_t h) { return ((~window & 0x1FFu) << 23) | (t << 15) | (h & 0x7FFFu); }
+// (9 tag bits cover the 128 windows of a 128 KB block many times over.)
+constexpr int LZ_KEY_HBITS = 23 - LZ_WIN_LOG;
+ZHD uint32_t first_key(uint32_t window, uint32_t t, uint32_t h) { return ((~window & 0x1FFu) << 23) | (t << LZ_KEY_HBITS) | (h & ((1u << LZ_KEY_HBITS) - 1u)); }
 // candidate from the side table for thread t of `window` (hash h), or -1
 ZHD int32_t first_candidate(uint32_t key, uint32_t window, uint32_t t, uint32_t h) {
-  const bool mine = (key >> 23) == (~window & 0x1FFu) && (key & 0x7FFFu) == (h & 0x7FFFu) && ((key >> 15) & 0xFFu) < t;
-  return mine ? (int32_t)(window * LZ_WIN + ((key >> 15) & 0xFFu)) : -1;
+  const uint32_t kt = (key >> LZ_KEY_HBITS) & (LZ_WIN - 1u), hm = (1u << LZ_KEY_HBITS) - 1u;
+  const bool mine = (key >> 23) == (~window & 0x1FFu) && (key & hm) == (h & hm) && kt < t;
+  return mine ? (int32_t)(window * LZ_WIN + kt) : -1;
 }
 // a position enters the tables unless its hash equals that of the position before it inside its group of 32 (runs keep
 // their first position, so that a later occurrence of the run finds the aligned candidate)

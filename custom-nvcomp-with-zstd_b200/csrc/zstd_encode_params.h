@@ -72,16 +72,17 @@ ZP_HD EncodeParams encode_params_for_level(int level, int checksum) {
 // tests/test_gpu_encode.py).  The parse arithmetic lives in zstd_encode_lz.cuh.
 struct EsdParams {
   int dfast;          // 0: one table (FAST), 1: 5-byte table + 8-byte "long" table (DFAST)
-  int hash_log;       // primary table: 1 << hash_log entries (uint16 for blocks <= 64 KB, uint32 above)
+  int hash_log;       // primary table: 1 << hash_log uint32 entries
   int hash_bytes;     // bytes hashed for the primary table
   int long_log;       // 8-byte-hash table; 0 = absent
   int lazy;           // 1: the position after the first candidate may replace it when its match is longer
 };
 ZP_HD bool esd_level(int level) { return level <= 4; }
-ZP_HD EsdParams esd_params_for_level(int level) {
+// big: the 128 KB block geometry (the block itself takes twice the shared memory, the tables half)
+ZP_HD EsdParams esd_params_for_level(int level, int big) {
   EsdParams e{};
-  if (level <= 2) { e.dfast = 0; e.hash_log = 14; e.hash_bytes = level <= 1 ? 6 : 5; e.long_log = 0; e.lazy = level >= 2 ? 1 : 0; }
-  else { e.dfast = 1; e.hash_log = 13; e.hash_bytes = 5; e.long_log = 13; e.lazy = 1; }
+  if (level <= 2) { e.dfast = 0; e.hash_log = big ? 14 : 15; e.hash_bytes = level <= 1 ? 6 : 5; e.long_log = 0; e.lazy = level >= 2 ? 1 : 0; }
+  else { e.dfast = 1; e.hash_log = big ? 13 : 14; e.hash_bytes = 5; e.long_log = big ? 13 : 14; e.lazy = 1; }
   return e;
 }
 

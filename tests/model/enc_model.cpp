@@ -179,7 +179,11 @@ void parse_block(const uint8_t *chunk, uint32_t blk_off, uint32_t bn, const Enco
 //   select stage : LZ_LANES lanes walk their sub-segments speculatively, then re-walk from the true entry state until
 //                  they meet their speculative walk; repeated until no lane's exit state changes.
 // ------------------------------------------------------------------------------------------------
-void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP, bool known_history, BlockOut &out) {
+void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool known_history, BlockOut &out) {
+  EsdParams EPm = EP_;
+  if (getenv("HLOG")) EPm.hash_log = atoi(getenv("HLOG"));
+  if (getenv("LLOG") && EPm.dfast) EPm.long_log = atoi(getenv("LLOG"));
+  const EsdParams &EP = EPm;
   using namespace b200zstd::lz;
   const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
   std::vector<uint32_t> R((size_t)bn + 8, 0);
@@ -211,6 +215,10 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP, bool kno
         if (inserts(p, h1[t + 1], h1[t])) tab1[h1[t + 1]] = std::max(tab1[h1[t + 1]], p);
         if (EP.dfast && inserts(p, h2[t + 1], h2[t])) tab2[h2[t + 1]] = std::max(tab2[h2[t + 1]], p);
         int32_t a1 = first_candidate(first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)], w, t, h1[t + 1]);
+        static int lzv2 = getenv("LZV2") ? atoi(getenv("LZV2")) : 0;
+        if (lzv2 == 1) { a1 = -1; for (uint32_t q = t; q-- > 0;) if (h1[q + 1] == h1[t + 1] && inserts(w0 + q, h1[q + 1], h1[q])) { a1 = (int32_t)(w0 + q); break; } }
+        if (lzv2 == 2) { a1 = -1; for (uint32_t q = 0; q < t; q++) if (h1[q + 1] == h1[t + 1] && inserts(w0 + q, h1[q + 1], h1[q])) { a1 = (int32_t)(w0 + q); break; } }
+        if (lzv2 == 3) { a1 = -1; }
         if (a1 < 0) a1 = c1[t] < (int32_t)p ? c1[t] : -1;
         int32_t a2 = -1;
         if (EP.dfast) {
@@ -294,7 +302,7 @@ size_t model_compress(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, in
     }
     BlockOut B;
     uint32_t rep_save[3] = {rep[0], rep[1], rep[2]};
-    if (esd_level(P.level) && n <= BLOCK_BYTES) parse_block_lz(src, bn, esd_params_for_level(P.level), true, B);
+    if (esd_level(P.level) && n <= BLOCK_BYTES) parse_block_lz(src, bn, esd_params_for_level(P.level, bn > 65536), true, B);
     else parse_block(src, (uint32_t)ip, bn, P, rep, B, MAX_SEQ_PER_BLOCK);
     uint32_t payload = B.ll.size() >= MAX_SEQ_PER_BLOCK ? 0 : encode_block_payload(W, B.lits.data(), (uint32_t)B.lits.size(), B.ll.data(), B.ml.data(), B.ofv.data(), (uint32_t)B.ll.size(), tmp.data(), bn - 1);
     if (payload == 0 || payload >= bn) {
