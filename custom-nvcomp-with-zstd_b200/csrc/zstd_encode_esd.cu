@@ -46,11 +46,13 @@ constexpr int MATCH_THREADS = MATCH_GROUPS * (int)LZ_WIN;
 constexpr uint32_t LZ_IN_PAD = 64;               // 16 bytes of alignment slack in front, read-ahead room behind
 constexpr uint32_t KIND_PARSED = 0, KIND_RLE = 1, KIND_SKIP = 2;
 
-// ---- scratch slot of one block: [BlockHdr 16 B | 32 x LaneHdr | R: uint32 x block_max | spec lists | prefix lists] ----
+// ---- scratch slot of one block: [BlockHdr 16 B | 32 x LaneHdr | bitmap "R[p] != 0": block_max bits | R: uint32 x block_max |
+//      spec lists | prefix lists] ----
 struct BlockHdr { uint32_t kind, pad0, pad1, pad2; };
 struct LaneHdr { uint16_t spec_cnt, sync_k, pre_cnt, pad; };
-__host__ __device__ constexpr size_t slot_r_off() { return 16 + LZ_LANES * sizeof(LaneHdr); }
-__host__ __device__ constexpr size_t slot_spec_off(uint32_t bm) { return slot_r_off() + (size_t)bm * 4; }
+__host__ __device__ constexpr size_t slot_map_off() { return 16 + LZ_LANES * sizeof(LaneHdr); }
+__host__ __device__ constexpr size_t slot_r_off(uint32_t bm) { return slot_map_off() + bm / 8; }
+__host__ __device__ constexpr size_t slot_spec_off(uint32_t bm) { return slot_r_off(bm) + (size_t)bm * 4; }
 __host__ __device__ constexpr size_t slot_lists_bytes(uint32_t bm) { return (size_t)LZ_LANES * ((bm / LZ_LANES + 4) / 4 + 8) * sizeof(Seq); }
 __host__ __device__ constexpr size_t slot_pre_off(uint32_t bm) { return slot_spec_off(bm) + slot_lists_bytes(bm); }
 __host__ __device__ constexpr size_t slot_bytes_of(uint32_t bm) { return (slot_pre_off(bm) + slot_lists_bytes(bm) + 255) & ~(size_t)255; }
@@ -205,7 +207,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_match_kernel(EsdArgs
     if (!rle) {
       const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
       const uint32_t nwin = (ilimit + LZ_WIN - 1) / LZ_WIN;
-      uint32_t *const Rg = reinterpret_cast<uint32_t *>(slot + slot_r_off());
+      uint32_t *const Rg = reinterpret_cast<uint32_t *>(slot + slot_r_off(K.slot_block_max));
+      uint32_t *const Mg = reinterpret_cast<uint32_t *>(slot + slot_map_off());
       auto rd = [&](uint32_t q) { return lds64(in_base, delta + q); };
       const int next_grp = (grp + 1) & (MATCH_GROUPS - 1);
       for (uint32_t w = (uint32_t)grp; w < nwin; w += MATCH_GROUPS) {
@@ -246,7 +249,10 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_match_kernel(EsdArgs
         // off the chain: verification
         if (a1 < 0) a1 = e1 < p ? (int32_t)e1 : -1;
         if (DFAST && a2 < 0) a2 = e2 < p ? (int32_t)e2 : -1;
-        if (act) Rg[p] = match_verify(rd, p, v, a2, a1, bn);
+        const uint32_t r = act ? match_verify(rd, p, v, a2, a1, bn) : 0u;
+        if (act) Rg[p] = r;
+        const uint32_t any = __ballot_sync(0xffffffffu, r != 0);
+        if (lane == 0) Mg[p >> 5] = any;
       }
     }
     __syncthreads();                              // every warp is done with the staged block and the tables
@@ -271,6 +277,125 @@ __device__ __forceinline__ State shfl_up_state(const State &s) {
   return r;
 }
 
+// The walk of zstd_encode_lz.cuh (select_step / select_walk / select_rewalk), restated for a warp whose lanes walk their
+// own sub-segments: one loop iteration takes every lane through the stages of one step -- decide, finish an open match,
+// extend backwards, emit -- and the lanes that are in the same stage execute it together, with all loads of a stage in
+// flight at once.  Literal skipping reads the "R != 0" bitmap, 32 positions per load.  Same sequences as the shared code.
+struct Walker {
+  const uint8_t *in;
+  const uint32_t *R, *map;
+  uint32_t n, lim;
+  int lazy;
+};
+enum : uint32_t { W_DECIDE = 0, W_SKIP = 1, W_EXT = 2, W_BACK = 3, W_DONE = 4 };
+
+template <bool REWALK>
+__device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool active, Seq *out, const Seq *spec, uint32_t spec_cnt, const State &spec0,
+                                               const State &spec_exit, uint32_t *sync_k) {
+  uint32_t cnt = 0, k = 0;
+  State sp = spec0;
+  uint32_t mode = (active && st.ip < K.lim) ? W_DECIDE : W_DONE;
+  uint32_t s = 0, off = 0, len = 0, q = 0;
+  bool synced = false;
+  while (__any_sync(0xffffffffu, mode != W_DONE)) {
+    if (mode == W_DECIDE) {
+      const uint32_t ip = st.ip;
+      const bool has1 = ip + 1 < K.lim;
+      const uint32_t e0 = K.R[ip], e1 = has1 ? K.R[ip + 1] : 0u;
+      const uint64_t v0 = rd64(K.in, ip);
+      const uint32_t nxt = has1 ? rd8(K.in, ip + 8) : 0u;
+      const bool behind = ip == st.anchor;
+      const bool try1 = behind && st.r1 != 0 && ip >= st.r1;
+      const bool try0a = st.r0 != 0 && ip >= st.r0 && !behind, try0b = st.r0 != 0 && ip + 1 >= st.r0 && has1;
+      uint64_t y = 0, x0 = 0;
+      if (try1) y = rd64(K.in, ip - st.r1);
+      // one load pair serves the repeat-offset checks at ip and ip + 1 when both are in range
+      if (try0a) x0 = rd64(K.in, ip - st.r0);
+      uint64_t x1 = 0;
+      if (try0b) x1 = try0a ? ((x0 >> 8) | ((uint64_t)rd8(K.in, ip - st.r0 + 8) << 56)) : rd64(K.in, ip + 1 - st.r0);
+      const uint64_t v1 = (v0 >> 8) | ((uint64_t)nxt << 56);
+      const uint32_t lt0 = e0 >> 17;
+      bool found = false;
+      if (try1) {
+        const uint32_t c = common8(v0, y);
+        if (c >= 4 && (c == 8 || c + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r1; len = c; mode = c == 8 ? W_EXT : W_BACK; found = true; }
+      }
+      if (!found) {
+        const uint32_t rl0 = try0a ? common8(v0, x0) : 0u, rl1 = try0b ? common8(v1, x1) : 0u;
+        const bool t0 = e0 != 0, r0ok = rl0 >= 4, r1ok = rl1 >= 4;
+        if (!t0 && !r0ok && !r1ok) { mode = W_SKIP; q = ip + 1; }
+        else {
+          bool open;
+          if (r0ok && (!t0 || rl0 == 8 || rl0 + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r0; len = rl0; open = rl0 == 8; }
+          else if (r1ok && (!t0 || rl1 == 8 || rl1 + LZ_REP_BONUS >= lt0)) { s = ip + 1; off = st.r0; len = rl1; open = rl1 == 8; }
+          else {
+            uint32_t e = e0;
+            s = ip;
+            if (K.lazy && (e1 >> 17) > lt0) { e = e1; s = ip + 1; }
+            off = e & LZ_OFF_MASK; len = e >> 17; open = len == LZ_LCAP;
+          }
+          mode = open ? W_EXT : W_BACK;
+        }
+      }
+    }
+    if (mode == W_SKIP) {
+      // next position >= q with a table candidate, one bitmap word per turn
+      const uint32_t word = K.map[q >> 5] & (0xFFFFFFFFu << (q & 31));
+      q = word ? (q & ~31u) + (uint32_t)(__ffs((int)word) - 1) : (q | 31u) + 1;
+      if (word || q >= K.lim) { st.ip = min(q, K.lim); mode = st.ip < K.lim ? W_DECIDE : W_DONE; }
+    }
+    if (mode == W_EXT) {
+      const uint32_t a = s + len;
+      if (a + 16 <= K.n) {
+        const uint64_t p0 = rd64(K.in, a), p1 = rd64(K.in, a + 8), c0 = rd64(K.in, a - off), c1 = rd64(K.in, a + 8 - off);
+        uint32_t c = common8(p0, c0);
+        if (c == 8) c += common8(p1, c1);
+        len += c;
+        if (c < 16) mode = W_BACK;
+      } else {
+        if (a + 8 <= K.n) { const uint32_t c = common8(rd64(K.in, a), rd64(K.in, a - off)); len += c; if (c == 8) { while (s + len < K.n && rd8(K.in, s + len) == rd8(K.in, s + len - off)) len++; } }
+        else while (s + len < K.n && rd8(K.in, s + len) == rd8(K.in, s + len - off)) len++;
+        mode = W_BACK;
+      }
+    }
+    if (mode == W_BACK) {
+      // backward extension into the pending literals, then the sequence is complete
+      uint32_t room = min(min(LZ_BACK_MAX, s - st.anchor), s >= off ? s - off : 0u);
+      uint32_t nb = 0;
+      if (room) {
+        if (s >= off + 8) {
+          const uint64_t x = rd64(K.in, s - 8) ^ rd64(K.in, s - 8 - off);
+          const uint32_t xh = (uint32_t)(x >> 32), xl = (uint32_t)x;
+          nb = xh ? (uint32_t)__clz((int)xh) >> 3 : xl ? 4u + ((uint32_t)__clz((int)xl) >> 3) : 8u;
+          nb = min(nb, room);
+        } else while (nb < room && rd8(K.in, s - nb - 1) == rd8(K.in, s - nb - 1 - off)) nb++;
+      }
+      s -= nb; len += nb;
+      const uint32_t code = code_offset(off, s == st.anchor, st.r0, st.r1, st.r2);
+      out[cnt++] = pack_seq(s, len, code);
+      st.ip = st.anchor = s + len;
+      mode = st.ip < K.lim ? W_DECIDE : W_DONE;
+      if (REWALK) {
+        while (k < spec_cnt) {
+          const Seq e = spec[k];
+          const uint32_t es = seq_start(e), ee = es + seq_len(e);
+          if (ee > st.anchor) break;
+          decode_offset(seq_code(e), es == sp.anchor, sp.r0, sp.r1, sp.r2);
+          sp.ip = sp.anchor = ee;
+          k++;
+          if (ee == st.anchor) break;
+        }
+        if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && sp.r2 == st.r2 && k > 0) { synced = true; mode = W_DONE; }
+      }
+    }
+  }
+  if (REWALK && active) {
+    *sync_k = synced ? k : spec_cnt;
+    if (synced) st = spec_exit;
+  }
+  return cnt;
+}
+
 __global__ void __launch_bounds__(32 * SEL_WARPS) zstd_lz_select_kernel(SelArgs S) {
   const int lane = threadIdx.x & 31;
   const uint32_t idx = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
@@ -278,37 +403,36 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) zstd_lz_select_kernel(SelArgs 
   const uint32_t item = S.wave_base + idx;
   uint8_t *const slot = S.slots + (size_t)idx * S.slot_bytes;
   if (reinterpret_cast<const BlockHdr *>(slot)->kind != KIND_PARSED) return;
-  const uint8_t *const in = (const uint8_t *)S.A.in_ptrs[item];
   const uint32_t bn = (uint32_t)S.A.in_sizes[item];
   const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
-  const uint32_t *const R = reinterpret_cast<const uint32_t *>(slot + slot_r_off());
   const uint32_t cap = lane_list_cap(S.slot_block_max);
   Seq *const spec = reinterpret_cast<Seq *>(slot + slot_spec_off(S.slot_block_max)) + (size_t)lane * cap;
   Seq *const prefix = reinterpret_cast<Seq *>(slot + slot_pre_off(S.slot_block_max)) + (size_t)lane * cap;
-  const SelectParams SP{S.lazy};
   const uint32_t span = lane_span(ilimit);
   const uint32_t B = lane_begin((uint32_t)lane, span, ilimit), E = lane_begin((uint32_t)lane + 1, span, ilimit);
+  Walker K;
+  K.in = (const uint8_t *)S.A.in_ptrs[item];
+  K.R = reinterpret_cast<const uint32_t *>(slot + slot_r_off(S.slot_block_max));
+  K.map = reinterpret_cast<const uint32_t *>(slot + slot_map_off());
+  K.n = bn; K.lim = E; K.lazy = S.lazy;
   // the history a decoder holds at the start of the block: the format's initial one, unless the block is coded on its
   // own inside a larger frame (block mode), where it is unknown (0 never matches and is never written as a repeat code)
   State st{B, B, 0, 0, 0};
   if (lane == 0 && !(S.A.block_mode != 0 && item != 0)) { st.r0 = 1; st.r1 = 4; st.r2 = 8; }
   const State spec0 = st;
-  const uint32_t spec_cnt = select_walk(in, bn, R, E, SP, st, spec);
+  uint32_t sync_k = 0;
+  const uint32_t spec_cnt = walk_lanes<false>(K, st, true, spec, nullptr, 0, spec0, spec0, &sync_k);
   const State spec_exit = st;
   State exit_state = st, entry_used = spec0;
-  uint32_t pre_cnt = 0, sync_k = 0;
-  __syncwarp();
+  uint32_t pre_cnt = 0;
+  sync_k = 0;
   for (;;) {
     const State entry = shfl_up_state(exit_state);
-    bool changed = false;
-    if (lane > 0 && !entry.same(entry_used)) {
-      entry_used = entry;
-      State s2 = entry;
-      pre_cnt = select_rewalk(in, bn, R, E, SP, s2, spec, spec_cnt, spec0, spec_exit, prefix, &sync_k);
-      if (!s2.same(exit_state)) { exit_state = s2; changed = true; }
-    }
-    __syncwarp();
-    if (!__any_sync(0xffffffffu, changed)) break;
+    const bool need = lane > 0 && !entry.same(entry_used);
+    if (!__any_sync(0xffffffffu, need)) break;
+    State s2 = entry;
+    const uint32_t c = walk_lanes<true>(K, s2, need, prefix, spec, spec_cnt, spec0, spec_exit, &sync_k);
+    if (need) { entry_used = entry; pre_cnt = c; exit_state = s2; }
   }
   LaneHdr h;
   h.spec_cnt = (uint16_t)spec_cnt; h.sync_k = (uint16_t)sync_k; h.pre_cnt = (uint16_t)pre_cnt; h.pad = 0;
