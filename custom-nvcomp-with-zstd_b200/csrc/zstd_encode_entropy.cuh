@@ -13,9 +13,9 @@ using namespace enc;
 // Entropy stage of one block, warp-parallel.  Produces exactly the bytes of enc::encode_block_payload
 // (the serial form the host model runs): histograms by shared-memory atomics across 32 lanes, the 4
 // Huffman streams cut into one piece per lane at bit offsets known from a bit-count pre-pass, the three FSE state
-// chains on 3 lanes fed by shuffles (state bits parked in the spare high bits of the sequence arrays), and the interleaved
-// sequence bitstream assembled by all lanes: each lane packs a contiguous run of sequences into
-// 32-bit words at a bit offset known from a prefix sum (atomicOr only for the two words it shares).
+// chains on 3 lanes, 32 sequences per round with the codes staged in shared memory, and the interleaved sequence
+// bitstream assembled by all lanes: each lane ORs the bits of its own sequence into a shared-memory staging buffer at a
+// bit offset known from a prefix sum, completed words leave with coalesced stores.
 // The table builders (Huffman lengths, FSE normalisation / CTable) stay on lane 0.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
@@ -189,20 +189,22 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
   if (nseq == 0) return op;
   const uint32_t modes_pos = op++;
   uint32_t modes = 0;
+  // one pass over the sequences for the three code histograms (W.count[0..63] LL, [64..127] OF, [128..191] ML)
+  for (int i = lane; i < 192; i += 32) W.count[i] = 0;
+  __syncwarp();
+  uint32_t mx = 0;
+  for (uint32_t i = lane; i < nseq; i += 32) {
+    const uint32_t c0 = ll_code(sll[i]), c1 = (uint32_t)hb32(sofv[i]), c2 = ml_code(sml[i]);
+    atomicAdd(&W.count[c0], 1u); atomicAdd(&W.count[64 + c1], 1u); atomicAdd(&W.count[128 + c2], 1u);
+    mx = max(mx & 0xFF, c0) | (max((mx >> 8) & 0xFF, c1) << 8) | (max(mx >> 16, c2) << 16);
+  }
+  uint32_t mx0 = warp_max_u32(mx & 0xFF), mx1 = warp_max_u32((mx >> 8) & 0xFF), mx2 = warp_max_u32(mx >> 16);
+  __syncwarp();
   for (int kind = 0; kind < 3; kind++) {
-    for (int i = lane; i < 64; i += 32) W.count[i] = 0;
-    __syncwarp();
-    uint32_t mx = 0;
-    for (uint32_t i = lane; i < nseq; i += 32) {
-      const uint32_t c = kind == 0 ? ll_code(sll[i]) : kind == 1 ? (uint32_t)hb32(sofv[i]) : ml_code(sml[i]);
-      atomicAdd(&W.count[c], 1u);
-      mx = max(mx, c);
-    }
-    const int maxc = (int)warp_max_u32(mx);
-    __syncwarp();
+    const int maxc = (int)(kind == 0 ? mx0 : kind == 1 ? mx1 : mx2);
     int mode = 0;
     uint32_t desc = 0;
-    if (lane == 0) mode = seq_table_prepare(W, kind, W.count, maxc, nseq, dst + op, cap - op, &desc);
+    if (lane == 0) mode = seq_table_prepare(W, kind, W.count + 64 * kind, maxc, nseq, dst + op, cap - op, &desc);
     mode = __shfl_sync(0xffffffffu, mode, 0);
     desc = __shfl_sync(0xffffffffu, desc, 0);
     __syncwarp();
@@ -211,32 +213,49 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
     modes |= (uint32_t)mode << (6 - 2 * kind);
   }
   if (lane == 0) dst[modes_pos] = (uint8_t)modes;
-  // ---- the three FSE state chains, one lane each: state bits parked above the 18-bit values ----
+  __syncwarp();
+  // ---- the interleaved bitstream, 32 sequences per round, last sequence first ----
+  // Every lane loads one sequence and computes its codes; the codes are staged in shared memory and the three FSE state
+  // chains (lanes 0: LL, 1: OF, 2: ML) walk them, leaving "bits | count << 9" per sequence; then every lane assembles the
+  // bits of its own sequence, a prefix sum places them, they are OR-ed into a staging buffer in shared memory and the
+  // completed words leave with coalesced stores.  W.count is free by now: [0..95] chain output, [96..127] codes,
+  // [128..223] staging.
   const int log_ll = W.tab_log[0], log_of = W.tab_log[1], log_ml = W.tab_log[2];
-  // Rounds of 32 sequences, last sequence first: every lane loads one sequence and computes its three codes; the codes
-  // are handed to the chain lanes (0: LL, 1: OF, 2: ML) one sequence at a time by shuffle, so the serial part of a step is
-  // two shared-memory lookups and no global access; what a chain emits for a sequence (bits | count << 9) comes back
-  // through W.count, which is free by now.
+  uint32_t *const park = W.count, *const codes = W.count + 96, *const stage = W.count + 128;
+  uint8_t *const sp = dst + op;
+  uint32_t *const w32 = reinterpret_cast<uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
+  const uint32_t lead = (uint32_t)((uintptr_t)sp & 3);
+  const uint32_t cap_stream = cap - op >= 3 ? cap - op - 3 : 0;
+  const uint32_t word_limit = (lead + cap_stream + 3) >> 2;            // words that may be written (the caller's buffer has this slack)
+  uint32_t carry = lead ? (*w32 & ((1u << (8 * lead)) - 1u)) : 0u;     // bytes in front of the stream inside its first word
+  uint32_t carry_bits = 8 * lead, wbase = 0;
+  unsigned long long total_bits = 0;
+  bool overflow = false;
   uint32_t fin = 0;
   {
     const int t = lane < 3 ? lane : 0;
     const int log = W.tab_log[t];
     const uint16_t *st = W.state_tab(t);
     const SymTT *tt = W.tt[t];
-    uint32_t *const park = W.count;                    // [3][32]
     uint32_t state = 0;
+    uint32_t na = 0, nb_ = 0, nc = 1;
+    if ((uint32_t)lane < nseq) { const uint32_t i = nseq - 1 - (uint32_t)lane; na = sll[i]; nb_ = sml[i]; nc = sofv[i]; }
     for (uint32_t base = 0; base < nseq; base += 32) {
       const uint32_t kk = base + (uint32_t)lane;       // stream order: k = 0 is the last sequence
       const bool valid = kk < nseq;
-      const uint32_t i = valid ? nseq - 1 - kk : 0;
-      uint32_t a = 0, b = 0, c = 1;
-      if (valid) { a = sll[i]; b = sml[i]; c = sofv[i]; }
-      const uint32_t pk = ll_code(a) | ((uint32_t)hb32(c) << 8) | (ml_code(valid ? b : 3u) << 16);
+      const uint32_t a = na, b = nb_, c = nc;
+      {
+        const uint32_t kn = kk + 32;                   // next round's sequence, in flight during this round
+        if (kn < nseq) { const uint32_t i = nseq - 1 - kn; na = sll[i]; nb_ = sml[i]; nc = sofv[i]; }
+      }
+      const uint32_t llc = ll_code(a), ofc = (uint32_t)hb32(c), mlc = ml_code(valid ? b : 3u);
+      codes[lane] = llc | (ofc << 8) | (mlc << 16);
+      stage[lane] = 0; stage[32 + lane] = 0; stage[64 + lane] = 0;
+      __syncwarp();
       const uint32_t nv = min(32u, nseq - base);
-      for (uint32_t j = 0; j < nv; j++) {
-        const uint32_t x = __shfl_sync(0xffffffffu, pk, (int)j);
-        if (lane < 3 && log) {
-          const uint32_t code = (x >> (8 * t)) & 0xFF;
+      if (lane < 3 && log) {
+        for (uint32_t j = 0; j < nv; j++) {
+          const uint32_t code = (codes[j] >> (8 * t)) & 0xFF;
           if (base + j == 0) state = fse_init_state(st, tt, code);
           else {
             const SymTT e = tt[code];
@@ -246,95 +265,74 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
           }
         }
       }
+      if (lane == 0) stage[0] = carry;
       __syncwarp();
-      if (valid && kk > 0) {
-        if (log_ll) { const uint32_t v = park[lane]; sll[i] = a | ((v & 0x1FF) << 18) | ((v >> 9) << 27); }
-        if (log_of) { const uint32_t v = park[32 + lane]; sofv[i] = c | ((v & 0x1FF) << 18) | ((v >> 9) << 27); }
-        if (log_ml) { const uint32_t v = park[64 + lane]; sml[i] = b | ((v & 0x1FF) << 18) | ((v >> 9) << 27); }
+      // bits of my sequence: [OF state][ML state][LL state] (not for the very first), LL extra, ML extra, OF extra
+      uint64_t lo = 0, hi = 0;
+      uint32_t nlo = 0, nhi = 0;
+      if (valid) {
+        if (kk > 0) {
+          if (log_of) { const uint32_t v = park[32 + lane]; lo |= (uint64_t)(v & 0x1FF) << nlo; nlo += v >> 9; }
+          if (log_ml) { const uint32_t v = park[64 + lane]; lo |= (uint64_t)(v & 0x1FF) << nlo; nlo += v >> 9; }
+          if (log_ll) { const uint32_t v = park[lane]; lo |= (uint64_t)(v & 0x1FF) << nlo; nlo += v >> 9; }
+        }
+        lo |= (uint64_t)(a - ll_base(llc)) << nlo; nlo += ll_xbits(llc);
+        hi = (uint64_t)(b - ml_base(mlc)); nhi = ml_xbits(mlc);
+        hi |= (uint64_t)(c - (1u << ofc)) << nhi; nhi += ofc;
+      }
+      const uint32_t mine = nlo + nhi;
+      uint32_t incl = mine;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+      const uint32_t round_bits = __shfl_sync(0xffffffffu, incl, 31);
+      if (valid) {
+        uint32_t pos = carry_bits + incl - mine;
+        if (nlo) {
+          const uint32_t wi = pos >> 5, sh = pos & 31;
+          const uint64_t x = lo << sh;                                    // nlo <= 42: up to 73 bits
+          atomicOr(&stage[wi], (uint32_t)x);
+          if (sh + nlo > 32) atomicOr(&stage[wi + 1], (uint32_t)(x >> 32));
+          if (sh + nlo > 64) atomicOr(&stage[wi + 2], (uint32_t)(lo >> (64 - sh)));
+        }
+        pos += nlo;
+        if (nhi) {
+          const uint32_t wi = pos >> 5, sh = pos & 31;
+          const uint64_t x = hi << sh;                                    // nhi <= 33: up to 64 bits
+          atomicOr(&stage[wi], (uint32_t)x);
+          if (sh + nhi > 32) atomicOr(&stage[wi + 1], (uint32_t)(x >> 32));
+        }
       }
       __syncwarp();
+      const uint32_t have = carry_bits + round_bits, full = have >> 5;
+      if (wbase + full > word_limit) overflow = true;
+      else for (uint32_t j = lane; j < full; j += 32) w32[wbase + j] = stage[j];
+      carry = stage[full];
+      carry_bits = have & 31;
+      wbase += full;
+      total_bits += round_bits;
+      __syncwarp();
+      if (overflow) break;
     }
     if (lane < 3) fin = state;
   }
   const uint32_t fin_ll = __shfl_sync(0xffffffffu, fin, 0), fin_of = __shfl_sync(0xffffffffu, fin, 1), fin_ml = __shfl_sync(0xffffffffu, fin, 2);
-  __syncwarp();
-  // ---- bit budget of every lane's run (stream order k = nseq-1-i), prefix sum, capacity check ----
-  const uint32_t R = (nseq + 31) / 32;
-  const uint32_t k_lo = min(nseq, (uint32_t)lane * R), k_hi = min(nseq, k_lo + R);
-  uint32_t my_bits = 0;
-  for (uint32_t k = k_lo; k < k_hi; k++) {
-    const uint32_t i = nseq - 1 - k;
-    const uint32_t a = sll[i], b = sml[i], c = sofv[i];
-    my_bits += ll_xbits(ll_code(a & SEQ_VAL_MASK)) + ml_xbits(ml_code(b & SEQ_VAL_MASK)) + (uint32_t)hb32(c & SEQ_VAL_MASK);
-    my_bits += (a >> 27) + (b >> 27) + (c >> 27);                   // zero for the first sequence in stream order
-  }
-  uint32_t incl = my_bits;
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  const uint32_t start_bit = incl - my_bits, body_bits = __shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t total_bits = body_bits + (uint32_t)(log_ml + log_of + log_ll) + 1;
-  const uint32_t nbytes = (total_bits + 7) >> 3;
-  if (nbytes > (cap - op >= 3 ? cap - op - 3 : 0)) return 0;
-  // zero the words the stream will be OR-ed / stored into (not the bytes before it in the first word)
-  uint8_t *sp = dst + op;
-  uint32_t *const w32 = reinterpret_cast<uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
-  const uint32_t lead = (uint32_t)((uintptr_t)sp & 3);
-  {
-    // exactly the words the stream touches: word 0 only from byte `lead` on (earlier bytes hold table descriptions)
-    const uint32_t last_word = (lead * 8 + total_bits - 1) >> 5;
-    const uint32_t head = (4 - lead) & 3;
-    if ((uint32_t)lane < head) sp[lane] = 0;
-    uint32_t *z = w32 + (lead ? 1 : 0);
-    const uint32_t words = lead ? last_word : last_word + 1;
-    for (uint32_t k = lane; k < words; k += 32) z[k] = 0;
-  }
-  __syncwarp();
-  // ---- every lane packs its run ----
-  {
-    uint32_t bitpos = lead * 8 + start_bit;
-    uint32_t wi = bitpos >> 5;
-    uint64_t acc = 0;
-    uint32_t nacc = bitpos & 31;
-    bool first = true;
-    auto put = [&](uint32_t v, uint32_t k) {
-      acc |= (uint64_t)v << nacc;
-      nacc += k;
-      if (nacc >= 32) {
-        if (first) { atomicOr(w32 + wi, (uint32_t)acc); first = false; } else w32[wi] = (uint32_t)acc;
-        wi++; acc >>= 32; nacc -= 32;
-      }
-    };
-    for (uint32_t k = k_lo; k < k_hi; k++) {
-      const uint32_t i = nseq - 1 - k;
-      const uint32_t a = sll[i], b = sml[i], c = sofv[i];
-      const uint32_t ll = a & SEQ_VAL_MASK, ml = b & SEQ_VAL_MASK, ofv = c & SEQ_VAL_MASK;
-      const uint32_t llc = ll_code(ll), mlc = ml_code(ml), ofc = (uint32_t)hb32(ofv);
-      if (k > 0) {
-        put((c >> 18) & 0x1FF, c >> 27);
-        put((b >> 18) & 0x1FF, b >> 27);
-        put((a >> 18) & 0x1FF, a >> 27);
-      }
-      put(ll - ll_base(llc), ll_xbits(llc));
-      put(ml - ml_base(mlc), ml_xbits(mlc));
-      put(ofv - (1u << ofc), ofc);
-    }
-    if (nacc > 0 && k_hi > k_lo) atomicOr(w32 + wi, (uint32_t)acc);
-  }
-  __syncwarp();
+  if (overflow) return 0;
+  const uint32_t tail_bits = (uint32_t)(log_ml + log_of + log_ll) + 1;
+  const unsigned long long all_bits = total_bits + tail_bits;
+  const uint32_t nbytes = (uint32_t)((all_bits + 7) >> 3);
+  if (nbytes > cap_stream) return 0;
   if (lane == 0) {
-    // final states (ML, OF, LL) and the end mark
+    // final states (ML, OF, LL) and the end mark behind the carried partial word
     uint64_t tail = 0;
     uint32_t nb = 0;
     tail |= (uint64_t)(fin_ml & ((1u << log_ml) - 1u)) << nb; nb += (uint32_t)log_ml;
     tail |= (uint64_t)(fin_of & ((1u << log_of) - 1u)) << nb; nb += (uint32_t)log_of;
     tail |= (uint64_t)(fin_ll & ((1u << log_ll) - 1u)) << nb; nb += (uint32_t)log_ll;
     tail |= 1ull << nb; nb += 1;
-    const uint32_t bitpos = lead * 8 + body_bits;
-    const uint32_t sh = bitpos & 31;
-    uint32_t wi = bitpos >> 5;
-    // up to 28 + 31 bits: at most two words
-    const uint64_t lo = tail << sh;
-    atomicOr(w32 + wi, (uint32_t)lo);
-    if ((lo >> 32) != 0) atomicOr(w32 + wi + 1, (uint32_t)(lo >> 32));
+    // carry_bits + nb <= 31 + 28 bits: the bytes that hold them are written one by one (nothing behind the stream is touched)
+    const uint64_t v = (uint64_t)carry | (tail << carry_bits);
+    const uint32_t end_byte = lead + nbytes;                           // offset of the stream's end from w32's first byte
+    uint8_t *const wb = reinterpret_cast<uint8_t *>(w32 + wbase);
+    for (uint32_t j = (wbase ? 0u : lead); wbase * 4 + j < end_byte; j++) wb[j] = (uint8_t)(v >> (8 * j));
   }
   __syncwarp();
   return op + nbytes;

@@ -521,8 +521,13 @@ __global__ void __launch_bounds__(32 * FIN_WARPS, 8) zstd_lz_finish_kernel(FinAr
           for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, sl_incl, o); if (lane >= o) sl_incl += t; }
           const uint32_t my_lit = nlit + sl_incl - ll;
           if (valid) { s_ll[nseq + lane] = ll; s_ml[nseq + lane] = ml; s_of[nseq + lane] = code; }
-          // literal runs: short ones by their own lane, long ones by the whole warp
-          if (valid && ll <= 8) for (uint32_t i = 0; i < ll; i++) lits[my_lit + i] = chunk[pe + i];
+          // literal runs: short ones by their own lane (one 8-byte read when the block has the room), long ones by the whole warp
+          if (valid && ll != 0 && ll <= 8) {
+            if (pe + 8 <= bn) {
+              const uint64_t v = rd64(chunk, pe);
+              for (uint32_t i = 0; i < ll; i++) lits[my_lit + i] = (uint8_t)(v >> (8 * i));
+            } else for (uint32_t i = 0; i < ll; i++) lits[my_lit + i] = chunk[pe + i];
+          }
           uint32_t big = __ballot_sync(0xffffffffu, valid && ll > 8);
           while (big) {
             const int src = __ffs((int)big) - 1;
