@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 // 8 bytes at byte offset `at` of the staged block (three aligned shared-memory words and two funnel shifts)
 __device__ __forceinline__ uint64_t lds64(const uint8_t *base16, uint32_t at) {
   const uint32_t *w = reinterpret_cast<const uint32_t *>(base16) + (at >> 2);
-  const uint32_t sh = (at & 3) * 8;
+  const uint32_t sh = at << 3;                       // the funnel shift takes it modulo 32
   const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
   return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 }
@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_match_kernel(EsdArgs
       uint32_t *const Mg = reinterpret_cast<uint32_t *>(slot + slot_map_off());
       auto rd = [&](uint32_t q) { return lds64(in_base, delta + q); };
       const int next_grp = (grp + 1) & (MATCH_GROUPS - 1);
+      constexpr uint32_t KEY_HMASK = (1u << LZ_KEY_HBITS) - 1u;
+      const uint32_t tkey = t << LZ_KEY_HBITS;
       for (uint32_t w = (uint32_t)grp; w < nwin; w += MATCH_GROUPS) {
         const uint32_t p = w * LZ_WIN + t;
         const bool act = p < ilimit;
@@ -229,28 +231,48 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_match_kernel(EsdArgs
         }
         // the window before this one must be in the tables
         if (w > 0) bar_sync(5 + grp, 2 * (int)LZ_WIN);
-        // phase 1: the state before this window, first-of-window side table
-        const uint32_t e1 = act ? tab1[h1] : 0u;
-        if (ins1) atomicMin(&first1[s1], first_key(w, t, h1));
+        // phase 1: the state before this window, first-of-window side table.  key = tag | t | low hash bits; my own
+        // key without t is what a same-hash entry of this window must equal outside the t field
+        const uint32_t tagw = (~w & 0x1FFu) << 23;
+        const uint32_t k1 = tagw | (h1 & KEY_HMASK), k2 = tagw | (h2 & KEY_HMASK);
+        const uint32_t e1 = tab1[h1];
+        if (ins1) atomicMin(&first1[s1], k1 | tkey);
         uint32_t e2 = 0;
         if (DFAST) {
-          e2 = act ? tab2[h2] : 0u;
-          if (ins2) atomicMin(&first2[s2], first_key(w, t, h2));
+          e2 = tab2[h2];
+          if (ins2) atomicMin(&first2[s2], k2 | tkey);
         }
         bar_sync(1 + grp, (int)LZ_WIN);
         // phase 2: inserts; the candidate is the first earlier position of this window with my hash, else the old entry
         if (ins1) atomicMax(&tab1[h1], p);
-        int32_t a1 = first_candidate(first1[s1], w, t, h1), a2 = -1;
+        const uint32_t x1 = first1[s1] ^ k1;
+        uint32_t x2 = 0;
         if (DFAST) {
           if (ins2) atomicMax(&tab2[h2], p);
-          a2 = first_candidate(first2[s2], w, t, h2);
+          x2 = first2[s2] ^ k2;
         }
         if (w + 1 < nwin) bar_arrive(5 + next_grp, 2 * (int)LZ_WIN);
-        // off the chain: verification
-        if (a1 < 0) a1 = e1 < p ? (int32_t)e1 : -1;
-        if (DFAST && a2 < 0) a2 = e2 < p ? (int32_t)e2 : -1;
-        const uint32_t r = act ? match_verify(rd, p, v, a2, a1, bn) : 0u;
-        if (act) Rg[p] = r;
+        // off the chain: verification (x = t' << KEY_HBITS exactly when the slot holds an earlier thread t' of this
+        // window with my hash bits; candidates at or beyond p never verify)
+        const uint32_t base_p = p - t;
+        const uint32_t c1 = (x1 < tkey && (x1 & KEY_HMASK) == 0) ? base_p + (x1 >> LZ_KEY_HBITS) : e1;
+        uint32_t r = 0;
+        if (act) {
+          uint32_t off = 0, len = 0;
+          const uint64_t y1 = rd(min(c1, p));
+          if (DFAST) {
+            const uint32_t c2 = (x2 < tkey && (x2 & KEY_HMASK) == 0) ? base_p + (x2 >> LZ_KEY_HBITS) : e2;
+            const uint64_t y2 = rd(min(c2, p));
+            if (c2 < p && y2 == v) { off = p - c2; len = 8; }
+          }
+          if (len == 0 && c1 < p) {
+            const uint32_t c = common8(v, y1);
+            if (c >= LZ_MIN_MATCH) { off = p - c1; len = c; }
+          }
+          if (len == 8 && p + 16 <= bn) len += common8(rd(p + 8), rd(p + 8 - off));
+          r = len ? (off | (len << 17)) : 0u;
+          Rg[p] = r;
+        }
         const uint32_t any = __ballot_sync(0xffffffffu, r != 0);
         if (lane == 0) Mg[p >> 5] = any;
       }
