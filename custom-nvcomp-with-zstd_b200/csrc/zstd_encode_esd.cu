@@ -309,7 +309,7 @@ struct Walker {
   uint32_t n, lim;
   int lazy;
 };
-enum : uint32_t { W_DECIDE = 0, W_SKIP = 1, W_EXT = 2, W_BACK = 3, W_DONE = 4 };
+enum : uint32_t { W_DECIDE = 0, W_SKIP = 1, W_MATCH = 2, W_DONE = 3 };
 
 template <bool REWALK>
 __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool active, Seq *out, const Seq *spec, uint32_t spec_cnt, const State &spec0,
@@ -317,13 +317,16 @@ __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool 
   uint32_t cnt = 0, k = 0;
   State sp = spec0;
   uint32_t mode = (active && st.ip < K.lim) ? W_DECIDE : W_DONE;
-  uint32_t s = 0, off = 0, len = 0, q = 0;
-  bool synced = false;
+  uint32_t s = 0, off = 0, len = 0, q = 0, nb = 0;
+  bool synced = false, open = false, back_done = false;
   while (__any_sync(0xffffffffu, mode != W_DONE)) {
+    // ---- decide: every load of the decision is independent of the others (one round trip), the bitmap word that a
+    //      literal skip would need included ----
     if (mode == W_DECIDE) {
       const uint32_t ip = st.ip;
       const bool has1 = ip + 1 < K.lim;
       const uint32_t e0 = K.R[ip], e1 = has1 ? K.R[ip + 1] : 0u;
+      const uint32_t mw = K.map[(ip + 1) >> 5];
       const uint64_t v0 = rd64(K.in, ip);
       const uint32_t nxt = has1 ? rd8(K.in, ip + 8) : 0u;
       const bool behind = ip == st.anchor;
@@ -340,14 +343,19 @@ __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool 
       bool found = false;
       if (try1) {
         const uint32_t c = common8(v0, y);
-        if (c >= 4 && (c == 8 || c + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r1; len = c; mode = c == 8 ? W_EXT : W_BACK; found = true; }
+        if (c >= 4 && (c == 8 || c + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r1; len = c; open = c == 8; found = true; }
       }
       if (!found) {
         const uint32_t rl0 = try0a ? common8(v0, x0) : 0u, rl1 = try0b ? common8(v1, x1) : 0u;
         const bool t0 = e0 != 0, r0ok = rl0 >= 4, r1ok = rl1 >= 4;
-        if (!t0 && !r0ok && !r1ok) { mode = W_SKIP; q = ip + 1; }
-        else {
-          bool open;
+        if (!t0 && !r0ok && !r1ok) {
+          // literals: on to the next position with a table candidate; the first bitmap word is already here
+          q = ip + 1;
+          const uint32_t word = mw & (0xFFFFFFFFu << (q & 31));
+          q = word ? (q & ~31u) + (uint32_t)(__ffs((int)word) - 1) : (q | 31u) + 1;
+          if (word || q >= K.lim) { st.ip = min(q, K.lim); mode = st.ip < K.lim ? W_DECIDE : W_DONE; }
+          else mode = W_SKIP;
+        } else {
           if (r0ok && (!t0 || rl0 == 8 || rl0 + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r0; len = rl0; open = rl0 == 8; }
           else if (r1ok && (!t0 || rl1 == 8 || rl1 + LZ_REP_BONUS >= lt0)) { s = ip + 1; off = st.r0; len = rl1; open = rl1 == 8; }
           else {
@@ -356,58 +364,66 @@ __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool 
             if (K.lazy && (e1 >> 17) > lt0) { e = e1; s = ip + 1; }
             off = e & LZ_OFF_MASK; len = e >> 17; open = len == LZ_LCAP;
           }
-          mode = open ? W_EXT : W_BACK;
+          found = true;
         }
       }
-    }
-    if (mode == W_SKIP) {
+      if (found) { mode = W_MATCH; back_done = false; }
+    } else if (mode == W_SKIP) {
       // next position >= q with a table candidate, one bitmap word per turn
       const uint32_t word = K.map[q >> 5] & (0xFFFFFFFFu << (q & 31));
       q = word ? (q & ~31u) + (uint32_t)(__ffs((int)word) - 1) : (q | 31u) + 1;
       if (word || q >= K.lim) { st.ip = min(q, K.lim); mode = st.ip < K.lim ? W_DECIDE : W_DONE; }
     }
-    if (mode == W_EXT) {
+    // ---- a match in hand: the loads of its forward extension (16 bytes per turn) and of its backward extension leave
+    //      together; the sequence is emitted in the turn its forward extension ends ----
+    if (mode == W_MATCH) {
       const uint32_t a = s + len;
-      if (a + 16 <= K.n) {
-        const uint64_t p0 = rd64(K.in, a), p1 = rd64(K.in, a + 8), c0 = rd64(K.in, a - off), c1 = rd64(K.in, a + 8 - off);
-        uint32_t c = common8(p0, c0);
-        if (c == 8) c += common8(p1, c1);
-        len += c;
-        if (c < 16) mode = W_BACK;
-      } else {
-        if (a + 8 <= K.n) { const uint32_t c = common8(rd64(K.in, a), rd64(K.in, a - off)); len += c; if (c == 8) { while (s + len < K.n && rd8(K.in, s + len) == rd8(K.in, s + len - off)) len++; } }
-        else while (s + len < K.n && rd8(K.in, s + len) == rd8(K.in, s + len - off)) len++;
-        mode = W_BACK;
+      const bool fast = open && a + 16 <= K.n;
+      uint64_t p0 = 0, p1 = 0, c0 = 0, c1 = 0, b0 = 0, b1 = 0;
+      const uint32_t room = back_done ? 0u : min(min(LZ_BACK_MAX, s - st.anchor), s >= off ? s - off : 0u);
+      const bool back8 = room != 0 && s >= off + 8;
+      if (fast) { p0 = rd64(K.in, a); p1 = rd64(K.in, a + 8); c0 = rd64(K.in, a - off); c1 = rd64(K.in, a + 8 - off); }
+      if (back8) { b0 = rd64(K.in, s - 8); b1 = rd64(K.in, s - 8 - off); }
+      if (open) {
+        if (fast) {
+          uint32_t c = common8(p0, c0);
+          if (c == 8) c += common8(p1, c1);
+          len += c;
+          if (c < 16) open = false;
+        } else {
+          if (a + 8 <= K.n) { const uint32_t c = common8(rd64(K.in, a), rd64(K.in, a - off)); len += c; if (c == 8) { while (s + len < K.n && rd8(K.in, s + len) == rd8(K.in, s + len - off)) len++; } }
+          else while (s + len < K.n && rd8(K.in, s + len) == rd8(K.in, s + len - off)) len++;
+          open = false;
+        }
       }
-    }
-    if (mode == W_BACK) {
-      // backward extension into the pending literals, then the sequence is complete
-      uint32_t room = min(min(LZ_BACK_MAX, s - st.anchor), s >= off ? s - off : 0u);
-      uint32_t nb = 0;
-      if (room) {
-        if (s >= off + 8) {
-          const uint64_t x = rd64(K.in, s - 8) ^ rd64(K.in, s - 8 - off);
+      if (!back_done) {
+        nb = 0;
+        if (back8) {
+          const uint64_t x = b0 ^ b1;
           const uint32_t xh = (uint32_t)(x >> 32), xl = (uint32_t)x;
           nb = xh ? (uint32_t)__clz((int)xh) >> 3 : xl ? 4u + ((uint32_t)__clz((int)xl) >> 3) : 8u;
           nb = min(nb, room);
         } else while (nb < room && rd8(K.in, s - nb - 1) == rd8(K.in, s - nb - 1 - off)) nb++;
+        back_done = true;
       }
-      s -= nb; len += nb;
-      const uint32_t code = code_offset(off, s == st.anchor, st.r0, st.r1, st.r2);
-      out[cnt++] = pack_seq(s, len, code);
-      st.ip = st.anchor = s + len;
-      mode = st.ip < K.lim ? W_DECIDE : W_DONE;
-      if (REWALK) {
-        while (k < spec_cnt) {
-          const Seq e = spec[k];
-          const uint32_t es = seq_start(e), ee = es + seq_len(e);
-          if (ee > st.anchor) break;
-          decode_offset(seq_code(e), es == sp.anchor, sp.r0, sp.r1, sp.r2);
-          sp.ip = sp.anchor = ee;
-          k++;
-          if (ee == st.anchor) break;
+      if (!open) {
+        s -= nb; len += nb;
+        const uint32_t code = code_offset(off, s == st.anchor, st.r0, st.r1, st.r2);
+        out[cnt++] = pack_seq(s, len, code);
+        st.ip = st.anchor = s + len;
+        mode = st.ip < K.lim ? W_DECIDE : W_DONE;
+        if (REWALK) {
+          while (k < spec_cnt) {
+            const Seq e = spec[k];
+            const uint32_t es = seq_start(e), ee = es + seq_len(e);
+            if (ee > st.anchor) break;
+            decode_offset(seq_code(e), es == sp.anchor, sp.r0, sp.r1, sp.r2);
+            sp.ip = sp.anchor = ee;
+            k++;
+            if (ee == st.anchor) break;
+          }
+          if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && sp.r2 == st.r2 && k > 0) { synced = true; mode = W_DONE; }
         }
-        if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && sp.r2 == st.r2 && k > 0) { synced = true; mode = W_DONE; }
       }
     }
   }
