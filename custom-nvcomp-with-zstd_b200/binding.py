@@ -46,6 +46,8 @@ EXPORTS = [
     "cuda_zstd_batch_get_compress_temp_size", "cuda_zstd_batch_get_decompress_temp_size", "cuda_zstd_batch_compress",
     "cuda_zstd_batch_decompress", "cuda_zstd_batch_compress_nosync", "cuda_zstd_batch_decompress_nosync",
     "cuda_zstd_batch_scan_sizes", "cuda_zstd_batch_pack", "cuda_zstd_batch_last_launch_count", "cuda_zstd_batch_error_string",
+    "cuda_zstd_batch_get_host_decompress_temp_size", "cuda_zstd_batch_get_host_compress_temp_size", "cuda_zstd_batch_decompress_host",
+    "cuda_zstd_batch_compress_host_packed",
     "cuda_zstd_create_manager", "cuda_zstd_destroy_manager", "cuda_zstd_compress", "cuda_zstd_decompress",
     "cuda_zstd_get_compress_workspace_size", "cuda_zstd_get_decompress_workspace_size", "cuda_zstd_train_dictionary",
     "cuda_zstd_destroy_dictionary", "cuda_zstd_set_dictionary", "cuda_zstd_get_error_string", "cuda_zstd_is_error",
@@ -98,6 +100,14 @@ def load_library() -> C.CDLL:
     for f in (lib.cuda_zstd_batch_compress_nosync, lib.cuda_zstd_batch_decompress_nosync):
         f.restype = i32
         f.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.cuda_zstd_batch_get_host_decompress_temp_size.restype = sz
+    lib.cuda_zstd_batch_get_host_decompress_temp_size.argtypes = [vp, vp, vp, sz]
+    lib.cuda_zstd_batch_get_host_compress_temp_size.restype = sz
+    lib.cuda_zstd_batch_get_host_compress_temp_size.argtypes = [vp, vp, sz]
+    lib.cuda_zstd_batch_decompress_host.restype = i32
+    lib.cuda_zstd_batch_decompress_host.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.cuda_zstd_batch_compress_host_packed.restype = i32
+    lib.cuda_zstd_batch_compress_host_packed.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, sz, vp]
     lib.cuda_zstd_batch_scan_sizes.restype = i32
     lib.cuda_zstd_batch_scan_sizes.argtypes = [vp, sz, u64, vp, vp]
     lib.cuda_zstd_batch_pack.restype = i32
@@ -224,6 +234,31 @@ class ZstdBatchCodec:
 
     def last_launch_count(self) -> int:
         return int(self.lib.cuda_zstd_batch_last_launch_count(self.h))
+
+    # ---- host-resident batches: payloads in (pinned) HOST memory, staged in waves by the library ----
+    def host_decompress_temp_size(self, comp_sizes: np.ndarray, caps: np.ndarray) -> int:
+        a, b = np.ascontiguousarray(comp_sizes, dtype=np.uint64), np.ascontiguousarray(caps, dtype=np.uint64)
+        return int(self.lib.cuda_zstd_batch_get_host_decompress_temp_size(self.h, a.ctypes.data, b.ctypes.data, len(a)))
+
+    def host_compress_temp_size(self, sizes: np.ndarray) -> int:
+        a = np.ascontiguousarray(sizes, dtype=np.uint64)
+        return int(self.lib.cuda_zstd_batch_get_host_compress_temp_size(self.h, a.ctypes.data, len(a)))
+
+    def decompress_host(self, h_in_ptrs: np.ndarray, in_sizes: np.ndarray, h_out_ptrs: np.ndarray, out_sizes: np.ndarray,
+                        workspace: torch.Tensor, statuses: Optional[np.ndarray] = None, stream=None) -> int:
+        """cuda_zstd_batch_decompress_host: all four tables are host uint64 arrays of HOST addresses; out_sizes is in/out."""
+        n = len(in_sizes)
+        return int(self.lib.cuda_zstd_batch_decompress_host(self.h, h_in_ptrs.ctypes.data, in_sizes.ctypes.data, n, h_out_ptrs.ctypes.data,
+                                                            out_sizes.ctypes.data, _addr(statuses), workspace.data_ptr(), workspace.numel(),
+                                                            _stream_handle(stream)))
+
+    def compress_host_packed(self, h_in_ptrs: np.ndarray, in_sizes: np.ndarray, h_packed, packed_cap: int, h_offsets: np.ndarray,
+                             workspace: torch.Tensor, statuses: Optional[np.ndarray] = None, stream=None) -> int:
+        """cuda_zstd_batch_compress_host_packed: frames packed back to back in h_packed, h_offsets[0..n] their exclusive scan."""
+        n = len(in_sizes)
+        return int(self.lib.cuda_zstd_batch_compress_host_packed(self.h, h_in_ptrs.ctypes.data, in_sizes.ctypes.data, n, _addr(h_packed), packed_cap,
+                                                                 h_offsets.ctypes.data, _addr(statuses), workspace.data_ptr(), workspace.numel(),
+                                                                 _stream_handle(stream)))
 
     # ---- tensor conveniences ----------------------------------------------------------------------
     def compress_chunks(self, data: torch.Tensor, chunk: int, workspace: Optional[torch.Tensor] = None

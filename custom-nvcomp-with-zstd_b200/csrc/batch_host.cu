@@ -1059,8 +1059,71 @@ std::vector<NvcompV5BenchmarkResult> benchmark_all_levels(const void *d_input, s
 using cuda_zstd::Status;
 using cuda_zstd::ZstdBatchManager;
 using cuda_zstd::nvcomp_v5::status_to_nvcomp_error;
+using cuda_zstd::u32;
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct cuda_zstd_batch { cuda_zstd::nvcomp_v5::NvcompV5BatchManager *m; };
+// streams and events of the host-resident batch calls (cuda_zstd_batch_*_host*), created on first use
+struct HostPipe {
+  static constexpr int MAX_WAVES = 4;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_entry = nullptr, ev_in[MAX_WAVES] = {}, ev_run[MAX_WAVES] = {}, ev_done = nullptr;
+  bool ready = false;
+  bool init() {
+    if (ready) return true;
+    bool ok = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ev_entry, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < MAX_WAVES && ok; i++)
+      ok = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev_run[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); return false; }
+    return ready = true;
+  }
+  ~HostPipe() {
+    if (!ready) return;
+    for (int i = 0; i < MAX_WAVES; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_run[i]); }
+    cudaEventDestroy(ev_entry); cudaEventDestroy(ev_done);
+    cudaStreamDestroy(s_in); cudaStreamDestroy(s_out);
+  }
+};
+struct cuda_zstd_batch { cuda_zstd::nvcomp_v5::NvcompV5BatchManager *m; HostPipe pipe; };
+
+namespace {
+// Host buffers of a batch usually sit back to back in a few large allocations: a RUN is a maximal stretch of items whose
+// host addresses ascend with gaps below 256 bytes, staged by ONE copy; the device image keeps every item's address
+// modulo 256.  Items that do not line up simply form runs of their own.
+struct HostRun { size_t first, count; const unsigned char *h_begin; size_t bytes; size_t d_off; };
+size_t plan_runs(const void *const *ptrs, const size_t *sizes, size_t lo, size_t hi, size_t d_off, std::vector<HostRun> &runs,
+                 std::vector<size_t> &item_off) {
+  size_t i = lo;
+  while (i < hi) {
+    const unsigned char *b = static_cast<const unsigned char *>(ptrs[i]);
+    const unsigned char *e = b + sizes[i];
+    size_t j = i + 1;
+    while (j < hi) {
+      const unsigned char *q = static_cast<const unsigned char *>(ptrs[j]);
+      if (q < e || (size_t)(q - e) >= 256) break;
+      e = q + sizes[j];
+      j++;
+    }
+    d_off = align_up(d_off, 256) + ((uintptr_t)b & 255);
+    runs.push_back(HostRun{i, j - i, b, (size_t)(e - b), d_off});
+    for (size_t k = i; k < j; k++) item_off[k] = d_off + (size_t)(static_cast<const unsigned char *>(ptrs[k]) - b);
+    d_off += (size_t)(e - b);
+    i = j;
+  }
+  return align_up(d_off, 256);
+}
+// chunk ranges of the pipeline waves: 1 : 2 : 4 : 9 sixteenths, so that the first results leave early
+int plan_waves(size_t n, size_t edges[HostPipe::MAX_WAVES + 1]) {
+  if (n < 1024) { edges[0] = 0; edges[1] = n; return 1; }
+  edges[0] = 0; edges[1] = n / 16; edges[2] = 3 * n / 16; edges[3] = 7 * n / 16; edges[4] = n;
+  return 4;
+}
+size_t staged_bytes_bound(const size_t *sizes, size_t n) {          // worst case of plan_runs: every item a run of its own
+  size_t t = 0;
+  for (size_t i = 0; i < n; i++) t += align_up(sizes[i], 256) + 512;
+  return t + 1024;
+}
+} // namespace
 
 extern "C" {
 
@@ -1155,6 +1218,166 @@ int cuda_zstd_batch_decompress_nosync(cuda_zstd_batch_t *b, const void *const *i
   if (!b) return 2;
   try {
     return status_to_nvcomp_error(b->m->batch_manager().impl()->run(false, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
+  } catch (...) { return 1; }
+}
+// ---- host-resident batches (include/cuda_zstd_batch_c.h): payloads in HOST memory, staged in waves over two copy
+// streams around the caller's stream; the codec calls are the device-table no-sync form ----
+size_t cuda_zstd_batch_get_host_decompress_temp_size(cuda_zstd_batch_t *b, const size_t *comp_sizes, const size_t *caps, size_t n) {
+  if (!b || !comp_sizes || !caps || n == 0) return 0;
+  return staged_bytes_bound(comp_sizes, n) + staged_bytes_bound(caps, n) + align_up(n * 40, 256) + 256 +
+         b->m->get_decompress_temp_size(comp_sizes, n);
+}
+size_t cuda_zstd_batch_get_host_compress_temp_size(cuda_zstd_batch_t *b, const size_t *sizes, size_t n) {
+  if (!b || !sizes || n == 0) return 0;
+  size_t frames = 0;
+  for (size_t i = 0; i < n; i++) frames += align_up(b->m->get_max_compressed_chunk_size(sizes[i]), 16);
+  return staged_bytes_bound(sizes, n) + 2 * align_up(frames, 256) + align_up(n * 40 + (n + 1) * 8, 256) + 256 +
+         b->m->get_compress_temp_size(sizes, n);
+}
+int cuda_zstd_batch_decompress_host(cuda_zstd_batch_t *b, const void *const *h_in, const size_t *in_sz, size_t n, void *const *h_out,
+                                    size_t *out_sz, uint32_t *h_status, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
+  if (!b) return 2;
+  if (n == 0) return 0;
+  if (!h_in || !in_sz || !h_out || !out_sz || !tmp) return 2;
+  try {
+    auto *I = b->m->batch_manager().impl();
+    std::lock_guard<std::mutex> lock(I->mu);
+    if (!b->pipe.init()) return 4;
+    HostPipe &P = b->pipe;
+    size_t edges[HostPipe::MAX_WAVES + 1];
+    const int nw = plan_waves(n, edges);
+    std::vector<HostRun> in_runs[HostPipe::MAX_WAVES], out_runs[HostPipe::MAX_WAVES];
+    std::vector<size_t> in_off(n), out_off(n);
+    size_t off = 0;
+    for (int w = 0; w < nw; w++) off = plan_runs(h_in, in_sz, edges[w], edges[w + 1], off, in_runs[w], in_off);
+    const size_t out_base = off;
+    for (int w = 0; w < nw; w++) off = plan_runs(h_out, out_sz, edges[w], edges[w + 1], off, out_runs[w], out_off);
+    const size_t tab_base = off, tab_bytes = align_up(n * 36, 256);
+    const size_t ws_base = tab_base + tab_bytes;
+    const size_t codec_need = b->m->get_decompress_temp_size(in_sz, n);
+    if (tmp_bytes < ws_base + codec_need) return 7;
+    unsigned char *d = static_cast<unsigned char *>(tmp);
+    (void)out_base;
+    // device-side tables: in_ptrs | in_sizes | out_ptrs | out_sizes | statuses
+    std::vector<unsigned long long> tab(4 * n);
+    for (size_t i = 0; i < n; i++) {
+      tab[i] = (unsigned long long)(uintptr_t)(d + in_off[i]); tab[n + i] = in_sz[i];
+      tab[2 * n + i] = (unsigned long long)(uintptr_t)(d + out_off[i]); tab[3 * n + i] = out_sz[i];
+    }
+    unsigned char *d_tab = d + tab_base;
+    u32 *d_status = reinterpret_cast<u32 *>(d_tab + 4 * n * 8);
+    cudaError_t e;
+    if ((e = cudaEventRecord(P.ev_entry, stream)) != cudaSuccess) return 4;
+    cudaStreamWaitEvent(P.s_in, P.ev_entry, 0);
+    cudaStreamWaitEvent(P.s_out, P.ev_entry, 0);
+    if ((e = cudaMemcpyAsync(d_tab, tab.data(), 4 * n * 8, cudaMemcpyHostToDevice, P.s_in)) != cudaSuccess) return 4;
+    int launches = 0;
+    Status overall = Status::SUCCESS;
+    for (int w = 0; w < nw; w++) {
+      const size_t lo = edges[w], m = edges[w + 1] - edges[w];
+      if (m == 0) continue;
+      for (const HostRun &r : in_runs[w])
+        if ((e = cudaMemcpyAsync(d + r.d_off, r.h_begin, r.bytes, cudaMemcpyHostToDevice, P.s_in)) != cudaSuccess) return 4;
+      cudaEventRecord(P.ev_in[w], P.s_in);
+      cudaStreamWaitEvent(stream, P.ev_in[w], 0);
+      Status s = I->run(false, reinterpret_cast<const void *const *>(d_tab) + lo, reinterpret_cast<const size_t *>(d_tab + n * 8) + lo, m,
+                        reinterpret_cast<void *const *>(d_tab + 2 * n * 8) + lo, reinterpret_cast<size_t *>(d_tab + 3 * n * 8) + lo, d_status + lo,
+                        true, d + ws_base, tmp_bytes - ws_base, stream, false, nullptr, nullptr);
+      if (s != Status::SUCCESS) overall = s;
+      launches += I->last_launches;
+      cudaEventRecord(P.ev_run[w], stream);
+      cudaStreamWaitEvent(P.s_out, P.ev_run[w], 0);
+      for (const HostRun &r : out_runs[w])
+        if ((e = cudaMemcpyAsync(const_cast<unsigned char *>(r.h_begin), d + r.d_off, r.bytes, cudaMemcpyDeviceToHost, P.s_out)) != cudaSuccess) return 4;
+    }
+    std::vector<u32> st(n);
+    cudaMemcpyAsync(out_sz, d_tab + 3 * n * 8, n * 8, cudaMemcpyDeviceToHost, P.s_out);
+    cudaMemcpyAsync(st.data(), d_status, n * 4, cudaMemcpyDeviceToHost, P.s_out);
+    cudaEventRecord(P.ev_done, P.s_out);
+    cudaStreamWaitEvent(stream, P.ev_done, 0);
+    if ((e = cudaStreamSynchronize(P.s_out)) != cudaSuccess) return 4;
+    I->last_launches = launches;
+    if (overall != Status::SUCCESS) return status_to_nvcomp_error(overall);
+    int rc = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (h_status) h_status[i] = st[i];
+      if (st[i] != 0 && rc == 0) rc = 1;
+    }
+    return rc;
+  } catch (...) { return 1; }
+}
+int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *b, const void *const *h_in, const size_t *in_sz, size_t n, void *h_packed,
+                                         size_t packed_cap, uint64_t *h_offsets, uint32_t *h_status, void *tmp, size_t tmp_bytes,
+                                         cudaStream_t stream) {
+  if (!b) return 2;
+  if (n == 0) return 0;
+  if (!h_in || !in_sz || !h_packed || !h_offsets || !tmp) return 2;
+  try {
+    auto *I = b->m->batch_manager().impl();
+    std::lock_guard<std::mutex> lock(I->mu);
+    if (!b->pipe.init()) return 4;
+    HostPipe &P = b->pipe;
+    size_t edges[HostPipe::MAX_WAVES + 1];
+    const int nw = plan_waves(n, edges);
+    std::vector<HostRun> in_runs[HostPipe::MAX_WAVES];
+    std::vector<size_t> in_off(n), caps(n), frame_off(n);
+    size_t off = 0;
+    for (int w = 0; w < nw; w++) off = plan_runs(h_in, in_sz, edges[w], edges[w + 1], off, in_runs[w], in_off);
+    size_t frames = 0;
+    for (size_t i = 0; i < n; i++) { caps[i] = b->m->get_max_compressed_chunk_size(in_sz[i]); frame_off[i] = frames; frames += align_up(caps[i], 16); }
+    const size_t frames_base = off, packed_base = frames_base + align_up(frames, 256);
+    const size_t tab_base = packed_base + align_up(frames, 256), tab_bytes = align_up(n * 36 + (n + 1) * 8, 256);
+    const size_t ws_base = tab_base + tab_bytes;
+    if (tmp_bytes < ws_base + b->m->get_compress_temp_size(in_sz, n)) return 7;
+    unsigned char *d = static_cast<unsigned char *>(tmp);
+    std::vector<unsigned long long> tab(4 * n);
+    for (size_t i = 0; i < n; i++) {
+      tab[i] = (unsigned long long)(uintptr_t)(d + in_off[i]); tab[n + i] = in_sz[i];
+      tab[2 * n + i] = (unsigned long long)(uintptr_t)(d + frames_base + frame_off[i]); tab[3 * n + i] = caps[i];
+    }
+    unsigned char *d_tab = d + tab_base;
+    u32 *d_status = reinterpret_cast<u32 *>(d_tab + 4 * n * 8);
+    uint64_t *d_offsets = reinterpret_cast<uint64_t *>(d_tab + align_up(n * 36, 8));
+    cudaError_t e;
+    if ((e = cudaEventRecord(P.ev_entry, stream)) != cudaSuccess) return 4;
+    cudaStreamWaitEvent(P.s_in, P.ev_entry, 0);
+    cudaStreamWaitEvent(P.s_out, P.ev_entry, 0);
+    if ((e = cudaMemcpyAsync(d_tab, tab.data(), 4 * n * 8, cudaMemcpyHostToDevice, P.s_in)) != cudaSuccess) return 4;
+    int launches = 0;
+    Status overall = Status::SUCCESS;
+    for (int w = 0; w < nw; w++) {
+      const size_t lo = edges[w], m = edges[w + 1] - edges[w];
+      if (m == 0) continue;
+      for (const HostRun &r : in_runs[w])
+        if ((e = cudaMemcpyAsync(d + r.d_off, r.h_begin, r.bytes, cudaMemcpyHostToDevice, P.s_in)) != cudaSuccess) return 4;
+      cudaEventRecord(P.ev_in[w], P.s_in);
+      cudaStreamWaitEvent(stream, P.ev_in[w], 0);
+      Status s = I->run(true, reinterpret_cast<const void *const *>(d_tab) + lo, reinterpret_cast<const size_t *>(d_tab + n * 8) + lo, m,
+                        reinterpret_cast<void *const *>(d_tab + 2 * n * 8) + lo, reinterpret_cast<size_t *>(d_tab + 3 * n * 8) + lo, d_status + lo,
+                        true, d + ws_base, tmp_bytes - ws_base, stream, false, nullptr, nullptr);
+      if (s != Status::SUCCESS) overall = s;
+      launches += I->last_launches;
+    }
+    // device-side exclusive scan of the frame sizes, pack, and two copies home: offsets first (they size the second)
+    if (b200zstd::launch_scan_sizes(reinterpret_cast<const size_t *>(d_tab + 3 * n * 8), n, 0, d_offsets, stream) != cudaSuccess) return 4;
+    if (b200zstd::launch_pack(reinterpret_cast<const void *const *>(d_tab + 2 * n * 8), reinterpret_cast<const size_t *>(d_tab + 3 * n * 8), d_offsets, n,
+                              d + packed_base, stream) != cudaSuccess) return 4;
+    launches += 2;
+    std::vector<u32> st(n);
+    cudaMemcpyAsync(h_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(st.data(), d_status, n * 4, cudaMemcpyDeviceToHost, stream);
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return 4;
+    I->last_launches = launches;
+    if (overall != Status::SUCCESS) return status_to_nvcomp_error(overall);
+    int rc = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (h_status) h_status[i] = st[i];
+      if (st[i] != 0 && rc == 0) rc = 1;
+    }
+    if (h_offsets[n] > packed_cap) return 7;
+    if ((e = cudaMemcpyAsync(h_packed, d + packed_base, (size_t)h_offsets[n], cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return 4;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return 4;
+    return rc;
   } catch (...) { return 1; }
 }
 int cuda_zstd_batch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream) {

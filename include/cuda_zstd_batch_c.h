@@ -81,6 +81,26 @@ int cuda_zstd_batch_decompress_nosync(cuda_zstd_batch_t *mgr, const void *const 
                                       size_t *d_uncompressed_sizes, uint32_t *d_statuses, void *d_temp, size_t temp_bytes,
                                       cudaStream_t stream);
 
+/* Host-resident batches: the payloads live in HOST memory (pinned for copy / kernel overlap; pageable works).  The
+ * library stages them through d_temp in waves -- H2D of wave k+1 and D2H of wave k-1 run on two internal streams beside
+ * the codec's kernels for wave k on `stream` -- and returns when the results are on the host.  This is the batch form of
+ * what the reference does for host data with one synchronous single-buffer call per item: HybridEngine::compress_batch /
+ * decompress_batch (src/cuda_zstd_hybrid.cu:926-951 -> :402-458) and NvcompV5BatchManager callers that copy around
+ * compress_async (src/cuda_zstd_nvcomp.cpp:300-484).  Items that sit back to back in host memory move with one copy.
+ *   decompress_host: frame i at h_compressed_ptrs[i] -> bytes at h_uncompressed_ptrs[i]; sizes in = capacity, out = bytes.
+ *   compress_host_packed: chunk i at h_uncompressed_ptrs[i] -> frames packed back to back in h_packed,
+ *     h_offsets[0..n] = exclusive scan of the frame sizes (device-side scan + gather, then two copies home).
+ * h_statuses (n x uint32, may be NULL) receives the per-item status.  Return values as above; 7 = d_temp / h_packed too small. */
+size_t cuda_zstd_batch_get_host_decompress_temp_size(cuda_zstd_batch_t *mgr, const size_t *compressed_sizes,
+                                                     const size_t *uncompressed_capacities, size_t num_chunks);
+size_t cuda_zstd_batch_get_host_compress_temp_size(cuda_zstd_batch_t *mgr, const size_t *chunk_sizes, size_t num_chunks);
+int cuda_zstd_batch_decompress_host(cuda_zstd_batch_t *mgr, const void *const *h_compressed_ptrs, const size_t *compressed_sizes,
+                                    size_t num_chunks, void *const *h_uncompressed_ptrs, size_t *uncompressed_sizes,
+                                    uint32_t *h_statuses, void *d_temp, size_t temp_bytes, cudaStream_t stream);
+int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *mgr, const void *const *h_uncompressed_ptrs, const size_t *chunk_sizes,
+                                         size_t num_chunks, void *h_packed, size_t packed_capacity, uint64_t *h_offsets,
+                                         uint32_t *h_statuses, void *d_temp, size_t temp_bytes, cudaStream_t stream);
+
 /* Device-side exclusive scan of per-chunk compressed sizes -> packed offsets, plus the grand total
  * in d_offsets[num_chunks]; `base` is this GPU's starting offset in a multi-GPU job (SURVEY.md
  * section 8e).  Replaces the reference's thrust::exclusive_scan wrapper

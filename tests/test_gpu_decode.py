@@ -163,7 +163,19 @@ def test_error_statuses(oracle, libzstd, pkg, gpu_codec_factory):
     assert st[0] == 0 and st[5] == 0
     assert st[1] == pkg.Status.ERROR_INVALID_MAGIC
     assert st[2] == pkg.Status.ERROR_CORRUPT_DATA
-    assert st[3] in (pkg.Status.ERROR_CORRUPT_DATA, 0)
+    # the damaged payload: the verdict is the oracle's on the same frame (and whatever libzstd rejects is rejected); when
+    # the damage leaves a decodable frame, the bytes must be the ones libzstd regenerates from it
+    orc_rc, orc_out = oracle.decompress(frames[3], 65536)
+    try:
+        z_out = libzstd.decompress(frames[3], 65536)
+    except RuntimeError:
+        z_out = None
+    if z_out is None:
+        assert st[3] == pkg.Status.ERROR_CORRUPT_DATA
+    assert (st[3] == 0) == (orc_rc == 0)
+    if st[3] == 0:
+        assert np.array_equal(out.cpu().numpy()[3 * 65536: 3 * 65536 + int(out_sizes.cpu().numpy()[3])], orc_out)
+        assert z_out is not None and np.array_equal(z_out, orc_out)
     assert st[4] == pkg.Status.ERROR_BUFFER_TOO_SMALL
     osz = out_sizes.cpu().numpy()
     assert osz[0] == 65536 and osz[1] == 0 and osz[2] == 0 and osz[4] == 0

@@ -56,8 +56,44 @@ def test_config3_compress_l1_1gib(oracle, libzstd, pkg):
 
 
 def test_config4_compress_l9_128k_checksum(oracle, libzstd, pkg):
-    ratio = _roundtrip(oracle, libzstd, pkg, 131072, 4096, 9, 0, 32768, True, sample=32)
+    # BASELINE config 4 at its full size: 16384 x 128 KiB = 2 GiB, level 9, XXH64 checksums
+    ratio = _roundtrip(oracle, libzstd, pkg, 131072, 16384, 9, 0, 32768, True, sample=32)
     assert ratio > 6.5
+
+
+def test_more_than_one_wave_of_ragged_mixed_chunks(oracle, libzstd, pkg):
+    """20,000 mixed-entropy chunks of ragged sizes (1 B .. 128 KiB) in ONE call: the decoder's fast path runs in waves of
+    16,384 chunks and the levels 1-4 encoder in waves of 8,192 / 4,096, both with items on every route (64 KiB and
+    128 KiB geometries, raw / RLE blocks, general decode kernel for what the pools cannot hold)."""
+    n = 20000
+    rng = np.random.default_rng(11)
+    lens = rng.integers(1, 65537, n).astype(np.int64)
+    lens[rng.choice(n, 300, replace=False)] = rng.integers(65537, 131073, 300)
+    lens[:4] = [1, 65536, 65537, 131072]
+    offs = np.zeros(n + 1, np.int64); offs[1:] = np.cumsum(lens)
+    total = int(offs[-1])
+    host = oracle.gen_batch(65536, (total + 65535) // 65536, 2, 0)[:total].copy()
+    dev = torch.from_numpy(host).cuda()
+    codec = pkg.ZstdBatchCodec(level=3)
+    caps = np.array([codec.max_compressed_size(int(l)) for l in lens], np.int64)
+    coffs = np.zeros(n + 1, np.int64); coffs[1:] = np.cumsum((caps + 15) // 16 * 16)
+    comp = torch.empty(int(coffs[-1]), dtype=torch.uint8, device="cuda")
+    sizes = lens.astype(np.uint64)
+    ws = torch.empty(max(codec.compress_temp_size(n, sizes), codec.decompress_temp_size(n)), dtype=torch.uint8, device="cuda")
+    csz = caps.astype(np.uint64)
+    rc = codec.compress_tables((np.uint64(dev.data_ptr()) + offs[:-1].astype(np.uint64)).astype(np.uint64), sizes, n,
+                               (np.uint64(comp.data_ptr()) + coffs[:-1].astype(np.uint64)).astype(np.uint64), csz, ws)
+    assert rc == 0 and (csz > 0).all()
+    ch = comp.cpu().numpy()
+    for i in rng.choice(n, 96, replace=False).tolist() + [0, 1, 2, 3, n - 1]:
+        f = ch[int(coffs[i]): int(coffs[i]) + int(csz[i])]
+        assert np.array_equal(libzstd.decompress(f, int(lens[i])), host[int(offs[i]): int(offs[i + 1])]), i
+    back = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    bsz = lens.astype(np.uint64)
+    rc = codec.decompress_tables((np.uint64(comp.data_ptr()) + coffs[:-1].astype(np.uint64)).astype(np.uint64), csz, n,
+                                 (np.uint64(back.data_ptr()) + offs[:-1].astype(np.uint64)).astype(np.uint64), bsz, ws)
+    assert rc == 0 and (bsz == sizes).all()
+    assert torch.equal(back, dev)
 
 
 def test_config5_mixed_entropy_shard(oracle, libzstd, pkg):
