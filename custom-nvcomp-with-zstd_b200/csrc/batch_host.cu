@@ -66,7 +66,9 @@ std::mutex g_err_mu;
 ErrorContext g_last_err;
 ErrorCallback g_err_cb = nullptr;
 
+thread_local bool g_quiet_errors = false;      // set around speculative attempts whose failure is not the call's result
 Status fail(Status s, const char *fn, const char *msg, cudaError_t ce = cudaSuccess) {
+  if (g_quiet_errors) return s;
   ErrorContext c(s, __FILE__, 0, fn, msg);
   c.cuda_error = ce;
   log_error(c);
@@ -260,13 +262,20 @@ public:
     return &overlap;
   }
 
-  Impl() {
+  int cached_dev = -1;
+  // the SM count and the decoder's residency belong to the CURRENT device: re-read when a call arrives on another one
+  void refresh_device() {
     int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; }
+    if (dev == cached_dev && sm_count > 0) return;
+    sm_count = 0;
+    if (dev >= 0) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) { (void)cudaGetLastError(); sm_count = 148; }     // size queries still work without a device
     dec_ctas_per_sm = b200zstd::decode_ctas_per_sm();
     (void)cudaGetLastError();
+    cached_dev = dev;
   }
+  Impl() { refresh_device(); }
   b200zstd::EncodeParams enc_params() const {
     return b200zstd::encode_params_for_level(cfg.level, cfg.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY);
   }
@@ -448,7 +457,9 @@ public:
     if (!info.ok || info.units < 2) return Status::ERROR_NOT_IMPLEMENTED;
     std::vector<u32> st;
     bare_mode = true;
+    g_quiet_errors = true;        // a unit that is not self-contained is not an error of the call: the serial decode decides
     Status s = run(false, u_in, u_in_sz, info.units, u_out, u_out_sz, nullptr, true, ws, body, stream, true, &st, nullptr);
+    g_quiet_errors = false;
     bare_mode = false;
     const int launches = last_launches + 1;
     if (s != Status::SUCCESS) return Status::ERROR_NOT_IMPLEMENTED;                  // some unit was not self-contained: serial decode decides
@@ -474,6 +485,7 @@ public:
     const char *fn = compress ? "compress_batch" : "decompress_batch";
     last_launches = 0;
     if (n == 0) return Status::SUCCESS;
+    refresh_device();
     if (!in_ptrs || !in_sizes || !out_ptrs || !out_sizes) return fail(Status::ERROR_INVALID_PARAMETER, fn, "null pointer table");
     if (n > 0xFFFFFFF0ull) return fail(Status::ERROR_INVALID_PARAMETER, fn, "too many chunks");
     size_t min_item = 0, max_item = 0;              // 0 / 0 = unknown (device-resident size table)
@@ -599,7 +611,9 @@ size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const {
   // a frame that needs more decodes serially
   const size_t est = std::min<size_t>(4096, (16 * n + Impl::BIG_BLOCK - 1) / Impl::BIG_BLOCK);
   const size_t core = est >= 2 ? std::max(pimpl_->dec_temp(1, &n), pimpl_->big_dec_temp(n, est)) : pimpl_->dec_temp(1, &n);
-  return core + align_up(n, 256) + 256;
+  // staging of pageable host buffers: the input, and the output for ratios up to 16 (a larger pageable output needs a
+  // larger workspace or a pinned / device destination)
+  return core + align_up(n, 256) + align_up(std::min<size_t>(16 * n, (size_t)1 << 28), 256) + 256;
 }
 size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
 size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size(), v.data()); }
@@ -686,7 +700,8 @@ static Status single_buffer(ZstdBatchManager::Impl &I, bool compress, const void
                             size_t ws_bytes, cudaStream_t stream) {
   const char *fn = compress ? "compress" : "decompress";
   const bool stage_in = mem_of(src) == Mem::PAGEABLE, stage_out = mem_of(dst) == Mem::PAGEABLE;
-  const size_t cap = *dst_size;
+  // a compressor never needs more than the worst-case size: capacities beyond it would only inflate the staging room
+  const size_t cap = compress ? std::min(*dst_size, estimate_compressed_size(n, I.cfg.level)) : *dst_size;
   const size_t tail = (stage_in ? stage_room(n) : 0) + (stage_out ? stage_room(cap) : 0);
   if (tail > ws_bytes) return fail(Status::ERROR_BUFFER_TOO_SMALL, fn, "workspace has no room to stage pageable host buffers");
   const size_t body = (ws_bytes - tail) & ~(size_t)255;
@@ -1210,14 +1225,18 @@ int cuda_zstd_batch_compress_nosync(cuda_zstd_batch_t *b, const void *const *in,
                                     size_t *out_sz, uint32_t *st, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
   if (!b) return 2;
   try {
-    return status_to_nvcomp_error(b->m->batch_manager().impl()->run(true, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
+    auto *I = b->m->batch_manager().impl();
+    std::lock_guard<std::mutex> lock(I->mu);
+    return status_to_nvcomp_error(I->run(true, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
   } catch (...) { return 1; }
 }
 int cuda_zstd_batch_decompress_nosync(cuda_zstd_batch_t *b, const void *const *in, const size_t *in_sz, size_t n, void *const *out,
                                       size_t *out_sz, uint32_t *st, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
   if (!b) return 2;
   try {
-    return status_to_nvcomp_error(b->m->batch_manager().impl()->run(false, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
+    auto *I = b->m->batch_manager().impl();
+    std::lock_guard<std::mutex> lock(I->mu);
+    return status_to_nvcomp_error(I->run(false, in, in_sz, n, out, out_sz, st, true, tmp, tmp_bytes, stream, false, nullptr, nullptr));
   } catch (...) { return 1; }
 }
 // ---- host-resident batches (include/cuda_zstd_batch_c.h): payloads in HOST memory, staged in waves over two copy

@@ -40,7 +40,8 @@ PipelinedBatchManager::~PipelinedBatchManager() { cleanup_resources(); }
 Status PipelinedBatchManager::init_resources() {
   for (auto &st : streams_)
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return Status::ERROR_CUDA_ERROR; }
-  const size_t out_cap = manager_->get_max_compressed_size(batch_size_) + 64;      // + frame header of the multi-block form
+  // + frame header of the multi-block form; rounded so that the 16-byte result mailbox behind it is aligned
+  const size_t out_cap = (manager_->get_max_compressed_size(batch_size_) + 64 + 15) & ~(size_t)15;
   const size_t ws_cap = manager_->get_compress_temp_size(batch_size_);
   for (auto &s : ring_buffer_) {
     s.input_capacity = batch_size_; s.output_capacity = out_cap; s.workspace_capacity = ws_cap;

@@ -190,7 +190,7 @@ __device__ inline uint64_t xxh64_warp(const uint8_t *p, uint32_t len, int lane) 
         // lanes 0/1 share one 16-byte load, lanes 2/3 the next: each lane keeps its own half
         const uint4 *q = (const uint4 *)p + (lane >> 1);
         for (uint32_t s = 0; s < stripes; s++) {
-          uint4 x = __ldg(q + 2 * s);
+          uint4 x = q[2 * s];          // plain load: the hashed bytes may have been written by this kernel (decoder output)
           uint64_t in = (lane & 1) ? ((uint64_t)x.w << 32 | x.z) : ((uint64_t)x.y << 32 | x.x);
           v = xx_round(v, in);
         }

@@ -24,6 +24,8 @@
 // device-side list and decoded by the general kernel in the same call.  Same reference functions replaced as zstd_decode.cu.
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+
 #include "zstd_common.cuh"
 #include "zstd_decode_tables.cuh"
 #include "zstd_device_api.h"
@@ -1140,12 +1142,16 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   const uint32_t n = F0.base.n;
   if (launches) *launches = 0;
   if (n == 0) return cudaSuccess;
-  static bool attr_done = false;
+  // the opt-in to large dynamic shared memory belongs to the (function, device) pair: once per device, whichever thread
+  // gets there first (a process may drive several GPUs)
+  static std::atomic<unsigned long long> attr_done_mask{0};
   cudaError_t e;
-  if (!attr_done) {
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if (dev >= 64 || !((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
     if ((e = cudaFuncSetAttribute(zstd_fast_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KA_SMEM)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
-    attr_done = true;
+    if (dev < 64) attr_done_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
   FastDecodeArgs F = F0;
   F.lo = 0; F.hi = n; F.sub = 0;
