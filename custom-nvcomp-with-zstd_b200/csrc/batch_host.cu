@@ -298,6 +298,26 @@ public:
     return (size_t)enc_grid(n) * general;
   }
   size_t enc_need(size_t n, uint32_t bm) const { return b200zstd::WS_HEADER_BYTES + table_bytes(n) + lists_bytes(n) + enc_scratch_bytes(n, bm); }
+  // what the size QUERIES report: the need of whichever level wants the most, so that a workspace sized with one manager
+  // serves a manager at any other level (the reference's tests size one workspace at "the highest level tested",
+  // tests/test_c_api_edge_cases.cu:268-272); run() itself only asks for what its own level needs
+  size_t enc_scratch_any_level(size_t n, uint32_t bm) const {
+    const bool ck = cfg.checksum != ChecksumPolicy::NO_COMPUTE_NO_VERIFY;
+    size_t scratch = b200zstd::esd_scratch_bytes(n, bm, sm_count);
+    for (int level : {1, 3, 5, 7, 9, 12, 19}) {
+      const b200zstd::EncodeParams prm = b200zstd::encode_params_for_level(level, ck);
+      const size_t general = b200zstd::encode_cta_scratch_bytes(prm);
+      int per = b200zstd::encode_ctas_per_sm(prm);
+      (void)cudaGetLastError();
+      const size_t grid = std::min<size_t>(n, (size_t)sm_count * (size_t)std::max(per, 1));
+      scratch = std::max(scratch, b200zstd::esd_level(level) ? general : grid * general);
+    }
+    return scratch;
+  }
+  size_t lists_bytes_any_level(size_t n) const { return align_up(n * 8 + b200zstd::esd_counter_words(n, 131072u) * 4, 256); }
+  size_t enc_need_any_level(size_t n, uint32_t bm) const {
+    return b200zstd::WS_HEADER_BYTES + table_bytes(n) + lists_bytes_any_level(n) + enc_scratch_any_level(n, bm);
+  }
   // a.counter / a.scratch are set here; w = workspace base, lists = 2 n words followed by the pipeline's counters
   cudaError_t enqueue_encode(b200zstd::EncodeArgs &a, unsigned char *w, unsigned char *lists, unsigned char *scratch, size_t scratch_bytes,
                              uint32_t bm, size_t min_item, size_t max_item, cudaStream_t stream, int *launches) {
@@ -344,7 +364,7 @@ public:
     if (n == 0) return 0;
     size_t max_item = 0;
     if (sizes) for (size_t i = 0; i < n; ++i) max_item = std::max(max_item, sizes[i]);
-    size_t e = enc_need(n, esd_block_max(max_item));
+    size_t e = enc_need_any_level(n, esd_block_max(max_item));
     // a compress workspace can always be reused for decompress (reference tests/test_c_api.cpp:62-64):
     // the decoder needs dec_fixed(); pool space beyond that only decides how many chunks take the fast path
     return std::max(e, dec_fixed(n) + wave_of(n) * (size_t)(64 * 1024));
@@ -361,6 +381,10 @@ public:
   size_t big_temp(size_t n) const {
     const size_t B = big_blocks(n);
     return b200zstd::WS_HEADER_BYTES + big_tables(B) + lists_bytes(B) + enc_scratch_bytes(B, 131072u) + B * big_slot();
+  }
+  size_t big_temp_any_level(size_t n) const {          // for the size queries (see enc_need_any_level)
+    const size_t B = big_blocks(n);
+    return b200zstd::WS_HEADER_BYTES + big_tables(B) + lists_bytes_any_level(B) + enc_scratch_any_level(B, 131072u) + B * big_slot();
   }
   // Enqueue only: nothing is synchronised.  The outcome {frame bytes, first failing block status} lands in the 16-byte
   // device mailbox at ws + 64 and, when h_result is given (pinned host memory), is copied there on the same stream.
@@ -602,7 +626,7 @@ CompressionConfig ZstdBatchManager::get_config() const { return pimpl_->cfg; }
 // single-buffer sizes include the tail that stages pageable host buffers (input; for compress also the worst-case output)
 size_t ZstdBatchManager::get_compress_temp_size(size_t n) const {
   if (n == 0) return 0;
-  const size_t core = n > Impl::BIG_BLOCK ? std::max(pimpl_->big_temp(n), pimpl_->enc_temp(1, &n)) : pimpl_->enc_temp(1, &n);
+  const size_t core = n > Impl::BIG_BLOCK ? std::max(pimpl_->big_temp_any_level(n), pimpl_->enc_temp(1, &n)) : pimpl_->enc_temp(1, &n);
   return core + align_up(n, 256) + align_up(estimate_compressed_size(n, pimpl_->cfg.level), 256) + 256;
 }
 size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const {
@@ -1103,11 +1127,12 @@ struct cuda_zstd_batch { cuda_zstd::nvcomp_v5::NvcompV5BatchManager *m; HostPipe
 
 namespace {
 // Host buffers of a batch usually sit back to back in a few large allocations: a RUN is a maximal stretch of items whose
-// host addresses ascend with gaps below 256 bytes, staged by ONE copy; the device image keeps every item's address
-// modulo 256.  Items that do not line up simply form runs of their own.
+// host addresses ascend with gaps of at most max_gap bytes, staged by ONE copy; the device image keeps every item's
+// address modulo 256.  Items that do not line up simply form runs of their own.  Inputs may bridge small gaps (the gap
+// bytes are only read); outputs must be exactly adjacent, because a copy home writes every byte of its run.
 struct HostRun { size_t first, count; const unsigned char *h_begin; size_t bytes; size_t d_off; };
 size_t plan_runs(const void *const *ptrs, const size_t *sizes, size_t lo, size_t hi, size_t d_off, std::vector<HostRun> &runs,
-                 std::vector<size_t> &item_off) {
+                 std::vector<size_t> &item_off, size_t max_gap) {
   size_t i = lo;
   while (i < hi) {
     const unsigned char *b = static_cast<const unsigned char *>(ptrs[i]);
@@ -1115,7 +1140,7 @@ size_t plan_runs(const void *const *ptrs, const size_t *sizes, size_t lo, size_t
     size_t j = i + 1;
     while (j < hi) {
       const unsigned char *q = static_cast<const unsigned char *>(ptrs[j]);
-      if (q < e || (size_t)(q - e) >= 256) break;
+      if (q < e || (size_t)(q - e) > max_gap) break;
       e = q + sizes[j];
       j++;
     }
@@ -1268,9 +1293,9 @@ int cuda_zstd_batch_decompress_host(cuda_zstd_batch_t *b, const void *const *h_i
     std::vector<HostRun> in_runs[HostPipe::MAX_WAVES], out_runs[HostPipe::MAX_WAVES];
     std::vector<size_t> in_off(n), out_off(n);
     size_t off = 0;
-    for (int w = 0; w < nw; w++) off = plan_runs(h_in, in_sz, edges[w], edges[w + 1], off, in_runs[w], in_off);
+    for (int w = 0; w < nw; w++) off = plan_runs(h_in, in_sz, edges[w], edges[w + 1], off, in_runs[w], in_off, 255);
     const size_t out_base = off;
-    for (int w = 0; w < nw; w++) off = plan_runs(h_out, out_sz, edges[w], edges[w + 1], off, out_runs[w], out_off);
+    for (int w = 0; w < nw; w++) off = plan_runs(h_out, out_sz, edges[w], edges[w + 1], off, out_runs[w], out_off, 0);
     const size_t tab_base = off, tab_bytes = align_up(n * 36, 256);
     const size_t ws_base = tab_base + tab_bytes;
     const size_t codec_need = b->m->get_decompress_temp_size(in_sz, n);
@@ -1341,7 +1366,7 @@ int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *b, const void *const
     std::vector<HostRun> in_runs[HostPipe::MAX_WAVES];
     std::vector<size_t> in_off(n), caps(n), frame_off(n);
     size_t off = 0;
-    for (int w = 0; w < nw; w++) off = plan_runs(h_in, in_sz, edges[w], edges[w + 1], off, in_runs[w], in_off);
+    for (int w = 0; w < nw; w++) off = plan_runs(h_in, in_sz, edges[w], edges[w + 1], off, in_runs[w], in_off, 255);
     size_t frames = 0;
     for (size_t i = 0; i < n; i++) { caps[i] = b->m->get_max_compressed_chunk_size(in_sz[i]); frame_off[i] = frames; frames += align_up(caps[i], 16); }
     const size_t frames_base = off, packed_base = frames_base + align_up(frames, 256);
