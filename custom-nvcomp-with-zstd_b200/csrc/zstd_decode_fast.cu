@@ -453,9 +453,11 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
 // =================================================================================================
 // KB: FSE tables in shared memory (one warp per chunk), then one lane per sequence stream
 // =================================================================================================
-constexpr int KB_THREADS = 64;                                  // the two decoding warps; everything else of the SM is left to KC
 constexpr int KB_GROUP = 56;                                   // chunks per CTA pass: 56 x 3.75 KB of packed tables
-constexpr int KB_DEC_WARPS = 2, KB_LANES = KB_GROUP / KB_DEC_WARPS;   // 2 decoding warps x 28 lanes
+// The 56 streams of a group are spread over KB_DEC_WARPS warps: a warp stalls whenever ANY of its lanes waits for a word
+// of its bitstream, so fewer lanes per warp means fewer shared stalls at the price of more issued instructions
+// (measured: see DESIGN.md 4.1).  CUDA_ZSTD_KB_WARPS selects another split for experiments.
+constexpr int KB_DEC_WARPS_DEFAULT = 4;
 __device__ __forceinline__ constexpr int kb_norm_off(int t) { return t == 0 ? 0 : t == 1 ? 40 : 72; }   // LL 36 | OF 32 | ML 53 normalised counts
 struct __align__(16) SeqScratch {                              // per-warp scratch for the table build (432 B: 28 of them fit beside the tables)
   int16_t norm[128];
@@ -727,7 +729,9 @@ __global__ void __launch_bounds__(KP_WARPS * 32) zstd_fast_prep_kernel(FastDecod
 }
 
 // ---- KB: 56 chunks' tables pulled into shared memory by bulk async copies, then one lane per sequence stream ----
-__global__ void __launch_bounds__(KB_THREADS, 1) zstd_fast_seq_kernel(FastDecodeArgs F) {
+template <int KB_DEC_WARPS>
+__global__ void __launch_bounds__(32 * KB_DEC_WARPS, 1) zstd_fast_seq_kernel(FastDecodeArgs F) {
+  constexpr int KB_THREADS = 32 * KB_DEC_WARPS, KB_LANES = KB_GROUP / KB_DEC_WARPS;
   extern __shared__ __align__(128) uint8_t kb_smem[];
   __shared__ uint32_t s_group;
   __shared__ __align__(8) uint64_t s_bar;
@@ -1138,7 +1142,17 @@ static uint32_t exec_grid(uint32_t chunks, uint32_t sms, bool last = false) {
   return blocks < cap ? blocks : cap;
 }
 
+static void launch_kb(int warps, uint32_t grid, cudaStream_t stream, const FastDecodeArgs &F) {
+  switch (warps) {
+    case 2: zstd_fast_seq_kernel<2><<<grid, 64, KB_SMEM, stream>>>(F); break;
+    case 4: zstd_fast_seq_kernel<4><<<grid, 128, KB_SMEM, stream>>>(F); break;
+    case 14: zstd_fast_seq_kernel<14><<<grid, 448, KB_SMEM, stream>>>(F); break;
+    default: zstd_fast_seq_kernel<8><<<grid, 256, KB_SMEM, stream>>>(F); break;
+  }
+}
+
 cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, const FastOverlap *ov, int *launches) {
+  static const int kb_warps = getenv("CUDA_ZSTD_KB_WARPS") ? atoi(getenv("CUDA_ZSTD_KB_WARPS")) : KB_DEC_WARPS_DEFAULT;
   const uint32_t n = F0.base.n;
   if (launches) *launches = 0;
   if (n == 0) return cudaSuccess;
@@ -1150,7 +1164,10 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if (dev >= 64 || !((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
     if ((e = cudaFuncSetAttribute(zstd_fast_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KA_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(zstd_fast_seq_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KB_SMEM)) != cudaSuccess) return e;
     if (dev < 64) attr_done_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
   FastDecodeArgs F = F0;
@@ -1178,14 +1195,14 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   const bool overlap = ov && nsub > 1 && nsub <= (uint32_t)FastOverlap::MAX_SUB;
   if (!overlap) {
     const uint32_t kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
-    zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
+    launch_kb(kb_warps, kb_groups < sms ? kb_groups : sms, stream, F);
     zstd_fast_exec_kernel<<<exec_grid(n, sms), EXEC_WARPS * 32, 0, stream>>>(F);
     count += 2;
   } else {
     for (uint32_t k = 0; k < nsub; k++) {
       F.lo = k * sub_chunks; F.hi = F.lo + sub_chunks < n ? F.lo + sub_chunks : n; F.sub = k;
       const uint32_t m = F.hi - F.lo, kb_groups = (m + KB_GROUP - 1) / KB_GROUP;
-      zstd_fast_seq_kernel<<<kb_groups < sms ? kb_groups : sms, KB_THREADS, KB_SMEM, stream>>>(F);
+      launch_kb(kb_warps, kb_groups < sms ? kb_groups : sms, stream, F);
       mark("KB", stream);
       if ((e = cudaEventRecord(ov->ev[k], stream)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(ov->side, ov->ev[k], 0)) != cudaSuccess) return e;
