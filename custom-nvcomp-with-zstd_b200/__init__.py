@@ -9,6 +9,7 @@ loudly if the library has not been built.
 from .binding import (  # noqa: F401
     LIB_PATH,
     Status,
+    ShardC,
     ZstdBatchCodec,
     ZstdHybrid,
     ZstdPipeline,

@@ -47,7 +47,7 @@ EXPORTS = [
     "cuda_zstd_batch_decompress", "cuda_zstd_batch_compress_nosync", "cuda_zstd_batch_decompress_nosync",
     "cuda_zstd_batch_scan_sizes", "cuda_zstd_batch_pack", "cuda_zstd_batch_last_launch_count", "cuda_zstd_batch_error_string",
     "cuda_zstd_batch_get_host_decompress_temp_size", "cuda_zstd_batch_get_host_compress_temp_size", "cuda_zstd_batch_decompress_host",
-    "cuda_zstd_batch_compress_host_packed",
+    "cuda_zstd_batch_compress_host_packed", "cuda_zstd_batch_compress_sharded", "cuda_zstd_batch_decompress_sharded",
     "cuda_zstd_create_manager", "cuda_zstd_destroy_manager", "cuda_zstd_compress", "cuda_zstd_decompress",
     "cuda_zstd_get_compress_workspace_size", "cuda_zstd_get_decompress_workspace_size", "cuda_zstd_train_dictionary",
     "cuda_zstd_destroy_dictionary", "cuda_zstd_set_dictionary", "cuda_zstd_get_error_string", "cuda_zstd_is_error",
@@ -58,6 +58,12 @@ EXPORTS = [
     "cuda_zstd_hybrid_create", "cuda_zstd_hybrid_create_default", "cuda_zstd_hybrid_destroy", "cuda_zstd_hybrid_compress",
     "cuda_zstd_hybrid_decompress", "cuda_zstd_hybrid_max_compressed_size", "cuda_zstd_hybrid_query_routing",
 ]
+
+
+class ShardC(C.Structure):                 # cuda_zstd_shard_t (include/cuda_zstd_batch_c.h)
+    _fields_ = [("device", C.c_int), ("mgr", C.c_void_p), ("d_in_ptrs", C.c_void_p), ("d_in_sizes", C.c_void_p), ("d_out_ptrs", C.c_void_p),
+                ("d_out_sizes", C.c_void_p), ("d_statuses", C.c_void_p), ("num_chunks", C.c_size_t), ("d_temp", C.c_void_p),
+                ("temp_bytes", C.c_size_t), ("stream", C.c_void_p), ("d_all_sizes", C.c_void_p), ("d_all_offsets", C.c_void_p)]
 
 
 class HybridConfigC(C.Structure):       # cuda_zstd_hybrid_config_t (include/cuda_zstd_hybrid.h)
@@ -108,6 +114,9 @@ def load_library() -> C.CDLL:
     lib.cuda_zstd_batch_decompress_host.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
     lib.cuda_zstd_batch_compress_host_packed.restype = i32
     lib.cuda_zstd_batch_compress_host_packed.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, vp, sz, vp]
+    for f in (lib.cuda_zstd_batch_compress_sharded, lib.cuda_zstd_batch_decompress_sharded):
+        f.restype = i32
+        f.argtypes = [C.POINTER(ShardC), i32]
     lib.cuda_zstd_batch_scan_sizes.restype = i32
     lib.cuda_zstd_batch_scan_sizes.argtypes = [vp, sz, u64, vp, vp]
     lib.cuda_zstd_batch_pack.restype = i32

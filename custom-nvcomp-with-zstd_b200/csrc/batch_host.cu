@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -1424,6 +1425,64 @@ int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *b, const void *const
     return rc;
   } catch (...) { return 1; }
 }
+// ---- shards of one batch on several GPUs of this process ----
+static int run_sharded(bool compress, cuda_zstd_shard_t *sh, int G) {
+  if (!sh || G <= 0) return 2;
+  for (int g = 0; g < G; g++)
+    if (!sh[g].mgr || !sh[g].d_in_ptrs || !sh[g].d_in_sizes || !sh[g].d_out_ptrs || !sh[g].d_out_sizes || !sh[g].d_statuses) return 2;
+  int home = 0;
+  cudaGetDevice(&home);
+  std::vector<int> rc(G, 0);
+  std::vector<cudaEvent_t> ev(G, nullptr);
+  std::vector<std::thread> th;
+  // one host thread per shard: the launches of different GPUs are issued side by side
+  for (int g = 0; g < G; g++)
+    th.emplace_back([&, g]() {
+      cuda_zstd_shard_t &s = sh[g];
+      if (cudaSetDevice(s.device) != cudaSuccess) { rc[g] = 4; return; }
+      if (cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming) != cudaSuccess) { rc[g] = 4; return; }
+      if (s.num_chunks)
+        rc[g] = compress ? cuda_zstd_batch_compress_nosync(s.mgr, s.d_in_ptrs, s.d_in_sizes, s.num_chunks, s.d_out_ptrs, s.d_out_sizes, s.d_statuses,
+                                                           s.d_temp, s.temp_bytes, s.stream)
+                         : cuda_zstd_batch_decompress_nosync(s.mgr, s.d_in_ptrs, s.d_in_sizes, s.num_chunks, s.d_out_ptrs, s.d_out_sizes, s.d_statuses,
+                                                             s.d_temp, s.temp_bytes, s.stream);
+      cudaEventRecord(ev[g], s.stream);
+    });
+  for (auto &t : th) t.join();
+  int overall = 0;
+  for (int g = 0; g < G; g++) if (rc[g] != 0 && overall == 0) overall = rc[g];
+  size_t total = 0;
+  std::vector<size_t> base(G);
+  for (int g = 0; g < G; g++) { base[g] = total; total += sh[g].num_chunks; }
+  // the exchange: every shard's sizes to every shard's table, then the scan on each device
+  if (overall == 0)
+    for (int h = 0; h < G; h++) {
+      if (!sh[h].d_all_sizes) continue;
+      cudaSetDevice(sh[h].device);
+      for (int g = 0; g < G; g++) {
+        if (!sh[g].num_chunks) continue;
+        cudaStreamWaitEvent(sh[h].stream, ev[g], 0);
+        if (cudaMemcpyPeerAsync(sh[h].d_all_sizes + base[g], sh[h].device, sh[g].d_out_sizes, sh[g].device, sh[g].num_chunks * sizeof(size_t),
+                                sh[h].stream) != cudaSuccess) overall = 4;
+      }
+      if (sh[h].d_all_offsets && total &&
+          b200zstd::launch_scan_sizes(sh[h].d_all_sizes, total, 0, sh[h].d_all_offsets, sh[h].stream) != cudaSuccess) overall = 4;
+    }
+  // completion and the per-chunk verdicts
+  for (int g = 0; g < G; g++) {
+    cudaSetDevice(sh[g].device);
+    std::vector<u32> st(sh[g].num_chunks);
+    if (sh[g].num_chunks && cudaMemcpyAsync(st.data(), sh[g].d_statuses, st.size() * 4, cudaMemcpyDeviceToHost, sh[g].stream) != cudaSuccess && overall == 0) overall = 4;
+    if (cudaStreamSynchronize(sh[g].stream) != cudaSuccess && overall == 0) overall = 4;
+    if (overall == 0) for (u32 v : st) if (v != 0) { overall = 1; break; }
+  }
+  for (int g = 0; g < G; g++) if (ev[g]) { cudaSetDevice(sh[g].device); cudaEventDestroy(ev[g]); }
+  cudaSetDevice(home);
+  return overall;
+}
+int cuda_zstd_batch_compress_sharded(cuda_zstd_shard_t *shards, int num_shards) { try { return run_sharded(true, shards, num_shards); } catch (...) { return 1; } }
+int cuda_zstd_batch_decompress_sharded(cuda_zstd_shard_t *shards, int num_shards) { try { return run_sharded(false, shards, num_shards); } catch (...) { return 1; } }
+
 int cuda_zstd_batch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream) {
   if (!d_sizes || !d_offsets) return 2;
   return b200zstd::launch_scan_sizes(d_sizes, n, base, d_offsets, stream) == cudaSuccess ? 0 : 4;

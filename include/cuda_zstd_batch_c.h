@@ -101,6 +101,30 @@ int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *mgr, const void *con
                                          size_t num_chunks, void *h_packed, size_t packed_capacity, uint64_t *h_offsets,
                                          uint32_t *h_statuses, void *d_temp, size_t temp_bytes, cudaStream_t stream);
 
+/* Multi-GPU inside ONE process (the reference lists multi-GPU as future work, README.md:1648).
+ * The batch is sharded by chunk index; shard g describes its own chunks with device-resident tables on its own GPU and is
+ * driven by its own host thread (cudaSetDevice + the no-sync batch call on the shard's stream).  No payload crosses GPUs.
+ * The one exchange: every shard's per-chunk output sizes are copied device-to-device (cudaMemcpyPeerAsync: NVLink when
+ * peer access is on) into each shard's d_all_sizes, at the shard's base index, and scanned there on the device into
+ * d_all_offsets -- the global packed offsets -- so every GPU ends up knowing where every frame goes.  Both are optional
+ * (NULL: no exchange).  Returns when all shards are done: 0, or 1 if any chunk failed (see d_statuses), or the launch error. */
+typedef struct cuda_zstd_shard {
+  int device;                      /* CUDA device ordinal of this shard */
+  cuda_zstd_batch_t *mgr;          /* a manager of this shard (one per shard) */
+  const void *const *d_in_ptrs;    /* this shard's chunks: device tables on `device` */
+  const size_t *d_in_sizes;
+  void *const *d_out_ptrs;
+  size_t *d_out_sizes;             /* in = capacity, out = bytes */
+  uint32_t *d_statuses;            /* per chunk, required */
+  size_t num_chunks;
+  void *d_temp;
+  size_t temp_bytes;
+  cudaStream_t stream;             /* a stream of `device` */
+  size_t *d_all_sizes;             /* optional: sum of all shards' num_chunks entries, on `device` */
+  uint64_t *d_all_offsets; /* optional: that + 1 entries, on `device` */ } cuda_zstd_shard_t;
+int cuda_zstd_batch_compress_sharded(cuda_zstd_shard_t *shards, int num_shards);
+int cuda_zstd_batch_decompress_sharded(cuda_zstd_shard_t *shards, int num_shards);
+
 /* Device-side exclusive scan of per-chunk compressed sizes -> packed offsets, plus the grand total
  * in d_offsets[num_chunks]; `base` is this GPU's starting offset in a multi-GPU job (SURVEY.md
  * section 8e).  Replaces the reference's thrust::exclusive_scan wrapper
