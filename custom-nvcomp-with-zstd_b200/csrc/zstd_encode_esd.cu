@@ -282,6 +282,182 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_match_kernel(EsdArgs
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// MATCH, levels 5-9: rows (zstd_encode_lz.cuh).  Same window hand-over as above; the 8-byte table holds rows of 16
+// tagged entries (128 KB), the 4-byte table single tagged entries.  A position reads its whole row with four 16-byte
+// loads, filters the ways by tag, and measures every surviving candidate exactly (up to LZ_QCAP bytes): the lanes of a
+// warp take their hits one per round, so a round costs one measurement whatever way the hits sit in.  Blocks above
+// 64 KB leave shared memory to the tables and read the block through L1 (BIG).
+// -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pick16(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint32_t y) {
+  const uint4 q = (y & 8) ? ((y & 4) ? d : c) : ((y & 4) ? b : a);
+  return (y & 2) ? ((y & 1) ? q.w : q.z) : ((y & 1) ? q.y : q.x);
+}
+
+template <int BIG>
+__global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_rows_kernel(EsdArgs K) {
+  constexpr uint32_t block_max = BIG ? 131072u : 65536u;
+  extern __shared__ __align__(128) uint8_t smem[];
+  MatchCtl *const ctl = reinterpret_cast<MatchCtl *>(smem);
+  uint8_t *const in_base = smem + 128;                                         // 16-byte aligned (unused when BIG)
+  uint32_t *const rows = reinterpret_cast<uint32_t *>(in_base + (BIG ? 0u : block_max + LZ_IN_PAD));
+  uint32_t *const tabs = rows + ((size_t)LZ_ROW_WAYS << K.E.long_log);
+  uint32_t *const first1 = tabs + ((size_t)1 << K.E.hash_log);
+  uint32_t *const first2 = first1 + (1u << LZ_FIRST_LOG);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid >> LZ_WIN_LOG;                     // warp-uniform
+  const uint32_t t = (uint32_t)tid & (LZ_WIN - 1u);
+  const EncodeArgs &A = K.A;
+  const bool blocks_only = A.block_mode != 0;
+  const int hash_log = K.E.hash_log, long_log = K.E.long_log, hash_bytes = K.E.hash_bytes;
+
+  if (tid == 0) mbar_init(&ctl->mbar, 1);
+  __syncthreads();
+
+  uint32_t phase = 0;
+  for (;;) {
+    if (tid == 0) {
+      const uint32_t idx = atomicAdd(K.work_head, 1u);
+      uint32_t item = 0xFFFFFFFFu;
+      if (K.list) { if (idx < *K.list_count) item = K.list[idx]; }
+      else if (idx < K.wave_n) item = K.wave_base + idx;
+      ctl->item = item;
+    }
+    __syncthreads();
+    const uint32_t item = ctl->item;
+    if (item == 0xFFFFFFFFu) break;
+    uint8_t *const slot = K.slots + (size_t)(item - K.wave_base) * K.slot_bytes;
+    BlockHdr *const hdr = reinterpret_cast<BlockHdr *>(slot);
+    const uint8_t *const chunk = (const uint8_t *)A.in_ptrs[item];
+    const size_t n = A.in_sizes[item];
+    uint8_t *const dst = (uint8_t *)A.out_ptrs[item];
+    const size_t cap = A.out_sizes[item];
+    uint32_t status = ST_OK;
+    if (!chunk || !dst) status = ST_INVALID_PARAMETER;
+    else if (n == 0) status = ST_INVALID_PARAMETER;                       // reference: manager.cu:1554-1558
+    else if (n > 0xFFFF0000ull) status = ST_UNSUPPORTED;
+    else if (blocks_only && n > BLOCK_BYTES) status = ST_INVALID_PARAMETER;
+    else {
+      const size_t nblocks = (n + BLOCK_BYTES - 1) / BLOCK_BYTES;
+      if (cap < (blocks_only ? 0 : (size_t)frame_header_size(n) + (A.prm.checksum ? 4 : 0)) + n + 3 * nblocks) status = ST_BUFFER_TOO_SMALL;
+    }
+    if (status != ST_OK || n > block_max) {
+      if (tid == 0) {
+        if (status != ST_OK) {
+          A.out_sizes[item] = 0;
+          if (A.statuses) A.statuses[item] = status;
+          hdr->kind = KIND_SKIP;
+        } else if (n > K.slot_block_max) {
+          K.big_list[atomicAdd(K.big_count, 1u)] = item;
+          hdr->kind = KIND_SKIP;
+        } else K.defer_list[atomicAdd(K.defer_count, 1u)] = item;
+      }
+      __syncthreads();
+      continue;
+    }
+    const uint32_t bn = (uint32_t)n;
+    const uint32_t delta = (uint32_t)((uintptr_t)chunk & 15);
+    if (!BIG && tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t total = (delta + bn + 15u) & ~15u;
+      mbar_arrive_tx(&ctl->mbar, total);
+      const uint8_t *src = chunk - delta;
+      for (uint32_t o = 0; o < total; o += 16384u) bulk_g2s(in_base + o, src + o, min(16384u, total - o), &ctl->mbar);
+    }
+    {
+      uint4 *z = reinterpret_cast<uint4 *>(rows);
+      const uint32_t vecs = (uint32_t)((((size_t)4 * LZ_ROW_WAYS) << long_log) + ((size_t)4 << hash_log)) >> 4;
+      for (uint32_t i = tid; i < vecs; i += MATCH_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = tid; i < (2u << LZ_FIRST_LOG); i += MATCH_THREADS) first1[i] = 0xFFFFFFFFu;
+    }
+    if (!BIG) { mbar_wait(&ctl->mbar, phase); phase ^= 1; }
+    auto rd = [&](uint32_t q) -> uint64_t { return BIG ? rd64(chunk, q) : lds64(in_base, delta + q); };
+    auto byte_at = [&](uint32_t q) -> uint32_t { return BIG ? (uint32_t)chunk[q] : (uint32_t)in_base[delta + q]; };
+    bool rle = false;
+    {
+      const uint32_t b0 = byte_at(0);
+      bool same = true;
+      if ((uint32_t)tid < min(bn, 32u)) same = byte_at((uint32_t)tid) == b0;
+      if (__syncthreads_and(same)) {
+        for (uint32_t i = tid; i < bn && same; i += MATCH_THREADS) same = byte_at(i) == b0;
+        rle = __syncthreads_and(same) && bn > 1;
+      }
+    }
+    __syncthreads();                                                       // tables cleared
+    if (tid == 0) hdr->kind = rle ? KIND_RLE : KIND_PARSED;
+    if (!rle) {
+      const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
+      const uint32_t nwin = (ilimit + LZ_WIN - 1) / LZ_WIN;
+      uint32_t *const Rg = reinterpret_cast<uint32_t *>(slot + slot_r_off(K.slot_block_max));
+      uint32_t *const Mg = reinterpret_cast<uint32_t *>(slot + slot_map_off());
+      const int next_grp = (grp + 1) & (MATCH_GROUPS - 1);
+      constexpr uint32_t KEY_HMASK = (1u << LZ_KEY_HBITS) - 1u;
+      const uint32_t tkey = t << LZ_KEY_HBITS;
+      for (uint32_t w = (uint32_t)grp; w < nwin; w += MATCH_GROUPS) {
+        const uint32_t p = w * LZ_WIN + t;
+        const bool act = p < ilimit;
+        const uint64_t v = act ? rd(p) : 0ull;
+        const uint32_t h1 = hash_short(v, hash_bytes, hash_log), h2 = hash_long(v, long_log);
+        const uint32_t tg1 = short_tag(v), tg2 = row_tag(v);
+        const uint32_t hp1 = __shfl_up_sync(0xffffffffu, h1, 1), hp2 = __shfl_up_sync(0xffffffffu, h2, 1);
+        const bool ins1 = act && inserts((uint32_t)lane, h1, hp1), ins2 = act && inserts((uint32_t)lane, h2, hp2);
+        const uint32_t s1 = h1 >> (hash_log - LZ_FIRST_LOG), s2 = h2 >> (long_log - LZ_FIRST_LOG);
+        if (w > 0) bar_sync(5 + grp, 2 * (int)LZ_WIN);
+        // phase 1: my row and my short entry as the windows before left them, first-of-window side tables
+        const uint32_t tagw = (~w & 0x1FFu) << 23;
+        const uint32_t k1 = tagw | (h1 & KEY_HMASK), k2 = tagw | (h2 & KEY_HMASK);
+        const uint4 *const rowp = reinterpret_cast<const uint4 *>(rows + (size_t)h2 * LZ_ROW_WAYS);
+        const uint4 ra = rowp[0], rb = rowp[1], rc = rowp[2], rdd = rowp[3];
+        const uint32_t e1 = tabs[h1];
+        if (ins1) atomicMin(&first1[s1], k1 | tkey);
+        if (ins2) atomicMin(&first2[s2], k2 | tkey);
+        bar_sync(1 + grp, (int)LZ_WIN);
+        // phase 2: inserts (way = window mod 16, highest position wins), side-table candidates
+        if (ins2) atomicMax(&rows[(size_t)h2 * LZ_ROW_WAYS + (w & (LZ_ROW_WAYS - 1))], row_entry(p, tg2));
+        if (ins1) atomicMax(&tabs[h1], row_entry(p, tg1));
+        const uint32_t x1 = first1[s1] ^ k1, x2 = first2[s2] ^ k2;
+        if (w + 1 < nwin) bar_arrive(5 + next_grp, 2 * (int)LZ_WIN);
+        // off the chain: hits = candidates whose tag fits (bits 0-15: ways, 16: first of window (8-byte), 17: first of
+        // window (4-byte), 18: short entry); every round measures one hit per lane
+        uint32_t r = 0;
+        uint32_t hits = 0;
+        const uint32_t base_p = p - t;
+        if (act) {
+#pragma unroll
+          for (int y = 0; y < 16; y++) {
+            const uint32_t e = pick16(ra, rb, rc, rdd, (uint32_t)y);
+            if ((e & 0x7FFFu) == tg2 && (e >> 15) < p) hits |= 1u << y;
+          }
+          if (x2 < tkey && (x2 & KEY_HMASK) == 0) hits |= 1u << 16;
+          if (x1 < tkey && (x1 & KEY_HMASK) == 0) hits |= 1u << 17;
+          if ((e1 & 0x7FFFu) == tg1 && (e1 >> 15) < p) hits |= 1u << 18;
+        }
+        uint32_t best_len = 0, best_off = 0;
+        while (__any_sync(0xffffffffu, hits != 0)) {
+          if (hits) {
+            const uint32_t y = (uint32_t)__ffs((int)hits) - 1;
+            hits &= hits - 1;
+            const uint32_t c = y < 16 ? pick16(ra, rb, rc, rdd, y) >> 15 : y == 16 ? base_p + (x2 >> LZ_KEY_HBITS) : y == 17 ? base_p + (x1 >> LZ_KEY_HBITS) : e1 >> 15;
+            take_better(p, c, match_len_q(rd, p, c, bn), best_len, best_off);
+          }
+        }
+        if (act) {
+          r = best_len >= LZ_Q_MIN_MATCH ? (best_off | (best_len << 17)) : 0u;
+          Rg[p] = r;
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, r != 0);
+        if (lane == 0) Mg[p >> 5] = any;
+      }
+    }
+    __syncthreads();                              // every warp is done with the staged block and the tables
+  }
+}
+
+// SELECT, levels 5-9: the shared walk (select_walk / select_rewalk of zstd_encode_lz.cuh) as it stands, lane by lane --
+// the lazy decisions of these levels read more of R and measure repeat-offset matches exactly, and the match kernel is
+// what bounds these levels
+constexpr int SELQ_WARPS = 4;
+// -----------------------------------------------------------------------------------------------------------------
 // SELECT: one warp per block, lane j walks sub-segment j.
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int SEL_WARPS = 4;
@@ -477,6 +653,48 @@ __global__ void __launch_bounds__(32 * SEL_WARPS) zstd_lz_select_kernel(SelArgs 
   reinterpret_cast<LaneHdr *>(slot + 16)[lane] = h;
 }
 
+__global__ void __launch_bounds__(32 * SELQ_WARPS) zstd_lz_select_rows_kernel(SelArgs S) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t idx = blockIdx.x * SELQ_WARPS + (threadIdx.x >> 5);
+  if (idx >= S.wave_n) return;
+  const uint32_t item = S.wave_base + idx;
+  uint8_t *const slot = S.slots + (size_t)idx * S.slot_bytes;
+  if (reinterpret_cast<const BlockHdr *>(slot)->kind != KIND_PARSED) return;
+  const uint8_t *const in = (const uint8_t *)S.A.in_ptrs[item];
+  const uint32_t bn = (uint32_t)S.A.in_sizes[item];
+  const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
+  const uint32_t *const R = reinterpret_cast<const uint32_t *>(slot + slot_r_off(S.slot_block_max));
+  const uint32_t cap = lane_list_cap(S.slot_block_max);
+  Seq *const spec = reinterpret_cast<Seq *>(slot + slot_spec_off(S.slot_block_max)) + (size_t)lane * cap;
+  Seq *const prefix = reinterpret_cast<Seq *>(slot + slot_pre_off(S.slot_block_max)) + (size_t)lane * cap;
+  const SelectParams SP{S.lazy, 1};
+  const uint32_t span = lane_span(ilimit);
+  const uint32_t B = lane_begin((uint32_t)lane, span, ilimit), E = lane_begin((uint32_t)lane + 1, span, ilimit);
+  State st{B, B, 0, 0, 0};
+  if (lane == 0 && !(S.A.block_mode != 0 && item != 0)) { st.r0 = 1; st.r1 = 4; st.r2 = 8; }
+  const State spec0 = st;
+  const uint32_t spec_cnt = select_walk(in, bn, R, E, SP, st, spec);
+  const State spec_exit = st;
+  State exit_state = st, entry_used = spec0;
+  uint32_t pre_cnt = 0, sync_k = 0;
+  __syncwarp();
+  for (;;) {
+    const State entry = shfl_up_state(exit_state);
+    const bool need = lane > 0 && !entry.same(entry_used);
+    if (!__any_sync(0xffffffffu, need)) break;
+    if (need) {
+      entry_used = entry;
+      State s2 = entry;
+      pre_cnt = select_rewalk(in, bn, R, E, SP, s2, spec, spec_cnt, spec0, spec_exit, prefix, &sync_k);
+      exit_state = s2;
+    }
+    __syncwarp();
+  }
+  LaneHdr h;
+  h.spec_cnt = (uint16_t)spec_cnt; h.sync_k = (uint16_t)sync_k; h.pre_cnt = (uint16_t)pre_cnt; h.pad = 0;
+  reinterpret_cast<LaneHdr *>(slot + 16)[lane] = h;
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 // FINISH: one warp per block.  Joins the lane lists into the three sequence arrays, gathers the literals from the
 // input, codes the block and writes the frame (or the bare block in block mode).
@@ -612,6 +830,18 @@ size_t match_smem_bytes(const EsdParams &e, int big) {
   return 128 + in + tabs + ((size_t)8 << LZ_FIRST_LOG);
 }
 
+size_t rows_smem_bytes(const EsdParams &e, int big) {
+  const size_t in = big ? 0 : 65536u + LZ_IN_PAD;
+  return 128 + in + (((size_t)4 * LZ_ROW_WAYS) << e.long_log) + ((size_t)4 << e.hash_log) + ((size_t)8 << LZ_FIRST_LOG);
+}
+template <int BIG> cudaError_t rows_launch_one(const EsdArgs &k, int grid, cudaStream_t stream) {
+  const size_t smem = rows_smem_bytes(k.E, BIG);
+  cudaError_t e = cudaFuncSetAttribute(zstd_lz_rows_kernel<BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  zstd_lz_rows_kernel<BIG><<<grid, MATCH_THREADS, smem, stream>>>(k);
+  return cudaGetLastError();
+}
+
 template <int DFAST, int BIG> cudaError_t match_launch_one(const EsdArgs &k, int grid, cudaStream_t stream) {
   const size_t smem = match_smem_bytes(k.E, BIG);
   cudaError_t e = cudaFuncSetAttribute(zstd_lz_match_kernel<DFAST, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -675,7 +905,7 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
       k.work_head = c + 0;
       k.defer_list = list128 + k.wave_base; k.defer_count = c + 3;
       const int grid = (int)min((size_t)k.wave_n, (size_t)L.sm_count);
-      e = k.E.dfast ? match_launch_one<1, 0>(k, grid, stream) : match_launch_one<0, 0>(k, grid, stream);
+      e = k.E.rows ? rows_launch_one<0>(k, grid, stream) : k.E.dfast ? match_launch_one<1, 0>(k, grid, stream) : match_launch_one<0, 0>(k, grid, stream);
       if (e != cudaSuccess) return e;
       nl++;
     }
@@ -685,7 +915,7 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
       k.work_head = c + 1;
       k.defer_list = nullptr; k.defer_count = nullptr;
       const int grid = (int)min((size_t)k.wave_n, (size_t)L.sm_count);
-      e = k.E.dfast ? match_launch_one<1, 1>(k, grid, stream) : match_launch_one<0, 1>(k, grid, stream);
+      e = k.E.rows ? rows_launch_one<1>(k, grid, stream) : k.E.dfast ? match_launch_one<1, 1>(k, grid, stream) : match_launch_one<0, 1>(k, grid, stream);
       if (e != cudaSuccess) return e;
       nl++;
     }
@@ -694,7 +924,8 @@ cudaError_t launch_encode_esd(const EncodeArgs &args, const EsdLaunch &L, cudaSt
     s.slots = L.scratch; s.slot_bytes = slot_bytes; s.slot_block_max = bm;
     s.wave_base = k.wave_base; s.wave_n = k.wave_n;
     s.lazy = esd_params_for_level(args.prm.level, 0).lazy;
-    zstd_lz_select_kernel<<<(k.wave_n + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, stream>>>(s);
+    if (esd_params_for_level(args.prm.level, 0).rows) zstd_lz_select_rows_kernel<<<(k.wave_n + SELQ_WARPS - 1) / SELQ_WARPS, 32 * SELQ_WARPS, 0, stream>>>(s);
+    else zstd_lz_select_kernel<<<(k.wave_n + SEL_WARPS - 1) / SEL_WARPS, 32 * SEL_WARPS, 0, stream>>>(s);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     nl++;
     FinArgs f{};

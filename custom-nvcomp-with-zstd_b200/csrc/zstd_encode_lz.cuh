@@ -68,6 +68,7 @@ ZHD uint64_t rd64(const uint8_t *in, uint32_t p) {
   return v;
 #endif
 }
+ZHD uint32_t min_u32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 ZHD uint32_t common8(uint64_t a, uint64_t b) {
   const uint32_t xl = (uint32_t)a ^ (uint32_t)b, xh = (uint32_t)(a >> 32) ^ (uint32_t)(b >> 32);
 #if defined(__CUDA_ARCH__)
@@ -89,6 +90,33 @@ ZHD uint32_t count_fwd(const uint8_t *in, uint32_t a, uint32_t off, uint32_t n) 
   }
   while (a + len < n && rd8(in, a + len) == rd8(in, a + len - off)) len++;
   return len;
+}
+
+// ---- levels 5+: rows.  A bucket of the 8-byte table is a row of LZ_ROW_WAYS entries "position << 15 | tag"; window w
+// writes way (w mod LZ_ROW_WAYS) of a row with atomicMax, so a row keeps, per way, the highest position among the windows
+// that map to it: up to 16 recent occurrences from different neighbourhoods, deterministic, no counters.  The tag (15 more
+// hash bits) filters the ways before any byte is compared. ----
+constexpr int LZ_ROW_WAYS = 16;
+constexpr uint32_t LZ_QCAP = 128;         // rows: matches are measured up to this length (the walk finishes longer ones)
+constexpr uint32_t LZ_Q_MIN_MATCH = 4;
+ZHD uint32_t row_tag(uint64_t v) { const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32); return ((lo * 3266489917u) ^ (hi * 668265263u)) >> 17; }
+ZHD uint32_t row_entry(uint32_t p, uint32_t tag) { return (p << 15) | tag; }
+ZHD uint32_t short_tag(uint64_t v) { return (((uint32_t)v) * 3266489917u) >> 17; }          // of the 4 hashed bytes
+// exact common length of the bytes at p and at c (< p), up to LZ_QCAP and the end of the block
+template <typename Rd64>
+ZHD uint32_t match_len_q(const Rd64 &rd, uint32_t p, uint32_t c, uint32_t n) {
+  uint32_t len = 0;
+  while (len < LZ_QCAP && p + len + 8 <= n) {
+    const uint32_t k = common8(rd(p + len), rd(c + len));
+    len += k;
+    if (k < 8) break;
+  }
+  return len > LZ_QCAP ? LZ_QCAP : len;
+}
+// keeps the longer match, the nearer one on a tie
+ZHD void take_better(uint32_t p, uint32_t c, uint32_t len, uint32_t &best_len, uint32_t &best_off) {
+  const uint32_t off = p - c;
+  if (len > best_len || (len == best_len && len != 0 && off < best_off)) { best_len = len; best_off = off; }
 }
 
 // ---- MATCH stage, per position (the kernel runs the same arithmetic on the block staged in shared memory) ----
@@ -154,7 +182,7 @@ ZHD uint32_t seq_start(const Seq &q) { return q.x & LZ_OFF_MASK; }
 ZHD uint32_t seq_len(const Seq &q) { return (q.x >> 17) | ((q.y >> 18) << 15); }
 ZHD uint32_t seq_code(const Seq &q) { return q.y & ((1u << 18) - 1); }
 
-struct SelectParams { int lazy; };
+struct SelectParams { int lazy; int rows; };
 
 // One decision of the walk at st.ip (< lim).  Either emits one sequence (returns true, *out filled) or skips literals.
 // n: block bytes; lim: first position this lane does not decide.
@@ -176,6 +204,10 @@ ZHD bool select_step(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t 
       if (ip >= st.r0 && ip != st.anchor) rl0 = common8(rd64(in, ip), rd64(in, ip - st.r0));
       if (ip + 1 >= st.r0 && ip + 1 < lim) rl1 = common8(rd64(in, ip + 1), rd64(in, ip + 1 - st.r0));
     }
+    if (P.rows) {           // levels 5+ compare exact lengths: finish the measurement of a repeat-offset match that filled its 8 bytes
+      if (rl0 == 8) rl0 += count_fwd(in, ip + 8, st.r0, min_u32(n, ip + LZ_QCAP));
+      if (rl1 == 8) rl1 += count_fwd(in, ip + 9, st.r0, min_u32(n, ip + 1 + LZ_QCAP));
+    }
     const bool t0 = e0 != 0, r0ok = rl0 >= 4, r1ok = rl1 >= 4;
     if (!t0 && !r0ok && !r1ok) {
       uint32_t q = ip + 1;
@@ -184,7 +216,35 @@ ZHD bool select_step(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t 
       return false;
     }
     bool open;
-    if (r0ok && (!t0 || rl0 == 8 || rl0 + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r0; len = rl0; open = rl0 == 8; }
+    if (P.rows) {
+      // levels 5+: compare by gain (4 bits per matched byte minus the offset's cost; a repeat offset costs nothing),
+      // then up to P.lazy positions further on may displace the choice when they gain more than the delay costs
+      const uint32_t cap = LZ_QCAP;
+      auto gain = [](uint32_t l, uint32_t o, bool rep) { return (int)(l * 4) - (rep ? 0 : enc::hb32(o + 1)); };
+      s = ip;
+      if (r0ok && (!t0 || gain(rl0, st.r0, true) + 4 >= gain(lt0, e0 & LZ_OFF_MASK, false))) { off = st.r0; len = rl0; open = rl0 >= cap; }
+      else if (t0) { off = e0 & LZ_OFF_MASK; len = lt0; open = len == cap; }
+      else { off = 0; len = 0; open = false; }
+      int g0 = len ? gain(len, off, off == st.r0) : -1000;
+      for (int step = 1; step <= P.lazy; step++) {
+        const uint32_t q = ip + (uint32_t)step;
+        if (q >= lim) break;
+        const uint32_t eq = step == 1 ? e1 : R[q];
+        uint32_t o2 = eq & LZ_OFF_MASK, l2 = eq >> 17;
+        bool rep2 = false, open2 = l2 == cap;
+        uint32_t rq = 0;
+        if (st.r0 != 0 && q >= st.r0) {
+          if (step == 1) rq = rl1;
+          else { rq = common8(rd64(in, q), rd64(in, q - st.r0)); if (rq == 8) rq += count_fwd(in, q + 8, st.r0, min_u32(n, q + LZ_QCAP)); }
+        }
+        if (rq >= 4 && (l2 == 0 || gain(rq, st.r0, true) + 4 >= gain(l2, o2, false))) { o2 = st.r0; l2 = rq; rep2 = true; open2 = rq >= cap; }
+        if (l2 == 0) continue;
+        const int g2 = gain(l2, o2, rep2);
+        if (g2 > g0 + 3 * step) { s = q; off = o2; len = l2; open = open2; g0 = g2; }
+      }
+      if (len == 0) { st.ip = ip + 1; return false; }       // only a too-short candidate at ip + 1 / ip + 2 brought us here
+    }
+    else if (r0ok && (!t0 || rl0 == 8 || rl0 + LZ_REP_BONUS >= lt0)) { s = ip; off = st.r0; len = rl0; open = rl0 == 8; }
     else if (r1ok && (!t0 || rl1 == 8 || rl1 + LZ_REP_BONUS >= lt0)) { s = ip + 1; off = st.r0; len = rl1; open = rl1 == 8; }
     else {
       uint32_t e = e0;

@@ -70,19 +70,28 @@ ZP_HD EncodeParams encode_params_for_level(int level, int checksum) {
 // speculatively and are stitched together exactly), and a third kernel codes the block.  libzstd's <= 128 KB rows for
 // these levels are fast (L1-2) and dfast (L3-4); sizes land within +-2 % of them or below (tools/model_ratio.cpp,
 // tests/test_gpu_encode.py).  The parse arithmetic lives in zstd_encode_lz.cuh.
+#ifndef LZ_MAX_LEVEL
+#define LZ_MAX_LEVEL 9
+#endif
 struct EsdParams {
   int dfast;          // 0: one table (FAST), 1: 5-byte table + 8-byte "long" table (DFAST)
   int hash_log;       // primary table: 1 << hash_log uint32 entries
   int hash_bytes;     // bytes hashed for the primary table
   int long_log;       // 8-byte-hash table; 0 = absent
   int lazy;           // 1: the position after the first candidate may replace it when its match is longer
+  int rows;           // levels 5+: the 8-byte table holds rows of LZ_ROW_WAYS tagged entries, matches are measured up to
+                      // LZ_QCAP bytes and the walk is lazy by gain with depth `lazy` (0, 1, 2); 0: the levels 1-4 form
 };
-ZP_HD bool esd_level(int level) { return level <= 4; }
+ZP_HD bool esd_level(int level) { return level <= LZ_MAX_LEVEL; }
 // big: the 128 KB block geometry (the block itself takes twice the shared memory, the tables half)
 ZP_HD EsdParams esd_params_for_level(int level, int big) {
   EsdParams e{};
   if (level <= 2) { e.dfast = 0; e.hash_log = big ? 14 : 15; e.hash_bytes = level <= 1 ? 6 : 5; e.long_log = 0; e.lazy = level >= 2 ? 1 : 0; }
-  else { e.dfast = 1; e.hash_log = big ? 13 : 14; e.hash_bytes = 5; e.long_log = big ? 13 : 14; e.lazy = 1; }
+  else if (level <= 4) { e.dfast = 1; e.hash_log = big ? 13 : 14; e.hash_bytes = 5; e.long_log = big ? 13 : 14; e.lazy = 1; }
+  else {
+    // rows: 2^11 rows x 16 ways x 4 B = 128 KB for the 8-byte hash, 2^12 single entries for the 4-byte hash
+    e.dfast = 1; e.rows = 1; e.hash_log = 12; e.hash_bytes = 4; e.long_log = 11; e.lazy = level == 5 ? 0 : level == 6 ? 1 : 2;
+  }
   return e;
 }
 

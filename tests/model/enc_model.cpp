@@ -187,7 +187,47 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
   using namespace b200zstd::lz;
   const uint32_t ilimit = bn > 8 ? bn - 8 : 0;
   std::vector<uint32_t> R((size_t)bn + 8, 0);
-  {
+  if (EP.rows) {
+    // levels 5+: rows of tagged entries for the 8-byte hash, single tagged entries for the 4-byte hash
+    std::vector<uint32_t> rows((size_t)LZ_ROW_WAYS << EP.long_log, 0), tabs((size_t)1 << EP.hash_log, 0);
+    std::vector<uint32_t> first1((size_t)1 << LZ_FIRST_LOG, 0xFFFFFFFFu), first2((size_t)1 << LZ_FIRST_LOG, 0xFFFFFFFFu);
+    auto rd = [&](uint32_t p) { return rd64(b, p); };
+    std::vector<uint32_t> h1(LZ_WIN + 1, 0), h2(LZ_WIN + 1, 0);
+    std::vector<uint32_t> snap((size_t)LZ_WIN * (LZ_ROW_WAYS + 1));
+    for (uint32_t w = 0; w * LZ_WIN < ilimit; w++) {
+      const uint32_t w0 = w * LZ_WIN, w1 = std::min(w0 + LZ_WIN, ilimit);
+      for (uint32_t p = w0; p < w1; p++) {              // phase 1: state before the window, side tables
+        const uint32_t t = p - w0;
+        const uint64_t v = rd64(b, p);
+        h1[t + 1] = hash_short(v, EP.hash_bytes, EP.hash_log);
+        h2[t + 1] = hash_long(v, EP.long_log);
+        for (int y = 0; y < LZ_ROW_WAYS; y++) snap[(size_t)t * (LZ_ROW_WAYS + 1) + y] = rows[(size_t)h2[t + 1] * LZ_ROW_WAYS + y];
+        snap[(size_t)t * (LZ_ROW_WAYS + 1) + LZ_ROW_WAYS] = tabs[h1[t + 1]];
+        if (inserts(p, h1[t + 1], h1[t])) { uint32_t &f = first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)]; f = std::min(f, first_key(w, t, h1[t + 1])); }
+        if (inserts(p, h2[t + 1], h2[t])) { uint32_t &f = first2[h2[t + 1] >> (EP.long_log - LZ_FIRST_LOG)]; f = std::min(f, first_key(w, t, h2[t + 1])); }
+      }
+      for (uint32_t p = w0; p < w1; p++) {              // phase 2: inserts, candidates, exact measurement
+        const uint32_t t = p - w0;
+        const uint64_t v = rd64(b, p);
+        const uint32_t tg2 = row_tag(v), tg1 = short_tag(v);
+        if (inserts(p, h2[t + 1], h2[t])) { uint32_t &e = rows[(size_t)h2[t + 1] * LZ_ROW_WAYS + (w & (LZ_ROW_WAYS - 1))]; e = std::max(e, row_entry(p, tg2)); }
+        if (inserts(p, h1[t + 1], h1[t])) { uint32_t &e = tabs[h1[t + 1]]; e = std::max(e, row_entry(p, tg1)); }
+        uint32_t best_len = 0, best_off = 0;
+        const int32_t a2 = first_candidate(first2[h2[t + 1] >> (EP.long_log - LZ_FIRST_LOG)], w, t, h2[t + 1]);
+        if (a2 >= 0) take_better(p, (uint32_t)a2, match_len_q(rd, p, (uint32_t)a2, bn), best_len, best_off);
+        for (int y = 0; y < LZ_ROW_WAYS; y++) {
+          const uint32_t e = snap[(size_t)t * (LZ_ROW_WAYS + 1) + y], c = e >> 15;
+          if ((e & 0x7FFFu) == tg2 && c < p) take_better(p, c, match_len_q(rd, p, c, bn), best_len, best_off);
+        }
+        const int32_t a1 = first_candidate(first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)], w, t, h1[t + 1]);
+        if (a1 >= 0) take_better(p, (uint32_t)a1, match_len_q(rd, p, (uint32_t)a1, bn), best_len, best_off);
+        { const uint32_t e = snap[(size_t)t * (LZ_ROW_WAYS + 1) + LZ_ROW_WAYS], c = e >> 15;
+          if ((e & 0x7FFFu) == tg1 && c < p) take_better(p, c, match_len_q(rd, p, c, bn), best_len, best_off); }
+        R[p] = best_len >= LZ_Q_MIN_MATCH ? (best_off | (best_len << 17)) : 0u;
+      }
+      h1[0] = h1[w1 - w0]; h2[0] = h2[w1 - w0];
+    }
+  } else {
     // table entries are positions; a never-written bucket reads as position 0 (a candidate like any other: the bytes decide)
     std::vector<uint32_t> tab1((size_t)1 << EP.hash_log, 0), tab2(EP.dfast ? (size_t)1 << EP.long_log : 0, 0);
     std::vector<uint32_t> first1((size_t)1 << LZ_FIRST_LOG, 0xFFFFFFFFu), first2((size_t)1 << LZ_FIRST_LOG, 0xFFFFFFFFu);
@@ -230,7 +270,7 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
       h1[0] = h1[w1 - w0]; h2[0] = h2[w1 - w0];
     }
   }
-  SelectParams SP{EP.lazy};
+  SelectParams SP{EP.lazy, EP.rows};
   const uint32_t span = lane_span(ilimit), cap = lane_list_cap(BLOCK_BYTES);
   std::vector<Seq> spec((size_t)LZ_LANES * cap), prefix((size_t)LZ_LANES * cap);
   State spec0[LZ_LANES], spec_exit[LZ_LANES], exit_[LZ_LANES], entry_used[LZ_LANES];
