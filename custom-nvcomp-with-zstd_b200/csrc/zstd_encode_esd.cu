@@ -417,19 +417,19 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_rows_kernel(EsdArgs 
         if (ins1) atomicMax(&tabs[h1], row_entry(p, tg1));
         const uint32_t x1 = first1[s1] ^ k1, x2 = first2[s2] ^ k2;
         if (w + 1 < nwin) bar_arrive(5 + next_grp, 2 * (int)LZ_WIN);
-        // off the chain: hits = candidates whose tag fits (bits 0-15: ways, 16: first of window (8-byte), 17: first of
-        // window (4-byte), 18: short entry); every round measures one hit per lane
+        // off the chain: hits = candidates whose tag fits, in the order they are tried (bit 0: first of window for the
+        // 8-byte hash, 1: for the 4-byte hash, 2-17: ways 0-15, 18: the 4-byte entry); every round tries one hit per lane
         uint32_t r = 0;
         uint32_t hits = 0;
         const uint32_t base_p = p - t;
         if (act) {
+          if (x2 < tkey && (x2 & KEY_HMASK) == 0) hits |= 1u;
+          if (x1 < tkey && (x1 & KEY_HMASK) == 0) hits |= 2u;
 #pragma unroll
           for (int y = 0; y < 16; y++) {
             const uint32_t e = pick16(ra, rb, rc, rdd, (uint32_t)y);
-            if ((e & 0x7FFFu) == tg2 && (e >> 15) < p) hits |= 1u << y;
+            if ((e & 0x7FFFu) == tg2 && (e >> 15) < p) hits |= 4u << y;
           }
-          if (x2 < tkey && (x2 & KEY_HMASK) == 0) hits |= 1u << 16;
-          if (x1 < tkey && (x1 & KEY_HMASK) == 0) hits |= 1u << 17;
           if ((e1 & 0x7FFFu) == tg1 && (e1 >> 15) < p) hits |= 1u << 18;
         }
         uint32_t best_len = 0, best_off = 0;
@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_rows_kernel(EsdArgs 
           if (hits) {
             const uint32_t y = (uint32_t)__ffs((int)hits) - 1;
             hits &= hits - 1;
-            const uint32_t c = y < 16 ? pick16(ra, rb, rc, rdd, y) >> 15 : y == 16 ? base_p + (x2 >> LZ_KEY_HBITS) : y == 17 ? base_p + (x1 >> LZ_KEY_HBITS) : e1 >> 15;
-            take_better(p, c, match_len_q(rd, p, c, bn), best_len, best_off);
+            const uint32_t c = y == 0 ? base_p + (x2 >> LZ_KEY_HBITS) : y == 1 ? base_p + (x1 >> LZ_KEY_HBITS) : y < 18 ? pick16(ra, rb, rc, rdd, y - 2) >> 15 : e1 >> 15;
+            try_candidate(rd, p, c, bn, best_len, best_off);
           }
         }
         if (act) {

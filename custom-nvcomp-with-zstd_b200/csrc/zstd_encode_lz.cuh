@@ -97,8 +97,12 @@ ZHD uint32_t count_fwd(const uint8_t *in, uint32_t a, uint32_t off, uint32_t n) 
 // that map to it: up to 16 recent occurrences from different neighbourhoods, deterministic, no counters.  The tag (15 more
 // hash bits) filters the ways before any byte is compared. ----
 constexpr int LZ_ROW_WAYS = 16;
-constexpr uint32_t LZ_QCAP = 128;         // rows: matches are measured up to this length (the walk finishes longer ones)
+constexpr uint32_t LZ_QCAP = 64;         // rows: matches are measured up to this length (the walk finishes longer ones)
 constexpr uint32_t LZ_Q_MIN_MATCH = 4;
+#ifndef LZ_QTARGET_V
+#define LZ_QTARGET_V 48
+#endif
+constexpr uint32_t LZ_QTARGET = LZ_QTARGET_V;     // a match this long is good enough: the remaining candidates are not tried
 ZHD uint32_t row_tag(uint64_t v) { const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32); return ((lo * 3266489917u) ^ (hi * 668265263u)) >> 17; }
 ZHD uint32_t row_entry(uint32_t p, uint32_t tag) { return (p << 15) | tag; }
 ZHD uint32_t short_tag(uint64_t v) { return (((uint32_t)v) * 3266489917u) >> 17; }          // of the 4 hashed bytes
@@ -113,10 +117,22 @@ ZHD uint32_t match_len_q(const Rd64 &rd, uint32_t p, uint32_t c, uint32_t n) {
   }
   return len > LZ_QCAP ? LZ_QCAP : len;
 }
-// keeps the longer match, the nearer one on a tie
-ZHD void take_better(uint32_t p, uint32_t c, uint32_t len, uint32_t &best_len, uint32_t &best_off) {
-  const uint32_t off = p - c;
-  if (len > best_len || (len == best_len && len != 0 && off < best_off)) { best_len = len; best_off = off; }
+// Candidates are tried in a fixed order (first of window for the 8-byte and the 4-byte hash, ways 0..15, the 4-byte entry);
+// one replaces the best so far only when it is LONGER, and it is measured only when the 8 bytes that end one past the best
+// length already agree -- most ways of a row share the hashed bytes and little more, and fail that test after two loads.
+// can candidate c still be longer than best_len?  (false is final: a larger best_len only makes it harder)
+template <typename Rd64>
+ZHD bool may_improve(const Rd64 &rd, uint32_t p, uint32_t c, uint32_t n, uint32_t best_len) {
+  if (best_len >= LZ_QTARGET || p + best_len + 1 > n) return false;
+  if (best_len >= 7) return rd(p + best_len - 7) == rd(c + best_len - 7);
+  if (best_len > 0) return p + 8 <= n && common8(rd(p), rd(c)) > best_len;
+  return true;
+}
+template <typename Rd64>
+ZHD void try_candidate(const Rd64 &rd, uint32_t p, uint32_t c, uint32_t n, uint32_t &best_len, uint32_t &best_off) {
+  if (!may_improve(rd, p, c, n, best_len)) return;
+  const uint32_t len = match_len_q(rd, p, c, n);
+  if (len > best_len) { best_len = len; best_off = p - c; }
 }
 
 // ---- MATCH stage, per position (the kernel runs the same arithmetic on the block staged in shared memory) ----
@@ -205,8 +221,8 @@ ZHD bool select_step(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t 
       if (ip + 1 >= st.r0 && ip + 1 < lim) rl1 = common8(rd64(in, ip + 1), rd64(in, ip + 1 - st.r0));
     }
     if (P.rows) {           // levels 5+ compare exact lengths: finish the measurement of a repeat-offset match that filled its 8 bytes
-      if (rl0 == 8) rl0 += count_fwd(in, ip + 8, st.r0, min_u32(n, ip + LZ_QCAP));
-      if (rl1 == 8) rl1 += count_fwd(in, ip + 9, st.r0, min_u32(n, ip + 1 + LZ_QCAP));
+      if (rl0 == 8) rl0 += count_fwd(in, ip + 8, st.r0, n);
+      if (rl1 == 8) rl1 += count_fwd(in, ip + 9, st.r0, n);
     }
     const bool t0 = e0 != 0, r0ok = rl0 >= 4, r1ok = rl1 >= 4;
     if (!t0 && !r0ok && !r1ok) {
@@ -222,25 +238,29 @@ ZHD bool select_step(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t 
       const uint32_t cap = LZ_QCAP;
       auto gain = [](uint32_t l, uint32_t o, bool rep) { return (int)(l * 4) - (rep ? 0 : enc::hb32(o + 1)); };
       s = ip;
-      if (r0ok && (!t0 || gain(rl0, st.r0, true) + 4 >= gain(lt0, e0 & LZ_OFF_MASK, false))) { off = st.r0; len = rl0; open = rl0 >= cap; }
-      else if (t0) { off = e0 & LZ_OFF_MASK; len = lt0; open = len == cap; }
-      else { off = 0; len = 0; open = false; }
+      open = false;                                     // every length compared here is exact
+      // a table match that filled the match stage's cap is measured to its end before it is compared
+      auto full_len = [&](uint32_t e, uint32_t q) { uint32_t l = e >> 17; if (l == cap) l += count_fwd(in, q + l, e & LZ_OFF_MASK, n); return l; };
+      const uint32_t fl0 = t0 ? full_len(e0, ip) : 0u;
+      if (r0ok && (!t0 || gain(rl0, st.r0, true) + 4 >= gain(fl0, e0 & LZ_OFF_MASK, false))) { off = st.r0; len = rl0; }
+      else if (t0) { off = e0 & LZ_OFF_MASK; len = fl0; }
+      else { off = 0; len = 0; }
       int g0 = len ? gain(len, off, off == st.r0) : -1000;
       for (int step = 1; step <= P.lazy; step++) {
         const uint32_t q = ip + (uint32_t)step;
         if (q >= lim) break;
         const uint32_t eq = step == 1 ? e1 : R[q];
-        uint32_t o2 = eq & LZ_OFF_MASK, l2 = eq >> 17;
-        bool rep2 = false, open2 = l2 == cap;
+        uint32_t o2 = eq & LZ_OFF_MASK, l2 = eq ? full_len(eq, q) : 0u;
+        bool rep2 = false;
         uint32_t rq = 0;
         if (st.r0 != 0 && q >= st.r0) {
           if (step == 1) rq = rl1;
-          else { rq = common8(rd64(in, q), rd64(in, q - st.r0)); if (rq == 8) rq += count_fwd(in, q + 8, st.r0, min_u32(n, q + LZ_QCAP)); }
+          else { rq = common8(rd64(in, q), rd64(in, q - st.r0)); if (rq == 8) rq += count_fwd(in, q + 8, st.r0, n); }
         }
-        if (rq >= 4 && (l2 == 0 || gain(rq, st.r0, true) + 4 >= gain(l2, o2, false))) { o2 = st.r0; l2 = rq; rep2 = true; open2 = rq >= cap; }
+        if (rq >= 4 && (l2 == 0 || gain(rq, st.r0, true) + 4 >= gain(l2, o2, false))) { o2 = st.r0; l2 = rq; rep2 = true; }
         if (l2 == 0) continue;
         const int g2 = gain(l2, o2, rep2);
-        if (g2 > g0 + 3 * step) { s = q; off = o2; len = l2; open = open2; g0 = g2; }
+        if (g2 > g0 + 3 * step) { s = q; off = o2; len = l2; g0 = g2; }
       }
       if (len == 0) { st.ip = ip + 1; return false; }       // only a too-short candidate at ip + 1 / ip + 2 brought us here
     }

@@ -214,15 +214,15 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
         if (inserts(p, h1[t + 1], h1[t])) { uint32_t &e = tabs[h1[t + 1]]; e = std::max(e, row_entry(p, tg1)); }
         uint32_t best_len = 0, best_off = 0;
         const int32_t a2 = first_candidate(first2[h2[t + 1] >> (EP.long_log - LZ_FIRST_LOG)], w, t, h2[t + 1]);
-        if (a2 >= 0) take_better(p, (uint32_t)a2, match_len_q(rd, p, (uint32_t)a2, bn), best_len, best_off);
+        if (a2 >= 0) try_candidate(rd, p, (uint32_t)a2, bn, best_len, best_off);
+        const int32_t a1 = first_candidate(first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)], w, t, h1[t + 1]);
+        if (a1 >= 0) try_candidate(rd, p, (uint32_t)a1, bn, best_len, best_off);
         for (int y = 0; y < LZ_ROW_WAYS; y++) {
           const uint32_t e = snap[(size_t)t * (LZ_ROW_WAYS + 1) + y], c = e >> 15;
-          if ((e & 0x7FFFu) == tg2 && c < p) take_better(p, c, match_len_q(rd, p, c, bn), best_len, best_off);
+          if ((e & 0x7FFFu) == tg2 && c < p) try_candidate(rd, p, c, bn, best_len, best_off);
         }
-        const int32_t a1 = first_candidate(first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)], w, t, h1[t + 1]);
-        if (a1 >= 0) take_better(p, (uint32_t)a1, match_len_q(rd, p, (uint32_t)a1, bn), best_len, best_off);
         { const uint32_t e = snap[(size_t)t * (LZ_ROW_WAYS + 1) + LZ_ROW_WAYS], c = e >> 15;
-          if ((e & 0x7FFFu) == tg1 && c < p) take_better(p, c, match_len_q(rd, p, c, bn), best_len, best_off); }
+          if ((e & 0x7FFFu) == tg1 && c < p) try_candidate(rd, p, c, bn, best_len, best_off); }
         R[p] = best_len >= LZ_Q_MIN_MATCH ? (best_off | (best_len << 17)) : 0u;
       }
       h1[0] = h1[w1 - w0]; h2[0] = h2[w1 - w0];
