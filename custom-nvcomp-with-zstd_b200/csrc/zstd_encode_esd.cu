@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_rows_kernel(EsdArgs 
         const bool act = p < ilimit;
         const uint64_t v = act ? rd(p) : 0ull;
         const uint32_t h1 = hash_short(v, hash_bytes, hash_log), h2 = hash_long(v, long_log);
-        const uint32_t tg1 = short_tag(v), tg2 = row_tag(v);
+        const uint32_t tg1 = short_tag(v), tg2 = row_tag(v, (act && p + 12 <= bn) ? (uint32_t)(rd(p + 4) >> 32) : 0u);
         const uint32_t hp1 = __shfl_up_sync(0xffffffffu, h1, 1), hp2 = __shfl_up_sync(0xffffffffu, h2, 1);
         const bool ins1 = act && inserts((uint32_t)lane, h1, hp1), ins2 = act && inserts((uint32_t)lane, h2, hp2);
         const uint32_t s1 = h1 >> (hash_log - LZ_FIRST_LOG), s2 = h2 >> (long_log - LZ_FIRST_LOG);
@@ -418,27 +418,32 @@ __global__ void __launch_bounds__(MATCH_THREADS, 1) zstd_lz_rows_kernel(EsdArgs 
         const uint32_t x1 = first1[s1] ^ k1, x2 = first2[s2] ^ k2;
         if (w + 1 < nwin) bar_arrive(5 + next_grp, 2 * (int)LZ_WIN);
         // off the chain: hits = candidates whose tag fits, in the order they are tried (bit 0: first of window for the
-        // 8-byte hash, 1: for the 4-byte hash, 2-17: ways 0-15, 18: the 4-byte entry); every round tries one hit per lane
+        // 8-byte hash, 1: for the 4-byte hash, 2-17: strong ways 0-15, 18: the 4-byte entry, 19: the first weak way, tried
+        // only while nothing of 12 bytes is in hand); every round tries one hit per lane
         uint32_t r = 0;
-        uint32_t hits = 0;
+        uint32_t hits = 0, weak_c = 0xFFFFFFFFu;
         const uint32_t base_p = p - t;
         if (act) {
           if (x2 < tkey && (x2 & KEY_HMASK) == 0) hits |= 1u;
           if (x1 < tkey && (x1 & KEY_HMASK) == 0) hits |= 2u;
 #pragma unroll
-          for (int y = 0; y < 16; y++) {
+          for (int y = 15; y >= 0; y--) {
             const uint32_t e = pick16(ra, rb, rc, rdd, (uint32_t)y);
-            if ((e & 0x7FFFu) == tg2 && (e >> 15) < p) hits |= 4u << y;
+            if ((e >> 15) >= p || ((e ^ tg2) & LZ_TAG_HI) != 0) continue;
+            if (((e ^ tg2) & LZ_TAG_ALL) == 0) hits |= 4u << y;              // strong: the four bytes behind the hashed ones fit too
+            else weak_c = e >> 15;                                            // weak: fewer than 12 equal bytes; the first one is kept
           }
           if ((e1 & 0x7FFFu) == tg1 && (e1 >> 15) < p) hits |= 1u << 18;
+          if (weak_c != 0xFFFFFFFFu) hits |= 1u << 19;
         }
         uint32_t best_len = 0, best_off = 0;
         while (__any_sync(0xffffffffu, hits != 0)) {
           if (hits) {
             const uint32_t y = (uint32_t)__ffs((int)hits) - 1;
             hits &= hits - 1;
-            const uint32_t c = y == 0 ? base_p + (x2 >> LZ_KEY_HBITS) : y == 1 ? base_p + (x1 >> LZ_KEY_HBITS) : y < 18 ? pick16(ra, rb, rc, rdd, y - 2) >> 15 : e1 >> 15;
-            try_candidate(rd, p, c, bn, best_len, best_off);
+            const uint32_t c = y == 0 ? base_p + (x2 >> LZ_KEY_HBITS) : y == 1 ? base_p + (x1 >> LZ_KEY_HBITS) : y < 18 ? pick16(ra, rb, rc, rdd, y - 2) >> 15
+                               : y == 18 ? e1 >> 15 : weak_c;
+            if (y < 19 || best_len < 12) try_candidate(rd, p, c, bn, best_len, best_off);
           }
         }
         if (act) {

@@ -103,7 +103,14 @@ constexpr uint32_t LZ_Q_MIN_MATCH = 4;
 #define LZ_QTARGET_V 48
 #endif
 constexpr uint32_t LZ_QTARGET = LZ_QTARGET_V;     // a match this long is good enough: the remaining candidates are not tried
-ZHD uint32_t row_tag(uint64_t v) { const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32); return ((lo * 3266489917u) ^ (hi * 668265263u)) >> 17; }
+// tag of a row entry: 8 bits of the 8 hashed bytes (filters hash collisions) | 7 bits of the 4 bytes behind them.  A way
+// whose high part fits is a candidate; it is STRONG when the low part fits too (12 equal bytes but for a 1 / 128 chance) and
+// WEAK otherwise -- a weak way matches fewer than 12 bytes for certain.  next4: bytes 8..11 from p (0 near the block's end).
+ZHD uint32_t row_tag(uint64_t v, uint32_t next4) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  return ((((lo * 3266489917u) ^ (hi * 668265263u)) >> 24) << 7) | ((next4 * 2246822519u) >> 25);
+}
+constexpr uint32_t LZ_TAG_HI = 0x7F80u, LZ_TAG_ALL = 0x7FFFu;
 ZHD uint32_t row_entry(uint32_t p, uint32_t tag) { return (p << 15) | tag; }
 ZHD uint32_t short_tag(uint64_t v) { return (((uint32_t)v) * 3266489917u) >> 17; }          // of the 4 hashed bytes
 // exact common length of the bytes at p and at c (< p), up to LZ_QCAP and the end of the block

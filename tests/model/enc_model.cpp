@@ -209,7 +209,7 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
       for (uint32_t p = w0; p < w1; p++) {              // phase 2: inserts, candidates, exact measurement
         const uint32_t t = p - w0;
         const uint64_t v = rd64(b, p);
-        const uint32_t tg2 = row_tag(v), tg1 = short_tag(v);
+        const uint32_t tg2 = row_tag(v, p + 12 <= bn ? (uint32_t)(rd64(b, p + 4) >> 32) : 0u), tg1 = short_tag(v);
         if (inserts(p, h2[t + 1], h2[t])) { uint32_t &e = rows[(size_t)h2[t + 1] * LZ_ROW_WAYS + (w & (LZ_ROW_WAYS - 1))]; e = std::max(e, row_entry(p, tg2)); }
         if (inserts(p, h1[t + 1], h1[t])) { uint32_t &e = tabs[h1[t + 1]]; e = std::max(e, row_entry(p, tg1)); }
         uint32_t best_len = 0, best_off = 0;
@@ -217,12 +217,16 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
         if (a2 >= 0) try_candidate(rd, p, (uint32_t)a2, bn, best_len, best_off);
         const int32_t a1 = first_candidate(first1[h1[t + 1] >> (EP.hash_log - LZ_FIRST_LOG)], w, t, h1[t + 1]);
         if (a1 >= 0) try_candidate(rd, p, (uint32_t)a1, bn, best_len, best_off);
+        int weak = -1;                                   // first way that shares the hashed bytes only
         for (int y = 0; y < LZ_ROW_WAYS; y++) {
           const uint32_t e = snap[(size_t)t * (LZ_ROW_WAYS + 1) + y], c = e >> 15;
-          if ((e & 0x7FFFu) == tg2 && c < p) try_candidate(rd, p, c, bn, best_len, best_off);
+          if (c >= p || ((e ^ tg2) & LZ_TAG_HI) != 0) continue;
+          if (((e ^ tg2) & LZ_TAG_ALL) == 0) try_candidate(rd, p, c, bn, best_len, best_off);
+          else if (weak < 0) weak = y;
         }
         { const uint32_t e = snap[(size_t)t * (LZ_ROW_WAYS + 1) + LZ_ROW_WAYS], c = e >> 15;
           if ((e & 0x7FFFu) == tg1 && c < p) try_candidate(rd, p, c, bn, best_len, best_off); }
+        if (weak >= 0 && best_len < 12) try_candidate(rd, p, snap[(size_t)t * (LZ_ROW_WAYS + 1) + weak] >> 15, bn, best_len, best_off);
         R[p] = best_len >= LZ_Q_MIN_MATCH ? (best_off | (best_len << 17)) : 0u;
       }
       h1[0] = h1[w1 - w0]; h2[0] = h2[w1 - w0];
