@@ -858,7 +858,7 @@ template <int DFAST, int BIG> cudaError_t match_launch_one(const EsdArgs &k, int
 constexpr int FIN_CTAS_PER_SM = 8;               // 32 finish warps per SM
 
 // blocks per wave: bounds the scratch (8 bytes per input byte of the wave)
-uint32_t esd_wave(size_t n, uint32_t block_max) { return (uint32_t)min(n, (size_t)(block_max > 65536 ? 2048 : 4096)); }
+uint32_t esd_wave(size_t n, uint32_t block_max) { return (uint32_t)min(n, (size_t)(block_max > 65536 ? 4096 : 8192)); }
 
 } // namespace
 

@@ -37,7 +37,7 @@ def test_size_queries_and_status_map_without_gpu(pkg, oracle):
     ct = lib.cuda_zstd_batch_get_compress_temp_size(h, sizes.ctypes.data, 16384)
     dt = lib.cuda_zstd_batch_get_decompress_temp_size(h, sizes.ctypes.data, 16384)
     assert 0 < dt and 0 < ct                           # (a compress workspace always suffices for decompress: GPU tests)
-    assert ct < 4 << 30 and dt < 6 << 30               # the reference needs ~213 GB / 61 GB for this batch
+    assert ct < 8 << 30 and dt < 6 << 30               # the reference needs ~213 GB / 61 GB for this batch
     real = np.full(16384, 12157, dtype=np.uint64)      # libzstd L3 frames of the P=0.50 class
     assert lib.cuda_zstd_batch_get_decompress_temp_size(h, real.ctypes.data, 16384) < 2200 << 20
     assert lib.cuda_zstd_batch_get_compress_temp_size(h, sizes.ctypes.data, 0) == 0
