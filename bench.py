@@ -604,6 +604,8 @@ def main():
                          "algorithmic_bytes_per_launch": U + Cb, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": args.steps, "ms_per_step": e2e_ms, "d2h_link_gbs": link_gbs,
+                    "host_limit": f"the step moves {d2h_bytes / 1e9:.2f} GB device->host per rank; a plain pinned D2H copy of that buffer ran at "
+                                  f"{link_gbs:.1f} GB/s on rank 0 right after the timed region ({world} rank(s) on this box share its PCIe / host memory)",
                     "call": "cuda_zstd_batch_decompress_host: frames + tables H2D and output + sizes + statuses D2H from / to pinned host memory, "
                             "staged in 4 waves on the library's copy streams beside the decode kernels"},
             "gpu_launches": total_launches, "clocks": clocks,
