@@ -264,6 +264,8 @@ public:
   }
 
   int cached_dev = -1;
+  std::vector<unsigned char> dict_bytes;      // raw content of the dictionary set on this manager (kept, not referenced by the encoder)
+  u32 dict_id = 0;
   // the SM count and the decoder's residency belong to the CURRENT device: re-read when a call arrives on another one
   void refresh_device() {
     int dev = 0;
@@ -643,9 +645,30 @@ size_t ZstdBatchManager::get_decompress_temp_size(size_t n) const {
 size_t ZstdBatchManager::get_max_compressed_size(size_t n) const { return estimate_compressed_size(n, pimpl_->cfg.level); }
 size_t ZstdBatchManager::get_batch_compress_temp_size(const std::vector<size_t> &v) const { return pimpl_->enc_temp(v.size(), v.data()); }
 size_t ZstdBatchManager::get_batch_decompress_temp_size(const std::vector<size_t> &v) const { return pimpl_->dec_temp(v.size(), v.data()); }
-Status ZstdBatchManager::set_dictionary(const dictionary::Dictionary &) { return Status::ERROR_NOT_IMPLEMENTED; }
-Status ZstdBatchManager::get_dictionary(dictionary::Dictionary &) const { return Status::ERROR_NOT_IMPLEMENTED; }
-Status ZstdBatchManager::clear_dictionary() { return Status::SUCCESS; }
+// Dictionaries (reference: set_dictionary src/cuda_zstd_manager.cu:3712-3760).  At the sizes of this path the reference
+// compresses through its host route, plain ZSTD_compress without the dictionary (manager.cu:1604-1668), so a manager with a
+// dictionary set writes ordinary frames there: no Dictionary_ID, decodable with or without the dictionary.  Same here: the
+// dictionary is validated, kept (a copy of the raw content) and reported back by get_dictionary; the match stage does not
+// reference it.  Frames that DO carry a Dictionary_ID are refused by the decoder (ERROR_DICTIONARY_MISMATCH).
+Status ZstdBatchManager::set_dictionary(const dictionary::Dictionary &d) {
+  if (!d.raw_content || d.raw_size == 0) return fail(Status::ERROR_INVALID_PARAMETER, "set_dictionary", "empty dictionary");
+  if (d.raw_size > ((size_t)1 << 27)) return fail(Status::ERROR_INVALID_PARAMETER, "set_dictionary", "dictionary too large");
+  std::lock_guard<std::mutex> lock(pimpl_->mu);
+  cudaPointerAttributes at{};
+  pimpl_->dict_bytes.resize(d.raw_size);
+  const bool on_device = cudaPointerGetAttributes(&at, d.raw_content) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  if (!on_device) (void)cudaGetLastError();
+  if (on_device) { if (cudaMemcpy(pimpl_->dict_bytes.data(), d.raw_content, d.raw_size, cudaMemcpyDeviceToHost) != cudaSuccess) return Status::ERROR_CUDA_ERROR; }
+  else std::memcpy(pimpl_->dict_bytes.data(), d.raw_content, d.raw_size);
+  pimpl_->dict_id = d.dict_id;
+  return Status::SUCCESS;
+}
+Status ZstdBatchManager::get_dictionary(dictionary::Dictionary &d) const {
+  if (pimpl_->dict_bytes.empty()) return Status::ERROR_INVALID_PARAMETER;
+  d.raw_content = pimpl_->dict_bytes.data(); d.raw_size = pimpl_->dict_bytes.size(); d.dict_id = pimpl_->dict_id;
+  return Status::SUCCESS;
+}
+Status ZstdBatchManager::clear_dictionary() { pimpl_->dict_bytes.clear(); pimpl_->dict_id = 0; return Status::SUCCESS; }
 const CompressionStats &ZstdBatchManager::get_stats() const { return pimpl_->stats; }
 Status ZstdBatchManager::set_compression_level(int level) {
   if (level < 1 || level > 22) return Status::ERROR_INVALID_PARAMETER;      // level left unchanged (manager.cu:1517-1522)
@@ -774,7 +797,7 @@ Status ZstdBatchManager::compress(const void *src, size_t n, void *dst, size_t *
                                   size_t dict_size, cudaStream_t stream, void *) {
   if (!src || !dst || !dst_size || !ws) return fail(Status::ERROR_INVALID_PARAMETER, "compress", "null argument");   // manager.cu:1549-1552
   if (n == 0) return fail(Status::ERROR_INVALID_PARAMETER, "compress", "zero-size input");                            // manager.cu:1554-1558
-  if (dict || dict_size) return fail(Status::ERROR_NOT_IMPLEMENTED, "compress", "dictionaries are out of scope");
+  (void)dict; (void)dict_size;        // a per-call dictionary is accepted and not referenced (see set_dictionary)
   return single_buffer(*pimpl_, true, src, n, dst, dst_size, ws, ws_bytes, stream);
 }
 Status ZstdBatchManager::decompress(const void *src, size_t n, void *dst, size_t *dst_size, void *ws, size_t ws_bytes, cudaStream_t stream) {
@@ -1102,6 +1125,8 @@ using cuda_zstd::nvcomp_v5::status_to_nvcomp_error;
 using cuda_zstd::u32;
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+struct cuda_zstd_dict_t { std::vector<unsigned char> bytes; uint32_t id = 0; };
+
 // streams and events of the host-resident batch calls (cuda_zstd_batch_*_host*), created on first use
 struct HostPipe {
   static constexpr int MAX_WAVES = 4;
@@ -1217,9 +1242,41 @@ int cuda_zstd_decompress(cuda_zstd_manager_t *m, const void *src, size_t n, void
 }
 size_t cuda_zstd_get_compress_workspace_size(cuda_zstd_manager_t *m, size_t n) { return nvcomp_zstd_get_compress_temp_size_v5(m, n); }
 size_t cuda_zstd_get_decompress_workspace_size(cuda_zstd_manager_t *m, size_t n) { return nvcomp_zstd_get_decompress_temp_size_v5(m, n); }
-cuda_zstd_dict_t *cuda_zstd_train_dictionary(const void **, const size_t *, size_t, size_t) { return nullptr; }
-void cuda_zstd_destroy_dictionary(cuda_zstd_dict_t *) {}
-int cuda_zstd_set_dictionary(cuda_zstd_manager_t *, cuda_zstd_dict_t *) { return static_cast<int>(Status::ERROR_NOT_IMPLEMENTED); }
+// cuda_zstd_train_dictionary (src/cuda_zstd_c_api.cpp:128-177; the reference runs COVER): a RAW-CONTENT dictionary made of
+// the last dict_size bytes of the samples laid end to end (the format gives the END of a raw dictionary the cheapest
+// offsets), with an id derived from the content.  Host memory only.
+cuda_zstd_dict_t *cuda_zstd_train_dictionary(const void **samples, const size_t *sizes, size_t n, size_t dict_size) {
+  if (!samples || !sizes || n == 0 || dict_size == 0) return nullptr;
+  try {
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) { if (!samples[i] && sizes[i]) return nullptr; total += sizes[i]; }
+    if (total == 0) return nullptr;
+    auto *d = new cuda_zstd_dict_t;
+    const size_t keep = std::min(total, dict_size);
+    d->bytes.resize(keep);
+    size_t skip = total - keep, w = 0;
+    for (size_t i = 0; i < n; i++) {
+      const unsigned char *p = static_cast<const unsigned char *>(samples[i]);
+      size_t len = sizes[i];
+      if (skip >= len) { skip -= len; continue; }
+      std::memcpy(d->bytes.data() + w, p + skip, len - skip);
+      w += len - skip; skip = 0;
+    }
+    uint32_t h = 2166136261u;                                  // FNV-1a of the content: ids below 32768 are reserved by the format
+    for (unsigned char c : d->bytes) h = (h ^ c) * 16777619u;
+    d->id = h | 0x8000u;
+    return d;
+  } catch (...) { return nullptr; }
+}
+void cuda_zstd_destroy_dictionary(cuda_zstd_dict_t *d) { delete d; }
+int cuda_zstd_set_dictionary(cuda_zstd_manager_t *m, cuda_zstd_dict_t *d) {
+  if (!m || !d) return static_cast<int>(Status::ERROR_INVALID_PARAMETER);
+  try {
+    cuda_zstd::dictionary::Dictionary x;
+    x.raw_content = d->bytes.data(); x.raw_size = d->bytes.size(); x.dict_id = d->id;
+    return static_cast<int>(reinterpret_cast<cuda_zstd::ZstdManager *>(m)->set_dictionary(x));
+  } catch (...) { return 1; }
+}
 const char *cuda_zstd_get_error_string(int code) { return cuda_zstd::status_to_string(static_cast<Status>(code)); }
 int cuda_zstd_is_error(int code) { return code != 0; }
 

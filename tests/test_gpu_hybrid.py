@@ -95,3 +95,42 @@ def test_errors_and_routing(hybrid, pkg, oracle):
         rc, cs, res = h.compress(data, 4096, comp, comp.size, HOST, HOST)
         assert rc == 0 and res.backend_used == GPU_KERNELS
         h.close()
+
+
+@pytest.mark.gpu
+def test_dictionary_calls_behave_like_the_reference_at_batch_sizes(oracle, libzstd, pkg):
+    """cuda_zstd_train_dictionary / set_dictionary (src/cuda_zstd_c_api.cpp:128-195): the dictionary is accepted and kept;
+    like the reference's host route at these sizes (src/cuda_zstd_manager.cu:1604-1668: plain ZSTD_compress) the frames
+    carry no Dictionary_ID and decode anywhere -- with stock libzstd, without the dictionary."""
+    import ctypes as C
+    import torch
+    lib = pkg.load_library()
+    lib.cuda_zstd_train_dictionary.restype = C.c_void_p
+    lib.cuda_zstd_train_dictionary.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.cuda_zstd_destroy_dictionary.argtypes = [C.c_void_p]
+    lib.cuda_zstd_set_dictionary.restype = C.c_int
+    lib.cuda_zstd_set_dictionary.argtypes = [C.c_void_p, C.c_void_p]
+    s1, s2 = oracle.gen_batch(16384, 1, 0, 30000), oracle.gen_batch(16384, 1, 0, 30000, first_idx=9)
+    ptrs = (C.c_void_p * 2)(s1.ctypes.data, s2.ctypes.data)
+    sizes = (C.c_size_t * 2)(s1.size, s2.size)
+    assert not lib.cuda_zstd_train_dictionary(None, None, 0, 1024)
+    d = lib.cuda_zstd_train_dictionary(ptrs, sizes, 2, 20000)
+    assert d
+    s = pkg.ZstdSingle(3)
+    assert lib.cuda_zstd_set_dictionary(s.h, d) == 0
+    assert lib.cuda_zstd_set_dictionary(s.h, None) != 0
+    n = 65536
+    x = oracle.gen_batch(n, 1, 0, 30000, first_idx=4)
+    xd = torch.from_numpy(x).cuda()
+    comp = torch.zeros(n * 2, dtype=torch.uint8, device="cuda")
+    w = torch.empty(s.compress_workspace(n), dtype=torch.uint8, device="cuda")
+    rc, csz = s.compress(xd, n, comp, comp.numel(), w, w.numel())
+    assert rc == 0 and 0 < csz < n
+    frame = comp.cpu().numpy()[:csz]
+    assert frame[4] & 3 == 0                                           # no Dictionary_ID field
+    assert np.array_equal(libzstd.decompress(frame, n), x)
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    rc, dsz = s.decompress(comp, csz, back, n, w, w.numel())
+    assert rc == 0 and dsz == n and torch.equal(back, xd)
+    s.close()
+    lib.cuda_zstd_destroy_dictionary(d)
