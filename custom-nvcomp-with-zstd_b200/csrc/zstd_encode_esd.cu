@@ -615,7 +615,7 @@ __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool 
   return cnt;
 }
 
-__global__ void __launch_bounds__(32 * SEL_WARPS) zstd_lz_select_kernel(SelArgs S) {
+__global__ void __launch_bounds__(32 * SEL_WARPS, 8) zstd_lz_select_kernel(SelArgs S) {
   const int lane = threadIdx.x & 31;
   const uint32_t idx = blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
   if (idx >= S.wave_n) return;
