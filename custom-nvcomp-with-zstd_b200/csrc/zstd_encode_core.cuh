@@ -467,8 +467,12 @@ ZHD void write_lit_header_compressed(uint8_t *dst, uint32_t hs, bool single, uin
 // Decides the coding mode of one sequence alphabet and prepares its compression table.
 // mode: 0 predefined, 1 RLE, 2 FSE-compressed.  Writes the table description (RLE byte or NCount) to
 // dst and returns its size through *desc_bytes.  count[] holds the histogram of `nseq` codes.
+// build_max_sym == nullptr: the compression table is built here (serial).  Otherwise the normalised counts to build from
+// are left in W.norm, *build_max_sym receives the last symbol (-1: nothing to build, RLE) and the caller builds the table
+// (the kernels do that with the whole warp: fse_build_ctable_warp).
 ZHDN int seq_table_prepare(EntropyWs &W, int kind, const uint32_t *count, int max_code_present, uint32_t nseq, uint8_t *dst,
-                           uint32_t cap, uint32_t *desc_bytes) {
+                           uint32_t cap, uint32_t *desc_bytes, int *build_max_sym = nullptr) {
+  if (build_max_sym) *build_max_sym = -1;
   *desc_bytes = 0;
   const int max_log = (kind == 1) ? 8 : 9;
   int16_t dnorm[64];
@@ -513,13 +517,15 @@ ZHDN int seq_table_prepare(EntropyWs &W, int kind, const uint32_t *count, int ma
     }
   }
   if (cmp_ok && (!def_ok || cmp_cost < def_cost)) {
-    fse_build_ctable(W.norm, max_code_present, log, W.state_tab(kind), W.tt[kind], W.cell, W.cumul);
+    if (build_max_sym) *build_max_sym = max_code_present;
+    else fse_build_ctable(W.norm, max_code_present, log, W.state_tab(kind), W.tt[kind], W.cell, W.cumul);
     W.tab_log[kind] = log;
     *desc_bytes = hdr;
     return 2;
   }
   if (!def_ok) return -1;
-  fse_build_ctable(dnorm, dmax, dlog, W.state_tab(kind), W.tt[kind], W.cell, W.cumul);
+  if (build_max_sym) { for (int s = 0; s <= dmax; s++) W.norm[s] = dnorm[s]; *build_max_sym = dmax; }
+  else fse_build_ctable(dnorm, dmax, dlog, W.state_tab(kind), W.tt[kind], W.cell, W.cumul);
   W.tab_log[kind] = dlog;
   return 0;
 }

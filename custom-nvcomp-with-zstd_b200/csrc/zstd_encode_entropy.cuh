@@ -28,6 +28,81 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 }
 constexpr uint32_t SEQ_VAL_MASK = (1u << 18) - 1;     // value | state bits << 18 | nb << 27
 
+// enc::fse_build_ctable with the whole warp; produces the same tables.  norm[0 .. max_sym] (-1 = low-probability symbol,
+// one cell at the top of the table), 2^log cells.  cumul and cell are scratch (as in the serial form).
+static __device__ void fse_build_ctable_warp(const int16_t *norm, int max_sym, int log, uint16_t *state_tab, SymTT *tt, uint8_t *cell, uint16_t *cumul,
+                                             uint16_t *spread_first /* max_sym + 2 entries of scratch */, int lane) {
+  const uint32_t size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+  const uint32_t lt = lanemask_lt();
+  // per symbol (two per lane): cells it owns, cells below it in the spread, low-probability symbols below it
+  uint32_t run_all = 0, run_spread = 0, run_low = 0;
+  uint32_t my_all[2], my_spread[2], my_low[2];
+  int my_c[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int s = lane + 32 * r;
+    const int c = s <= max_sym ? (int)norm[s] : 0;
+    my_c[r] = c;
+    const uint32_t all = c == -1 ? 1u : (uint32_t)max(c, 0), spread = (uint32_t)max(c, 0), low = c == -1 ? 1u : 0u;
+    uint32_t ia = all, is = spread, il = low;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), ts = __shfl_up_sync(0xffffffffu, is, o), tl = __shfl_up_sync(0xffffffffu, il, o);
+      if (lane >= o) { ia += ta; is += ts; il += tl; }
+    }
+    my_all[r] = run_all + ia - all; my_spread[r] = run_spread + is - spread; my_low[r] = run_low + il - low;
+    run_all += __shfl_sync(0xffffffffu, ia, 31); run_spread += __shfl_sync(0xffffffffu, is, 31); run_low += __shfl_sync(0xffffffffu, il, 31);
+  }
+  const uint32_t nlow = run_low, high = size - 1 - nlow;
+  // cumul[] = first slot of every symbol in the state table, spread_first[] = its first occurrence in the spread (a binary
+  // search over it finds the owner of an occurrence); the per-symbol transform; the low-probability cells
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int s = lane + 32 * r;
+    if (s > max_sym) continue;
+    const int c = my_c[r];
+    cumul[s] = (uint16_t)my_all[r];
+    spread_first[s] = (uint16_t)my_spread[r];
+    if (c == -1) cell[size - 1 - my_low[r]] = (uint8_t)s;
+    SymTT e;
+    if (c == 0) { e.delta_nb = ((log + 1) << 16) - (1 << log); e.delta_state = 0; }
+    else if (c == -1 || c == 1) { e.delta_nb = (log << 16) - (1 << log); e.delta_state = (int32_t)my_all[r] - 1; }
+    else {
+      const int max_bits_out = log - hb32((uint32_t)(c - 1));
+      e.delta_nb = (max_bits_out << 16) - (c << max_bits_out);
+      e.delta_state = (int32_t)my_all[r] - c;
+    }
+    tt[s] = e;
+  }
+  if (lane == 0) spread_first[max_sym + 1] = (uint16_t)run_spread;
+  __syncwarp();
+  // spread: the i-th position of the walk 0, step, 2 step, ... (mod size) that is not above `high` takes occurrence i
+  uint32_t seen = 0;
+  for (uint32_t k0 = 0; k0 < size; k0 += 32) {
+    const uint32_t pos = ((k0 + (uint32_t)lane) * step) & mask;
+    const bool valid = pos <= high;
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const uint32_t i = seen + (uint32_t)__popc(vm & lt);
+      int lo = 0, hi = max_sym;                                     // last symbol whose first occurrence is <= i and that owns cells
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (spread_first[mid] <= i) lo = mid; else hi = mid - 1; }
+      cell[pos] = (uint8_t)lo;
+    }
+    seen += (uint32_t)__popc(vm);
+  }
+  __syncwarp();
+  // state table: the cells of a symbol, in cell order, take consecutive slots from cumul[symbol]
+  for (uint32_t u0 = 0; u0 < size; u0 += 32) {
+    const uint32_t u = u0 + (uint32_t)lane;
+    const uint32_t s = cell[u];
+    const uint32_t same = __match_any_sync(0xffffffffu, s);
+    const uint32_t base = cumul[s];
+    __syncwarp();
+    state_tab[base + (uint32_t)__popc(same & lt)] = (uint16_t)(size + u);
+    if ((same & lt) == 0) cumul[s] = (uint16_t)(base + (uint32_t)__popc(same));
+    __syncwarp();
+  }
+}
+
 static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits, uint32_t nlit, uint32_t *sll, uint32_t *sml, uint32_t *sofv,
                                        uint32_t nseq, uint8_t *dst, uint32_t cap, int lane) {
   uint32_t op = 0;
@@ -204,11 +279,16 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
     const int maxc = (int)(kind == 0 ? mx0 : kind == 1 ? mx1 : mx2);
     int mode = 0;
     uint32_t desc = 0;
-    if (lane == 0) mode = seq_table_prepare(W, kind, W.count + 64 * kind, maxc, nseq, dst + op, cap - op, &desc);
+    int build_max = -1;
+    if (lane == 0) mode = seq_table_prepare(W, kind, W.count + 64 * kind, maxc, nseq, dst + op, cap - op, &desc, &build_max);
     mode = __shfl_sync(0xffffffffu, mode, 0);
     desc = __shfl_sync(0xffffffffu, desc, 0);
+    build_max = __shfl_sync(0xffffffffu, build_max, 0);
     __syncwarp();
     if (mode < 0) return 0;
+    if (build_max >= 0) fse_build_ctable_warp(W.norm, build_max, W.tab_log[kind], W.state_tab(kind), W.tt[kind], W.cell, W.cumul,
+                                              reinterpret_cast<uint16_t *>(W.count + 192), lane);      // W.count[192..255] is free
+    __syncwarp();
     op += desc;
     modes |= (uint32_t)mode << (6 - 2 * kind);
   }
