@@ -490,7 +490,7 @@ struct Walker {
   uint32_t n, lim;
   int lazy;
 };
-enum : uint32_t { W_DECIDE = 0, W_SKIP = 1, W_MATCH = 2, W_DONE = 3 };
+enum : uint32_t { W_DECIDE = 0, W_SKIP = 1, W_MATCH = 2, W_DONE = 3, W_RECODE = 4 };
 
 template <bool REWALK>
 __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool active, Seq *out, const Seq *spec, uint32_t spec_cnt, const State &spec0,
@@ -603,8 +603,27 @@ __device__ __forceinline__ uint32_t walk_lanes(const Walker &K, State &st, bool 
             k++;
             if (ee == st.anchor) break;
           }
-          if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && sp.r2 == st.r2 && k > 0) { synced = true; mode = W_DONE; }
+          // Same position and the same two youngest history entries: every decision from here on is the speculative
+          // walk's (decisions never read the third entry).  With the third entry equal too the lists are identical;
+          // otherwise only offset codes that involve it can differ, and the lane goes on copying the speculative
+          // sequences, re-coded on the true history, until a new offset pushes the differing entry out.
+          if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && k > 0) {
+            if (sp.r2 == st.r2) { synced = true; mode = W_DONE; }
+            else mode = W_RECODE;
+          }
         }
+      }
+    } else if (REWALK && mode == W_RECODE) {
+      if (k == spec_cnt) { st.ip = spec_exit.ip; st.anchor = spec_exit.anchor; mode = W_DONE; }
+      else {
+        const Seq e = spec[k];
+        const uint32_t es = seq_start(e), el = seq_len(e);
+        const bool ll0 = es == st.anchor;
+        const uint32_t o = decode_offset(seq_code(e), ll0, sp.r0, sp.r1, sp.r2);
+        out[cnt++] = pack_seq(es, el, code_offset(o, ll0, st.r0, st.r1, st.r2));
+        st.ip = st.anchor = sp.anchor = es + el;
+        k++;
+        if (sp.r2 == st.r2) { synced = true; mode = W_DONE; }
       }
     }
   }
@@ -649,9 +668,45 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 8) zstd_lz_select_kernel(SelAr
     const State entry = shfl_up_state(exit_state);
     const bool need = lane > 0 && !entry.same(entry_used);
     if (!__any_sync(0xffffffffu, need)) break;
+    // An entry that differs from the last one only in the third history entry leads to the same decisions: the lane's
+    // lists are re-coded (prefix in place, then the kept speculative sequences are copied behind it) until the two
+    // histories meet, without reading the input again.
+    const bool recode = need && entry.ip == entry_used.ip && entry.anchor == entry_used.anchor && entry.r0 == entry_used.r0 && entry.r1 == entry_used.r1;
+    if (recode) {
+      uint32_t o0 = entry_used.r0, o1 = entry_used.r1, o2 = entry_used.r2, n0 = entry.r0, n1 = entry.r1, n2 = entry.r2;
+      uint32_t anchor = entry.anchor;
+      bool met = false;
+      for (uint32_t i = 0; i < pre_cnt && !met; i++) {
+        const Seq e = prefix[i];
+        const uint32_t es = seq_start(e), el = seq_len(e);
+        const bool ll0 = es == anchor;
+        const uint32_t o = decode_offset(seq_code(e), ll0, o0, o1, o2);
+        const uint32_t code = code_offset(o, ll0, n0, n1, n2);
+        if (code != seq_code(e)) prefix[i] = pack_seq(es, el, code);
+        anchor = es + el;
+        met = o2 == n2;
+      }
+      if (!met) {
+        uint32_t k = sync_k;
+        while (k < spec_cnt && !met) {
+          const Seq e = spec[k];
+          const uint32_t es = seq_start(e), el = seq_len(e);
+          const bool ll0 = es == anchor;
+          const uint32_t o = decode_offset(seq_code(e), ll0, o0, o1, o2);
+          prefix[pre_cnt++] = pack_seq(es, el, code_offset(o, ll0, n0, n1, n2));
+          anchor = es + el;
+          k++;
+          met = o2 == n2;
+        }
+        sync_k = k;
+        if (!met) { exit_state.r0 = n0; exit_state.r1 = n1; exit_state.r2 = n2; }
+      }
+      entry_used = entry;
+    }
+    const bool walk = need && !recode;
     State s2 = entry;
-    const uint32_t c = walk_lanes<true>(K, s2, need, prefix, spec, spec_cnt, spec0, spec_exit, &sync_k);
-    if (need) { entry_used = entry; pre_cnt = c; exit_state = s2; }
+    const uint32_t c = walk_lanes<true>(K, s2, walk, prefix, spec, spec_cnt, spec0, spec_exit, &sync_k);
+    if (walk) { entry_used = entry; pre_cnt = c; exit_state = s2; }
   }
   LaneHdr h;
   h.spec_cnt = (uint16_t)spec_cnt; h.sync_k = (uint16_t)sync_k; h.pre_cnt = (uint16_t)pre_cnt; h.pad = 0;

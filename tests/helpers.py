@@ -39,4 +39,9 @@ def edge_inputs(orc, sizes=(1, 2, 3, 7, 8, 9, 31, 32, 33, 63, 64, 65, 255, 256, 
         out[f"zero{n}"] = np.zeros(n, np.uint8)
         out[f"two{n}"] = rng.integers(0, 2, n, dtype=np.uint8)
         out[f"per7_{n}"] = (np.arange(n) % 7).astype(np.uint8)
+        if n in (5000, 65536, 131072):
+            # the pattern of the reference's single-buffer benchmarks (benchmarks/benchmark_nvcomp_interface.cu:40-42):
+            # two offsets alternate for the whole buffer, so the third repeat-offset entry never leaves the history
+            i = np.arange(n, dtype=np.int64)
+            out[f"drift{n}"] = ((i * 17 + i // 256) % 256).astype(np.uint8)
     return out
