@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(32 * SEL_WARPS, 8) zstd_lz_select_kernel(SelAr
     if (!__any_sync(0xffffffffu, need)) break;
     // An entry that differs from the last one only in the third history entry leads to the same decisions: the lane's
     // lists are re-coded (prefix in place, then the kept speculative sequences are copied behind it) until the two
-    // histories meet, without reading the input again.
+    // histories meet, without reading the input again (select_recode of zstd_encode_lz.cuh, written out: the call costs this kernel 3 ms per 16,384 chunks).
     const bool recode = need && entry.ip == entry_used.ip && entry.anchor == entry_used.anchor && entry.r0 == entry_used.r0 && entry.r1 == entry_used.r1;
     if (recode) {
       uint32_t o0 = entry_used.r0, o1 = entry_used.r1, o2 = entry_used.r2, n0 = entry.r0, n1 = entry.r1, n2 = entry.r2;
@@ -742,7 +742,10 @@ __global__ void __launch_bounds__(32 * SELQ_WARPS) zstd_lz_select_rows_kernel(Se
     const State entry = shfl_up_state(exit_state);
     const bool need = lane > 0 && !entry.same(entry_used);
     if (!__any_sync(0xffffffffu, need)) break;
-    if (need) {
+    if (need && entry_differs_in_r2_only(entry, entry_used)) {
+      select_recode(prefix, pre_cnt, spec, spec_cnt, sync_k, entry_used, entry, exit_state);
+      entry_used = entry;
+    } else if (need) {
       entry_used = entry;
       State s2 = entry;
       pre_cnt = select_rewalk(in, bn, R, E, SP, s2, spec, spec_cnt, spec0, spec_exit, prefix, &sync_k);

@@ -205,7 +205,7 @@ ZHD uint32_t seq_start(const Seq &q) { return q.x & LZ_OFF_MASK; }
 ZHD uint32_t seq_len(const Seq &q) { return (q.x >> 17) | ((q.y >> 18) << 15); }
 ZHD uint32_t seq_code(const Seq &q) { return q.y & ((1u << 18) - 1); }
 
-struct SelectParams { int lazy; int rows; };
+struct SelectParams { int lazy; int rows; int exact_stitch = 0; };       // exact_stitch: tests only (see select_rewalk)
 
 // One decision of the walk at st.ip (< lim).  Either emits one sequence (returns true, *out filled) or skips literals.
 // n: block bytes; lim: first position this lane does not decide.
@@ -305,6 +305,11 @@ ZHD uint32_t select_walk(const uint8_t *in, uint32_t n, const uint32_t *R, uint3
 //   *sync_k   index of the first speculative sequence that is kept (spec_cnt: none)
 //   st        the lane's true exit state
 // returns the number of prefix sequences.
+// The two walks have met when they stand at the same position with the same two youngest history entries: no decision
+// reads the third one (select_step), so from there on the true walk takes the speculative walk's sequences.  While the
+// third entries differ an offset code that involves it can differ, so the speculative sequences are copied to prefix,
+// re-coded on the true history, until a new offset has pushed the differing entry out; the rest is kept as it is.
+// (P.exact_stitch: keep walking until all three entries agree -- the plain rule, used by the tests as a cross-check.)
 ZHD uint32_t select_rewalk(const uint8_t *in, uint32_t n, const uint32_t *R, uint32_t lim, const SelectParams &P, State &st, const Seq *spec,
                            uint32_t spec_cnt, const State &spec0, const State &spec_exit, Seq *prefix, uint32_t *sync_k) {
   uint32_t cnt = 0, k = 0;
@@ -323,15 +328,59 @@ ZHD uint32_t select_rewalk(const uint8_t *in, uint32_t n, const uint32_t *R, uin
       k++;
       if (ee == st.anchor) break;
     }
-    if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && sp.r2 == st.r2 && k > 0) {
-      // same position, same history: the rest of the speculative walk is the rest of the true walk
+    if (sp.anchor == st.anchor && sp.r0 == st.r0 && sp.r1 == st.r1 && k > 0 && (sp.r2 == st.r2 || !P.exact_stitch)) {
+      while (sp.r2 != st.r2 && k < spec_cnt) {
+        const Seq e = spec[k];
+        const uint32_t es = seq_start(e), el = seq_len(e);
+        const bool ll0 = es == st.anchor;
+        const uint32_t o = decode_offset(seq_code(e), ll0, sp.r0, sp.r1, sp.r2);
+        prefix[cnt++] = pack_seq(es, el, code_offset(o, ll0, st.r0, st.r1, st.r2));
+        st.anchor = sp.anchor = es + el;
+        k++;
+      }
       *sync_k = k;
-      st = spec_exit;
+      if (sp.r2 == st.r2) st = spec_exit;
+      else { st.ip = spec_exit.ip; st.anchor = spec_exit.anchor; }      // the list ended first: the true history stays
       return cnt;
     }
   }
   *sync_k = spec_cnt;
   return cnt;
+}
+
+// The lane's entry changed in the third history entry only (`from` -> `to`): same decisions as its last walk, so its
+// lists are re-coded -- prefix in place, then kept speculative sequences are copied behind it -- until the two
+// histories meet, without reading the input.  exit_state keeps its position and takes the new history if they never meet.
+ZHD bool entry_differs_in_r2_only(const State &a, const State &b) {
+  return a.ip == b.ip && a.anchor == b.anchor && a.r0 == b.r0 && a.r1 == b.r1 && a.r2 != b.r2;
+}
+ZHD void select_recode(Seq *prefix, uint32_t &pre_cnt, const Seq *spec, uint32_t spec_cnt, uint32_t &sync_k, const State &from, const State &to,
+                       State &exit_state) {
+  uint32_t o0 = from.r0, o1 = from.r1, o2 = from.r2, n0 = to.r0, n1 = to.r1, n2 = to.r2;
+  uint32_t anchor = to.anchor;
+  for (uint32_t i = 0; i < pre_cnt; i++) {
+    const Seq e = prefix[i];
+    const uint32_t es = seq_start(e), el = seq_len(e);
+    const bool ll0 = es == anchor;
+    const uint32_t o = decode_offset(seq_code(e), ll0, o0, o1, o2);
+    const uint32_t code = code_offset(o, ll0, n0, n1, n2);
+    if (code != seq_code(e)) prefix[i] = pack_seq(es, el, code);
+    anchor = es + el;
+    if (o2 == n2) return;
+  }
+  uint32_t k = sync_k;
+  while (k < spec_cnt) {
+    const Seq e = spec[k];
+    const uint32_t es = seq_start(e), el = seq_len(e);
+    const bool ll0 = es == anchor;
+    const uint32_t o = decode_offset(seq_code(e), ll0, o0, o1, o2);
+    prefix[pre_cnt++] = pack_seq(es, el, code_offset(o, ll0, n0, n1, n2));
+    anchor = es + el;
+    k++;
+    if (o2 == n2) { sync_k = k; return; }
+  }
+  sync_k = k;
+  exit_state.r0 = n0; exit_state.r1 = n1; exit_state.r2 = n2;
 }
 
 // sub-segment geometry: lane j decides positions [lane_begin(j), lane_begin(j + 1)) of [0, ilimit)

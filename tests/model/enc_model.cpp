@@ -275,6 +275,7 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
     }
   }
   SelectParams SP{EP.lazy, EP.rows};
+  if (const char *e = getenv("ENC_MODEL_EXACT_STITCH")) SP.exact_stitch = atoi(e);      // cross-check of the stitching rule (tests/test_model.py)
   const uint32_t span = lane_span(ilimit), cap = lane_list_cap(BLOCK_BYTES);
   std::vector<Seq> spec((size_t)LZ_LANES * cap), prefix((size_t)LZ_LANES * cap);
   State spec0[LZ_LANES], spec_exit[LZ_LANES], exit_[LZ_LANES], entry_used[LZ_LANES];
@@ -294,6 +295,13 @@ void parse_block_lz(const uint8_t *b, uint32_t bn, const EsdParams &EP_, bool kn
     for (uint32_t j = 1; j < LZ_LANES; j++) entry[j] = exit_[j - 1];          // (a shuffle on the GPU: all lanes see the same round)
     for (uint32_t j = 1; j < LZ_LANES; j++) {
       if (entry[j].same(entry_used[j])) continue;
+      if (!SP.exact_stitch && entry_differs_in_r2_only(entry[j], entry_used[j])) {
+        State ex = exit_[j];
+        select_recode(&prefix[(size_t)j * cap], pre_cnt[j], &spec[(size_t)j * cap], spec_cnt[j], sync_k[j], entry_used[j], entry[j], ex);
+        entry_used[j] = entry[j];
+        if (!ex.same(exit_[j])) { exit_[j] = ex; changed = true; }
+        continue;
+      }
       entry_used[j] = entry[j];
       const uint32_t E = lane_begin(j + 1, span, ilimit);
       State st = entry[j];

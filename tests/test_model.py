@@ -47,3 +47,24 @@ def test_model_uses_huffman_fse_and_repcodes(oracle, model):
     t = oracle.gen_textlike(65536)
     f = model.compress(t, 3)
     assert f.size < 3600                                          # libzstd -3 needs 3288 on this chunk
+
+
+@pytest.mark.parametrize("level", [1, 3, 5, 9])
+def test_model_stitching_shortcut_equals_plain_rule(oracle, model, level, monkeypatch):
+    """The lanes' walks are joined where position and the two youngest repeat offsets agree, the sequences up to
+    the point where the third one agrees too being re-coded (zstd_encode_lz.cuh: select_rewalk / select_recode).
+    The plain rule -- keep walking until all three agree -- must give the same frame, byte for byte."""
+    inputs = {k: v for k, v in edge_inputs(oracle).items() if v.size >= 4096}
+    for name, kind, P in CLASSES:
+        inputs[name] = oracle.gen_batch(65536, 1, kind, P)
+    rng = np.random.default_rng(11)
+    # a few offsets in rotation: repeat codes of all three history entries, long stretches without a new offset
+    base = rng.integers(0, 256, 700, dtype=np.uint8)
+    rot = np.concatenate([np.roll(base, int(s))[: int(l)] for s, l in zip(rng.integers(0, 3, 400) * 231, rng.integers(20, 400, 400))])
+    inputs["rotating"] = rot[:131072].copy()
+    for name, d in inputs.items():
+        monkeypatch.delenv("ENC_MODEL_EXACT_STITCH", raising=False)
+        fast = model.compress(d, level)
+        monkeypatch.setenv("ENC_MODEL_EXACT_STITCH", "1")
+        plain = model.compress(d, level)
+        assert np.array_equal(fast, plain), (name, level)
