@@ -577,6 +577,7 @@ public:
         f.slow_list = reinterpret_cast<u32 *>(slow_list);
         f.slow_count = counter + 16;
         f.group_counters = counter + 48;
+        f.lit_buckets = counter + 60;               // 65 words, inside the 512-byte header
         f.sm_count = sm_count;
         f.general_grid = dec_grid(m);
         f.bare_blocks = bare_mode ? 1u : 0u;

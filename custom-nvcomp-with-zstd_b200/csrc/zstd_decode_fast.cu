@@ -32,6 +32,9 @@
 
 namespace b200zstd {
 
+// KA takes the Huffman chunks in descending order of literal count (buckets of 2 KB, counting sort: KP ranks, the order kernel
+// places), so that the streams a group decodes side by side are of one length and the long ones start first.
+constexpr uint32_t KA_BUCKETS = 64, KA_BUCKET_SHIFT = 11;
 struct __align__(16) FastDesc {
   uint32_t state;        // 0 fast path continues, 1 finished in prep, 2 routed to the general kernel
   uint32_t status;
@@ -55,6 +58,7 @@ struct __align__(16) FastDesc {
   uint32_t seq_status, out_end, lit_end;      // written by the sequence thread
   uint32_t lit_status[4];                     // written by the Huffman threads
   uint32_t lit_slot, seq_slot;                // pool offsets in 16-byte units
+  uint32_t ka_key;                            // Huffman chunks: literal-count bucket << 16 | rank inside the bucket (KA's work order)
 };
 // The tail of the descriptor area holds KC's per-chunk hand-over words: [0] parts of the chunk executed so far, [1] the status
 // the finished parts arrived at (zeroed by KP; see zstd_fast_exec_kernel).
@@ -299,6 +303,10 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
       const unsigned long long lo = atomicAdd(&F.pool_heads[0], lit_need + seq_need);
       if (lo + lit_need + seq_need > F.lit_pool_bytes) route = true;
       D.lit_slot = (uint32_t)(lo >> 4); D.seq_slot = (uint32_t)((lo + lit_need) >> 4);
+      if (!route && D.lit_type == 2) {
+        const uint32_t b = min(D.lit_size >> KA_BUCKET_SHIFT, KA_BUCKETS - 1u);
+        D.ka_key = (b << 16) | atomicAdd(F.lit_buckets + b, 1u);
+      }
     }
     route = __shfl_sync(0xffffffffu, route ? 1 : 0, 0) != 0;
     if (lane == 0) {
@@ -328,9 +336,10 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
 // KA: literals -- 28 chunks' Huffman tables pulled into shared memory by bulk async copies (two CTAs per SM), then one
 // thread per Huffman stream
 // =================================================================================================
-constexpr int KA_THREADS = 128;
-constexpr int KA_GROUP = 28;                                   // chunks per CTA pass: 28 x 4 KB of tables, two CTAs per SM
-constexpr size_t KA_SMEM = (size_t)KA_GROUP * 4096;
+constexpr int KA_GROUP = 24;                                   // chunks per CTA pass: 24 x (4 KB table + 4 stream rings), two CTAs per SM
+constexpr int KA_THREADS = 4 * KA_GROUP;
+constexpr int KA_RING_WORDS = 32;                              // per stream: the 128 bytes of bitstream around its read position
+constexpr size_t KA_SMEM = (size_t)KA_GROUP * 4096 + (size_t)KA_THREADS * KA_RING_WORDS * 4;
 
 __device__ __forceinline__ uint32_t top_bits(uint32_t hi, int skip, int n) { return ((hi << skip) >> 1) >> (31 - n); }   // n in [0,31]
 __device__ __forceinline__ uint32_t peek32(const uint32_t *W, int t) {             // bits [t-32, t) of the stream, t may be anything
@@ -339,7 +348,7 @@ __device__ __forceinline__ uint32_t peek32(const uint32_t *W, int t) {          
 }
 
 __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
-                                                    uint32_t k, uint32_t *status_out, uint32_t lead);
+                                                    uint32_t k, uint32_t *status_out, uint32_t lead, uint32_t *ring);
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
@@ -361,6 +370,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!done);
 }
 
+// counting sort, second half: bucket sizes -> start positions (largest bucket first); every Huffman chunk writes its index
+// to its place.  The order occupies the END of the slow-list array, last entry first (a chunk is in one list or the other).
+__global__ void __launch_bounds__(256) zstd_fast_order_kernel(FastDecodeArgs F) {
+  __shared__ uint32_t start[KA_BUCKETS];
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t hi = F.lit_buckets[KA_BUCKETS - 1 - lane], lo = F.lit_buckets[KA_BUCKETS - 33 - lane];     // descending bucket order
+    uint32_t a = hi, b = lo;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, a, d), y = __shfl_up_sync(0xffffffffu, b, d);
+      if (lane >= (uint32_t)d) { a += x; b += y; }
+    }
+    const uint32_t first_half = __shfl_sync(0xffffffffu, a, 31);
+    start[KA_BUCKETS - 1 - lane] = a - hi;
+    start[KA_BUCKETS - 33 - lane] = first_half + b - lo;
+    if (blockIdx.x == 0 && lane == 31) F.lit_buckets[KA_BUCKETS] = first_half + b;
+  }
+  __syncthreads();
+  const uint32_t chunk = blockIdx.x * 256 + threadIdx.x;
+  if (chunk >= F.base.n) return;
+  const FastDesc *const D = slot_of(F, chunk).desc();
+  if (D->state != 0 || D->lit_type != 2) return;
+  const uint32_t key = D->ka_key;
+  F.slow_list[F.base.n - 1 - (start[key >> 16] + (key & 0xFFFFu))] = chunk;
+}
+
 __global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArgs F) {
   extern __shared__ __align__(128) uint8_t ka_smem[];
   __shared__ uint32_t s_group;
@@ -372,14 +407,16 @@ __global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArg
   for (;;) {
     if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 0, 1u);
     __syncthreads();                                            // also: every thread is done with the previous group's tables
-    const uint32_t g0 = s_group * KA_GROUP;
-    if (g0 >= A.n) break;
-    const uint32_t c = threadIdx.x >> 2, k = threadIdx.x & 3, chunk = g0 + c;
+    const uint32_t g0 = s_group * KA_GROUP, n_huf = F.lit_buckets[KA_BUCKETS];
+    if (g0 >= n_huf) break;
+    const uint32_t c = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const bool have = g0 + c < n_huf;
+    const uint32_t chunk = F.slow_list[A.n - 1 - (have ? g0 + c : g0)];
     bool work = false;
-    ChunkSlot slot = slot_of(F, chunk < A.n ? chunk : g0);
+    ChunkSlot slot = slot_of(F, chunk);
     FastDesc *const D = slot.desc();
     if (c < KA_GROUP) {
-      const bool live = chunk < A.n && D->state == 0 && D->lit_type == 2;
+      const bool live = have && D->state == 0 && D->lit_type == 2;
       work = live && k < D->n_streams;
       if (k == 0) {                                             // the chunk's first thread pulls its table
         if (live) {
@@ -392,7 +429,9 @@ __global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArg
     }
     mbar_wait(&s_bar, phase);
     phase ^= 1;
-    if (work) fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, k, &D->lit_status[k], F.bare_blocks ? 6u : 0u);
+    if (work)
+      fast_decode_huffman((const uint8_t *)A.in_ptrs[chunk], D, slot.lits(), tables + (size_t)c * 2048, k, &D->lit_status[k], F.bare_blocks ? 6u : 0u,
+                          reinterpret_cast<uint32_t *>(ka_smem + (size_t)KA_GROUP * 4096) + (size_t)threadIdx.x * KA_RING_WORDS);
   }
 }
 
@@ -400,15 +439,23 @@ __global__ void __launch_bounds__(KA_THREADS) zstd_fast_lit_kernel(FastDecodeArg
 // Huffman stream decode (one thread), table in shared memory
 // =================================================================================================
 // `lead` = bytes known to be readable in front of src (0 for a frame, 6 for a block unit inside a frame)
+// The bitstream reaches the thread through its own 128-byte ring in shared memory, filled by 16-byte `cp.async.cg` copies
+// (LDGSTS, past the L1) that run eight granules ahead of the read position.  Direct loads -- every thread of the SM walking
+// its own stream -- need one 128-byte L1 line per stream, and 2 x 112 of them beside 224 KB of tables do not fit what is
+// left of the L1: ncu on literal-only chunks showed 30 % L1 hits, 13 x the stream bytes fetched from the L2 and the warps
+// waiting on those loads 65 % of the time (3.8 ms per 16,384 chunks; 2.2 ms of the 6.1 of a config-5 wave).
+__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const FastDesc *D, uint8_t *lits, const uint16_t *tab,
-                                                    uint32_t k, uint32_t *status_out, uint32_t lead) {
+                                                    uint32_t k, uint32_t *status_out, uint32_t lead, uint32_t *ring) {
   const uint32_t seg = D->seg, lit_size = D->lit_size;
   const uint32_t count = (D->n_streams == 1) ? lit_size : (k < 3 ? seg : lit_size - 3 * seg);
   uint8_t *dst = lits + (size_t)k * seg_padded(seg);                          // 16-byte aligned segment
   const int sh = 64 - (int)D->huf_log;
   const uint8_t *const p = src + D->st_off[k];
   const uint32_t nb = D->st_len[k];
-  // position-based reader (see the sequence loop in KB): the words under bit `t` are loaded each round, so there is no
+  // position-based reader (see the sequence loop in KB): the words under bit `t` are taken each round, so there is no
   // refill branch.  W[-1], W[-2] are read under the first stream bits: >= 12 header bytes always precede a Huffman stream.
   bool ok = nb != 0 && D->st_off[k] + lead >= 12 && p[nb - 1] != 0;
   if (ok) {
@@ -417,15 +464,28 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
     int t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);
     uint32_t i = 0;
     uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-    // Five words ride in registers: q0..q2 = W[k], W[k-1], W[k-2] feed this round, q3 and q4 were requested one round
-    // earlier.  A round consumes at most 44 bits, so the window moves down by 0, 1 or 2 words: three selects, and no load on
-    // the path from one round's bit position to the next round's table lookups (the lanes of a warp stall together, and
-    // with 32 streams in lockstep some lane would miss the small L1 on almost every round)
-    int k = max(t >> 5, 0);
-    uint32_t q0 = W[k], q1 = W[max(k - 1, -2)], q2 = W[max(k - 2, -2)], q3 = W[max(k - 3, -2)], q4 = W[max(k - 4, -2)];
+    // Ring numbering: word W[k] is word j = k + bias of an array G that starts on a 16-byte boundary one granule below
+    // W's own (never read below W[-2]); granule g = words 4g .. 4g + 3 lives in ring slot g & 7.
+    const int bias = (int)(((uintptr_t)W >> 2) & 3) + 4;
+    const uint32_t *const G = W - bias;
+    const int jmin = bias - 2, glo = jmin >> 2;
+    int j = max(t >> 5, 0) + bias;
+    // the top granule by word loads (a 16-byte copy could read up to 15 bytes past the stream), seven more by async copies
+    for (int w = max((j >> 2) * 4, jmin); w <= j; w++) ring[w & (KA_RING_WORDS - 1)] = G[w];
+    int gnext = (j >> 2) - 1;
+#pragma unroll
+    for (int r = 0; r < 7; r++)
+      if (gnext >= glo) { cp_async16(ring + (gnext & 7) * 4, G + gnext * 4); gnext--; }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // Five words ride in registers: q0..q2 = W[k], W[k-1], W[k-2] feed this round, q3 and q4 were taken one round
+    // earlier.  A round consumes at most 44 bits, so the window moves down by 0, 1 or 2 words (three selects) and the ring
+    // by at most one granule: one copy request per round keeps it full, and the two granules under the window are always
+    // the two oldest of the eight, so all but the six youngest requests must have landed.
+#define KA_RING(jj) ring[max((jj), jmin) & (KA_RING_WORDS - 1)]
+    uint32_t q0 = KA_RING(j), q1 = KA_RING(j - 1), q2 = KA_RING(j - 2), q3 = KA_RING(j - 3), q4 = KA_RING(j - 4);
     for (; i + 4 <= count; i += 4) {                                          // 4 symbols (<= 44 bits) -> one aligned 32-bit store
       const uint32_t s = (uint32_t)t & 31u;
-      if ((i & 31u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(W + max(k - 32, 0)));
       uint64_t win = ((uint64_t)__funnelshift_r(q1, q0, s) << 32) | __funnelshift_r(q2, q1, s);
       const uint32_t e0 = tab[win >> sh]; win <<= (e0 >> 8);
       const uint32_t e1 = tab[win >> sh]; win <<= (e1 >> 8);
@@ -433,13 +493,21 @@ __device__ __forceinline__ void fast_decode_huffman(const uint8_t *src, const Fa
       const uint32_t e3 = tab[win >> sh];
       t -= (int)((e0 >> 8) + (e1 >> 8) + (e2 >> 8) + (e3 >> 8));
       d32[i >> 2] = (e0 & 0xFF) | ((e1 & 0xFF) << 8) | ((e2 & 0xFF) << 16) | (e3 << 24);
-      const int kn = max(t >> 5, 0), dk = k - kn;
+      const int jn = max(t >> 5, 0) + bias, dk = j - jn;
       const uint32_t n0 = dk == 0 ? q0 : dk == 1 ? q1 : q2;
       const uint32_t n1 = dk == 0 ? q1 : dk == 1 ? q2 : q3;
       const uint32_t n2 = dk == 0 ? q2 : dk == 1 ? q3 : q4;
-      q0 = n0; q1 = n1; q2 = n2; k = kn;
-      q3 = W[max(k - 3, -2)]; q4 = W[max(k - 4, -2)];
+      q0 = n0; q1 = n1; q2 = n2; j = jn;
+      if ((j >> 2) - gnext < 8 && gnext >= glo) {
+        cp_async16(ring + (gnext & 7) * 4, G + gnext * 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        gnext--;
+      }
+      asm volatile("cp.async.wait_group 6;" ::: "memory");
+      q3 = KA_RING(j - 3); q4 = KA_RING(j - 4);
     }
+#undef KA_RING
+    asm volatile("cp.async.wait_group 0;" ::: "memory");                      // (the ring is reused by the next group's stream)
     for (; i < count; i++) {
       const uint32_t e = tab[((uint64_t)peek32(W, t) << 32) >> sh];
       t -= (int)(e >> 8);
@@ -1184,10 +1252,11 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   const uint32_t kp_blocks = (n + KP_WARPS - 1) / KP_WARPS;
   zstd_fast_prep_kernel<<<kp_blocks < 5 * sms ? kp_blocks : 5 * sms, KP_WARPS * 32, 0, stream>>>(F);
   mark("KP", stream);
+  zstd_fast_order_kernel<<<(n + 255) / 256, 256, 0, stream>>>(F);
   const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
   zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
   mark("KA", stream);
-  int count = 2;
+  int count = 3;
   // KB (SMEM-bound: one CTA and two busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
   // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1
   const uint32_t sub_chunks = sms * KB_GROUP;

@@ -9,7 +9,7 @@
 namespace b200zstd {
 
 constexpr size_t LIT_SCRATCH_BYTES = 128 * 1024 + 256;   // per in-flight chunk: one block's literals
-constexpr size_t WS_HEADER_BYTES = 256;                   // work counters etc. at the start of the workspace
+constexpr size_t WS_HEADER_BYTES = 512;                   // work counters etc. at the start of the workspace
 
 // All pointers are DEVICE memory.  out_sizes: in = capacity, out = bytes produced (0 on failure).
 struct DecodeArgs {
@@ -47,6 +47,7 @@ struct FastDecodeArgs {
   uint32_t *slow_list;      // n entries
   uint32_t *slow_count;     // 1 entry, zeroed by the launcher
   uint32_t *group_counters; // [0] literal kernel, [1] sequence kernel work queues; zeroed by the launcher
+  uint32_t *lit_buckets;    // 64 counters + [64] their sum: Huffman chunks by literal count (KP -> order kernel -> KA); zeroed by the launcher
   int general_grid;
   int sm_count;
   uint32_t lo, hi, sub;     // set by the launcher: chunk sub-range and work-queue index of a KB / KC launch
