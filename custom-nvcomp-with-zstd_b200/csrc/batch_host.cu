@@ -249,6 +249,7 @@ public:
     if (overlap_ready) {
       for (auto &e : overlap.ev) cudaEventDestroy(e);
       cudaEventDestroy(overlap.done);
+      cudaEventDestroy(overlap.prep);
       cudaStreamDestroy(overlap.side);
     }
   }
@@ -256,6 +257,7 @@ public:
     if (!overlap_ready) {
       if (cudaStreamCreateWithFlags(&overlap.side, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
       bool ok = cudaEventCreateWithFlags(&overlap.done, cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&overlap.prep, cudaEventDisableTiming) == cudaSuccess;
       for (auto &e : overlap.ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
       if (!ok) { (void)cudaGetLastError(); return nullptr; }
       overlap_ready = true;

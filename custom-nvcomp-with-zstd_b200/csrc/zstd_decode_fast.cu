@@ -1253,15 +1253,23 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   zstd_fast_prep_kernel<<<kp_blocks < 5 * sms ? kp_blocks : 5 * sms, KP_WARPS * 32, 0, stream>>>(F);
   mark("KP", stream);
   zstd_fast_order_kernel<<<(n + 255) / 256, 256, 0, stream>>>(F);
-  const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
-  zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, stream>>>(F);
-  mark("KA", stream);
   int count = 3;
-  // KB (SMEM-bound: one CTA and two busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
-  // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1
+  // KB (SMEM-bound: one CTA and four busy warps per SM) and KC (no SMEM, wants many warps) run together: the batch
+  // is cut into sub-waves of one full KB pass; KC of sub-wave k runs on the side stream while KB decodes k+1.
+  // KA needs nothing from KB and KB nothing from KA (only KC needs both): KA goes to the side stream in front of the first
+  // KC, so that KB's CTAs move in as KA's work queue drains -- on mixed batches KA ends in a long thin tail.
   const uint32_t sub_chunks = sms * KB_GROUP;
   const uint32_t nsub = ov ? (n + sub_chunks - 1) / sub_chunks : 1;
   const bool overlap = ov && nsub > 1 && nsub <= (uint32_t)FastOverlap::MAX_SUB;
+  const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
+  cudaStream_t ka_stream = stream;
+  if (overlap) {
+    if ((e = cudaEventRecord(ov->prep, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(ov->side, ov->prep, 0)) != cudaSuccess) return e;
+    ka_stream = ov->side;
+  }
+  zstd_fast_lit_kernel<<<ka_groups < 2 * sms ? ka_groups : 2 * sms, KA_THREADS, KA_SMEM, ka_stream>>>(F);
+  mark("KA", ka_stream);
   if (!overlap) {
     const uint32_t kb_groups = (n + KB_GROUP - 1) / KB_GROUP;
     launch_kb(kb_warps, kb_groups < sms ? kb_groups : sms, stream, F);

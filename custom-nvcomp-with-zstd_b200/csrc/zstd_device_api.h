@@ -74,6 +74,7 @@ struct FastOverlap {
   cudaStream_t side;
   cudaEvent_t ev[MAX_SUB];
   cudaEvent_t done;
+  cudaEvent_t prep;         // KP + order kernel finished: KA may start on the side stream while KB runs on the caller's
 };
 // returns the number of kernels launched through *launches
 cudaError_t launch_decode_fast(const FastDecodeArgs &args, cudaStream_t stream, const FastOverlap *overlap, int *launches);
