@@ -526,6 +526,7 @@ constexpr int KB_GROUP = 56;                                   // chunks per CTA
 // of its bitstream, so fewer lanes per warp means fewer shared stalls at the price of more issued instructions
 // (measured: see DESIGN.md 4.1).  CUDA_ZSTD_KB_WARPS selects another split for experiments.
 constexpr int KB_DEC_WARPS_DEFAULT = 4;
+constexpr uint32_t KB_SPLIT_DEFAULT = 2;                       // KB launches per sub-wave (see launch_decode_fast)
 __device__ __forceinline__ constexpr int kb_norm_off(int t) { return t == 0 ? 0 : t == 1 ? 40 : 72; }   // LL 36 | OF 32 | ML 53 normalised counts
 struct __align__(16) SeqScratch {                              // per-warp scratch for the table build (432 B: 28 of them fit beside the tables)
   int16_t norm[128];
@@ -688,31 +689,62 @@ struct SeqLane {                                      // one lane's decoder stat
 // `lead`: see fast_decode_huffman.  `unknown_history`: a block unit other than the first of its frame starts with repeat
 // offsets nobody knows yet; sentinels far above any legal offset make every use of them fail KC's range check, which
 // sends the whole frame to the serial decoder
+// `seg` of `segs` (FastDecodeArgs::seq_seg / seq_segs): decode only the sequences of KC's parts [seg P / segs, (seg + 1) P / segs),
+// P = EXEC_PARTS; a segment that is not the last leaves the chain's state in the slot (behind SeqInfo) and, at the index it
+// stopped at, a record with the positions reached, which ends KC's last literal run; a later segment picks the state up.
+#ifndef EXEC_PARTS_V
+#define EXEC_PARTS_V 8
+#endif
+constexpr uint32_t EXEC_PARTS = EXEC_PARTS_V;     // KC's work items per chunk (see the queue in zstd_fast_exec_kernel)
+struct SeqSave { int t; uint32_t sl, sm, so, rep0, rep1, rep2, out_pos, lit_pos, err; };
+static_assert(sizeof(SeqInfo) + sizeof(SeqSave) <= 64, "the slot reserves 64 bytes for SeqInfo + SeqSave");
 __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
-                                                      const SeqInfo &I, uint32_t lead, bool unknown_history) {
+                                                      const SeqInfo &I, uint32_t lead, bool unknown_history, uint32_t seg, uint32_t segs, SeqSave *save) {
   const uint32_t nseq = D->nseq;
+  const uint32_t groups = (nseq + 31) >> 5;
+  // first sequence of KC part p (< nseq for p < P: a segment that is not the last never reaches the last sequence)
+  auto part_begin = [&](uint32_t p) { return p >= EXEC_PARTS ? nseq : min(nseq, (groups * p / EXEC_PARTS) << 5); };
+  const uint32_t begin = part_begin(seg * EXEC_PARTS / segs), end = seg + 1 == segs ? nseq : part_begin((seg + 1) * EXEC_PARTS / segs);
   uint32_t err = ST_OK;
   SeqLane L;
   L.out_pos = 0; L.lit_pos = 0;
   const uint8_t *const p = src + I.bits_off;
   const uint32_t nb = I.bits_len;
   // W[-1], W[-2] are read under the first stream bits: a fast-path frame has >= 12 header bytes before the bitstream
-  if (nb == 0 || I.bits_off + lead < 12 || p[nb - 1] == 0) err = ST_CORRUPT;
+  if (nb == 0 || I.bits_off + lead < 12 || p[nb - 1] == 0 || (seg != 0 && save->err != ST_OK)) err = ST_CORRUPT;
   else {
     L.ll16 = T.t16; L.ml16 = T.t16 + 512; L.of16 = T.t16 + 1024;
     L.ll8 = T.t8; L.ml8 = T.t8 + 512; L.of8 = T.t8 + 1024;
     L.bases = bases; L.out = out;
     L.W = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
     const int d = (int)((uintptr_t)p & 3), low = 8 * d;
-    L.t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);       // the sentinel bit itself is not payload
-    { const uint32_t a = peek32(L.W, L.t); L.sl = top_bits(a, 0, (int)I.ll_log); L.so = top_bits(a, (int)I.ll_log, (int)I.of_log);
-      L.sm = top_bits(a, (int)(I.ll_log + I.of_log), (int)I.ml_log); L.t -= (int)(I.ll_log + I.of_log + I.ml_log); }
-    L.rep0 = 1; L.rep1 = 4; L.rep2 = 8;
-    if (unknown_history) { L.rep0 = 0xFFFFFF01u; L.rep1 = 0xFFFFFF02u; L.rep2 = 0xFFFFFF03u; }
-    for (uint32_t i = 0; i + 1 < nseq; i++) L.step<false>(i);
-    L.step<true>(nseq - 1);
-    // positions stay bounded even on garbage (they cannot wrap within 65536 sequences), and KC checks every record before using it
-    if (L.t != low) err = ST_CORRUPT;                      // the stream must end exactly on its first bit
+    if (seg != 0) {
+      const SeqSave s = *save;
+      L.t = s.t; L.sl = s.sl; L.sm = s.sm; L.so = s.so; L.rep0 = s.rep0; L.rep1 = s.rep1; L.rep2 = s.rep2;
+      L.out_pos = s.out_pos; L.lit_pos = s.lit_pos;
+    } else {
+      L.t = 8 * (d + (int)nb - 1) + highbit32(p[nb - 1]);       // the sentinel bit itself is not payload
+      { const uint32_t a = peek32(L.W, L.t); L.sl = top_bits(a, 0, (int)I.ll_log); L.so = top_bits(a, (int)I.ll_log, (int)I.of_log);
+        L.sm = top_bits(a, (int)(I.ll_log + I.of_log), (int)I.ml_log); L.t -= (int)(I.ll_log + I.of_log + I.ml_log); }
+      L.rep0 = 1; L.rep1 = 4; L.rep2 = 8;
+      if (unknown_history) { L.rep0 = 0xFFFFFF01u; L.rep1 = 0xFFFFFF02u; L.rep2 = 0xFFFFFF03u; }
+    }
+    const uint32_t stop = min(end, nseq - 1);
+    for (uint32_t i = begin; i < stop; i++) L.step<false>(i);
+    if (end == nseq) {
+      L.step<true>(nseq - 1);
+      // positions stay bounded even on garbage (they cannot wrap within 65536 sequences), and KC checks every record before using it
+      if (L.t != low) err = ST_CORRUPT;                      // the stream must end exactly on its first bit
+    }
+  }
+  if (end != nseq) {
+    SeqSave s;
+    s.t = L.t; s.sl = L.sl; s.sm = L.sm; s.so = L.so; s.rep0 = L.rep0; s.rep1 = L.rep1; s.rep2 = L.rep2;
+    s.out_pos = L.out_pos; s.lit_pos = L.lit_pos; s.err = err;
+    *save = s;
+    out[end] = make_uint4(L.out_pos, L.lit_pos, 0, 0);       // (the next segment writes the whole record: same positions)
+    D->seq_status = err;
+    return;
   }
   out[nseq] = make_uint4(L.out_pos, L.lit_pos, 0, 0);       // sentinel: literal length of the last sequence, block totals
   D->seq_status = err; D->out_end = L.out_pos; D->lit_end = L.lit_pos;
@@ -813,7 +845,7 @@ __global__ void __launch_bounds__(32 * KB_DEC_WARPS, 1) zstd_fast_seq_kernel(Fas
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   uint32_t phase = 0;
   for (;;) {
-    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + 1 + F.sub, 1u);
+    if (threadIdx.x == 0) s_group = atomicAdd(F.group_counters + F.kb_queue, 1u);
     __syncthreads();                                                  // also: every lane is done with the previous group's tables
     const uint32_t g0 = F.lo + s_group * KB_GROUP;
     if (g0 >= F.hi) break;
@@ -835,7 +867,8 @@ __global__ void __launch_bounds__(32 * KB_DEC_WARPS, 1) zstd_fast_seq_kernel(Fas
     if (mine && info.ready) {
       const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
       fast_decode_sequences((const uint8_t *)A.in_ptrs[g0 + c], slot.desc(), slot.seqs(), T, bases, info, F.bare_blocks ? 6u : 0u,
-                            F.bare_blocks && (F.unit_base + g0 + c) != 0);
+                            F.bare_blocks && (F.unit_base + g0 + c) != 0, F.seq_seg, F.seq_segs,
+                            reinterpret_cast<SeqSave *>(slot.seq_info() + sizeof(SeqInfo)));
     }
   }
 }
@@ -844,7 +877,6 @@ __global__ void __launch_bounds__(32 * KB_DEC_WARPS, 1) zstd_fast_seq_kernel(Fas
 // KC: sequence execution, one warp per chunk, one lane per sequence
 // =================================================================================================
 constexpr int EXEC_WARPS = 4;
-constexpr uint32_t EXEC_PARTS = 4;     // work items per chunk (see the queue in zstd_fast_exec_kernel)
 
 struct LitSrc {
   const uint8_t *base;
@@ -905,14 +937,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
   // quarter of the warps idle; quarters make that 6.9 -> 7 rounds of a quarter's length.  A part waits for its predecessor
   // on the chunk's hand-over word (release / acquire at gpu scope: its matches read what the predecessor wrote, possibly
   // on another SM); the predecessor is always held by a running warp, and part 0 waits for nobody.
-  uint32_t *const queue = F.base.counter + 2 + F.sub;
+  // (When KB decodes a sub-wave in two launches, this launch executes parts [part_lo, part_hi) only.)
+  uint32_t *const queue = F.base.counter + F.kc_queue;
   const uint32_t span = F.hi - F.lo;
   for (;;) {
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(queue, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= span * EXEC_PARTS) break;
-    const uint32_t part = item / span, chunk = F.lo + (item - part * span);
+    if (item >= span * (F.part_hi - F.part_lo)) break;
+    const uint32_t part = F.part_lo + item / span, chunk = F.lo + item % span;
     ChunkSlot slot = slot_of(F, chunk);
     const FastDesc *D = slot.desc();
     if (D->state != 0) continue;
@@ -935,6 +968,8 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
       }
       __syncwarp();
       status = __shfl_sync(0xffffffffu, seen, 0);
+      // the first part of a later launch: KB has finished the chunk in between, its verdict on the whole stream counts now
+      if (part == F.part_lo && status == ST_OK) status = D->seq_status;
     }
     uint32_t total = 0;
     if (status == ST_OK) {
@@ -1240,11 +1275,12 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   }
   FastDecodeArgs F = F0;
   F.lo = 0; F.hi = n; F.sub = 0;
+  F.seq_seg = 0; F.seq_segs = 1; F.part_lo = 0; F.part_hi = EXEC_PARTS; F.kb_queue = 1; F.kc_queue = 2;
   // CUDA_ZSTD_TRACE=1: events after every launch, printed as "kernel@ms since the call began" once the call has drained
   // (a debugging aid: it synchronises the stream; this is how the KB / KC overlap in DESIGN.md 4.1 was timed)
   static const bool trace = getenv("CUDA_ZSTD_TRACE") != nullptr;
-  cudaEvent_t te[24]; const char *tn[24]; int tc = 0;
-  auto mark = [&](const char *name, cudaStream_t st) { if (trace && tc < 24 && cudaEventCreate(&te[tc]) == cudaSuccess) { cudaEventRecord(te[tc], st); tn[tc++] = name; } };
+  cudaEvent_t te[40]; const char *tn[40]; int tc = 0;
+  auto mark = [&](const char *name, cudaStream_t st) { if (trace && tc < 40 && cudaEventCreate(&te[tc]) == cudaSuccess) { cudaEventRecord(te[tc], st); tn[tc++] = name; } };
   mark("start", stream);
   // one memset zeroes every counter of the pipeline: general work queue, slow count, pool heads, group counters
   if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
@@ -1276,16 +1312,27 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
     zstd_fast_exec_kernel<<<exec_grid(n, sms), EXEC_WARPS * 32, 0, stream>>>(F);
     count += 2;
   } else {
+    // Each sub-wave's sequences are decoded by S KB launches (the chain's state waits in the slot in between): KC starts on
+    // the first parts of every chunk while KB decodes the sequences of the later ones (CUDA_ZSTD_KB_SPLIT=S; 1: one launch).
+    static const uint32_t split_env = getenv("CUDA_ZSTD_KB_SPLIT") ? (uint32_t)atoi(getenv("CUDA_ZSTD_KB_SPLIT")) : KB_SPLIT_DEFAULT;
+    uint32_t S = split_env < 1 ? 1u : split_env > EXEC_PARTS ? EXEC_PARTS : split_env;
+    while (S > 1 && (S * nsub > (uint32_t)FastOverlap::MAX_SUB || EXEC_PARTS % S)) S--;
     for (uint32_t k = 0; k < nsub; k++) {
       F.lo = k * sub_chunks; F.hi = F.lo + sub_chunks < n ? F.lo + sub_chunks : n; F.sub = k;
       const uint32_t m = F.hi - F.lo, kb_groups = (m + KB_GROUP - 1) / KB_GROUP;
-      launch_kb(kb_warps, kb_groups < sms ? kb_groups : sms, stream, F);
-      mark("KB", stream);
-      if ((e = cudaEventRecord(ov->ev[k], stream)) != cudaSuccess) return e;
-      if ((e = cudaStreamWaitEvent(ov->side, ov->ev[k], 0)) != cudaSuccess) return e;
-      zstd_fast_exec_kernel<<<exec_grid(m, sms, k + 1 == nsub), EXEC_WARPS * 32, 0, ov->side>>>(F);
-      mark("KC", ov->side);
-      count += 2;
+      for (uint32_t h = 0; h < S; h++) {
+        const uint32_t q = S * k + h;
+        F.seq_seg = h; F.seq_segs = S;
+        F.part_lo = h * EXEC_PARTS / S; F.part_hi = (h + 1) * EXEC_PARTS / S;
+        F.kb_queue = 1 + q; F.kc_queue = S > 1 ? 20 + q : 2 + q;
+        launch_kb(kb_warps, kb_groups < sms ? kb_groups : sms, stream, F);
+        mark(h ? "KBb" : "KB", stream);
+        if ((e = cudaEventRecord(ov->ev[q], stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(ov->side, ov->ev[q], 0)) != cudaSuccess) return e;
+        zstd_fast_exec_kernel<<<exec_grid(m, sms, k + 1 == nsub && h + 1 == S), EXEC_WARPS * 32, 0, ov->side>>>(F);
+        mark(h ? "KCb" : "KC", ov->side);
+        count += 2;
+      }
     }
     if ((e = cudaEventRecord(ov->done, ov->side)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(stream, ov->done, 0)) != cudaSuccess) return e;
