@@ -526,7 +526,9 @@ constexpr int KB_GROUP = 56;                                   // chunks per CTA
 // of its bitstream, so fewer lanes per warp means fewer shared stalls at the price of more issued instructions
 // (measured: see DESIGN.md 4.1).  CUDA_ZSTD_KB_WARPS selects another split for experiments.
 constexpr int KB_DEC_WARPS_DEFAULT = 4;
-constexpr uint32_t KB_SPLIT_DEFAULT = 2;                       // KB launches per sub-wave (see launch_decode_fast)
+constexpr uint32_t KB_SPLIT_DEFAULT = 2;                       // KB launches per sub-wave (see launch_decode_fast) ...
+constexpr uint32_t KB_SPLIT_ONE_SUBWAVE = 4;                   // ... and when the batch is a single sub-wave
+constexpr uint32_t KB_SPLIT_MIN_CHUNKS = 1;                    // (measured down to one chunk: 0.88 -> 0.60 ms; CUDA_ZSTD_MIN_SPLIT raises it)
 __device__ __forceinline__ constexpr int kb_norm_off(int t) { return t == 0 ? 0 : t == 1 ? 40 : 72; }   // LL 36 | OF 32 | ML 53 normalised counts
 struct __align__(16) SeqScratch {                              // per-warp scratch for the table build (432 B: 28 of them fit beside the tables)
   int16_t norm[128];
@@ -1296,7 +1298,9 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   // KC, so that KB's CTAs move in as KA's work queue drains -- on mixed batches KA ends in a long thin tail.
   const uint32_t sub_chunks = sms * KB_GROUP;
   const uint32_t nsub = ov ? (n + sub_chunks - 1) / sub_chunks : 1;
-  const bool overlap = ov && nsub > 1 && nsub <= (uint32_t)FastOverlap::MAX_SUB;
+  // (a batch of one sub-wave overlaps too, through the segments below, once it is large enough to pay for the extra launches)
+  static const uint32_t min_split = getenv("CUDA_ZSTD_MIN_SPLIT") ? (uint32_t)atoi(getenv("CUDA_ZSTD_MIN_SPLIT")) : KB_SPLIT_MIN_CHUNKS;
+  const bool overlap = ov && (nsub > 1 || n >= min_split) && nsub <= (uint32_t)FastOverlap::MAX_SUB;
   const uint32_t ka_groups = (n + KA_GROUP - 1) / KA_GROUP;
   cudaStream_t ka_stream = stream;
   if (overlap) {
@@ -1314,8 +1318,9 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   } else {
     // Each sub-wave's sequences are decoded by S KB launches (the chain's state waits in the slot in between): KC starts on
     // the first parts of every chunk while KB decodes the sequences of the later ones (CUDA_ZSTD_KB_SPLIT=S; 1: one launch).
-    static const uint32_t split_env = getenv("CUDA_ZSTD_KB_SPLIT") ? (uint32_t)atoi(getenv("CUDA_ZSTD_KB_SPLIT")) : KB_SPLIT_DEFAULT;
-    uint32_t S = split_env < 1 ? 1u : split_env > EXEC_PARTS ? EXEC_PARTS : split_env;
+    static const uint32_t split_env = getenv("CUDA_ZSTD_KB_SPLIT") ? (uint32_t)atoi(getenv("CUDA_ZSTD_KB_SPLIT")) : 0u;
+    uint32_t S = split_env ? split_env : nsub == 1 ? KB_SPLIT_ONE_SUBWAVE : KB_SPLIT_DEFAULT;
+    if (S > EXEC_PARTS) S = EXEC_PARTS;
     while (S > 1 && (S * nsub > (uint32_t)FastOverlap::MAX_SUB || EXEC_PARTS % S)) S--;
     for (uint32_t k = 0; k < nsub; k++) {
       F.lo = k * sub_chunks; F.hi = F.lo + sub_chunks < n ? F.lo + sub_chunks : n; F.sub = k;
