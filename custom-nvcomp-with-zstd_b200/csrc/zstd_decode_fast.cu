@@ -909,7 +909,16 @@ __device__ __forceinline__ void warp_copy_match(uint8_t *out, uint32_t d, uint32
       const uint8_t a = sp[k], b = sp[k + 32], c = sp[k + 64], e = sp[k + 96];
       dp[k] = a; dp[k + 32] = b; dp[k + 64] = c; dp[k + 96] = e;
     }
-    for (; k < ml; k += 32) dp[k] = sp[k];
+    // (up to three more steps: their loads leave together too -- a step-by-step tail costs one L2 round trip per 32 bytes)
+    const bool h0 = k < ml, h1 = k + 32 < ml, h2 = k + 64 < ml;
+    uint8_t a = 0, b = 0, c = 0;
+    if (h0) a = sp[k];
+    if (h1) b = sp[k + 32];
+    if (h2) c = sp[k + 64];
+    if (h0) dp[k] = a;
+    if (h1) dp[k + 32] = b;
+    if (h2) dp[k + 64] = c;
+    for (k += 96; k < ml; k += 32) dp[k] = sp[k];
   } else if (offset >= 32) {
     // every 32-byte step reads bytes that earlier steps wrote: keep the steps ordered
     for (uint32_t k0 = 0; k0 < ml; k0 += 32) {
@@ -1172,8 +1181,8 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
 // Multi-block frames: cut ONE frame into block units so that its blocks decode side by side
 // =================================================================================================
 // One thread walks the block headers (a frame of B blocks costs B dependent 3-byte reads).  The cut is speculative: unit k
-// is given the output range [k * 128 KB, +min(128 KB, rest)), i.e. every block but the last is assumed to regenerate a
-// full block -- what one-shot compressors (libzstd's, and this library's block-parallel one) emit.  The units are then
+// is given the output range [k * B, +min(B, rest)), B = the frame's Block_Maximum_Size, i.e. every block but the last is
+// assumed to regenerate a full block -- what one-shot compressors (libzstd's, and this library's block-parallel one) emit.  The units are then
 // decoded as bare blocks; a unit that regenerates anything else, uses repeat offsets it did not establish itself,
 // reaches behind its own output, or needs a previous block's tables fails, and the caller decodes the frame serially.
 __global__ void zstd_split_frame_kernel(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, uint32_t max_units, const void **in_ptrs,
@@ -1189,13 +1198,20 @@ __global__ void zstd_split_frame_kernel(const uint8_t *src, size_t n, uint8_t *d
     const uint32_t fcs_size = fcs_flag == 0 ? single : (1u << fcs_flag);
     if (fcs_size == 0) break;                                             // no content size: nothing to speculate on
     if (h + (single ? 0 : 1) + fcs_size + 3 > n) break;
-    if (!single) h++;
+    // Block_Maximum_Size = min(Window_Size, 128 KB) (RFC 8878 3.1.1.2.4): a frame whose window is below 128 KB -- this
+    // library's block-parallel compressor writes 64 KB blocks for mid-sized buffers -- is cut at that size
+    uint64_t blk = BLOCK_MAX;
+    if (!single) {
+      const uint32_t wd = src[h++];
+      const uint64_t wbase = 1ull << (10 + (wd >> 3)), wsize = wbase + (wbase >> 3) * (wd & 7);
+      if (wsize < blk) blk = wsize;
+    }
     uint64_t fcs = 0;
     for (uint32_t k = 0; k < fcs_size; k++) fcs |= (uint64_t)src[h + k] << (8 * k);
     if (fcs_size == 2) fcs += 256;
     h += fcs_size;
-    if (fcs <= BLOCK_MAX || fcs > cap) break;                             // one block: the ordinary path is as good
-    const uint64_t want = (fcs + BLOCK_MAX - 1) / BLOCK_MAX;
+    if (fcs <= blk || fcs > cap) break;                                   // one block: the ordinary path is as good
+    const uint64_t want = (fcs + blk - 1) / blk;
     if (want > max_units) break;
     uint32_t units = 0;
     bool good = true, last = false;
@@ -1205,12 +1221,12 @@ __global__ void zstd_split_frame_kernel(const uint8_t *src, size_t n, uint8_t *d
       last = bh & 1;
       const uint32_t btype = (bh >> 1) & 3, bsize = bh >> 3;
       const uint32_t body = btype == 1 ? 1u : bsize;
-      if (btype == 3 || bsize > BLOCK_MAX || (uint64_t)h + 3 + body > n) { good = false; break; }
+      if (btype == 3 || bsize > blk || (uint64_t)h + 3 + body > n) { good = false; break; }
       in_ptrs[units] = src + h;
       in_sizes[units] = 3 + (size_t)body;
-      out_ptrs[units] = dst + (size_t)units * BLOCK_MAX;
-      const uint64_t rest = fcs - (uint64_t)units * BLOCK_MAX;
-      out_sizes[units] = rest < BLOCK_MAX ? rest : BLOCK_MAX;
+      out_ptrs[units] = dst + (size_t)units * blk;
+      const uint64_t rest = fcs - (uint64_t)units * blk;
+      out_sizes[units] = rest < blk ? rest : blk;
       units++;
       h += 3 + body;
     }

@@ -128,8 +128,9 @@ def test_scan_and_pack(oracle, pkg):
 @pytest.mark.gpu
 @pytest.mark.parametrize("level", [1, 3, 5, 9])
 def test_large_single_buffer_is_one_frame_of_parallel_blocks(oracle, libzstd, pkg, level):
-    """a single buffer above 128 KB is cut into independent 128 KB blocks encoded side by side and
-    assembled into ONE stock frame (windowed header, 4-byte content size).  libzstd and the oracle must decode it."""
+    """a single buffer above 128 KB is cut into independent blocks (64 KB up to 4 MB, 128 KB above) encoded
+    side by side and assembled into ONE stock frame (windowed header: window = block size, 4-byte content size).  libzstd and
+    the oracle must decode it."""
     if True:
         for n in (131073, (1 << 20) + 12345, 6 << 20):
             x = oracle.gen_batch(65536, (n + 65535) // 65536, 0, 26000)[:n].copy()
@@ -139,13 +140,16 @@ def test_large_single_buffer_is_one_frame_of_parallel_blocks(oracle, libzstd, pk
             xd = torch.from_numpy(x).cuda()
             s = pkg.ZstdSingle(level)
             # (the single-buffer C API has no checksum switch: checksummed big frames are covered by tests/cpp)
-            cap = n + n // 255 + 3 * ((n + 131071) // 131072) + 512
+            cap = n + n // 255 + 3 * ((n + 65535) // 65536) + 512
             comp = torch.zeros(cap, dtype=torch.uint8, device="cuda")
             w = torch.empty(s.compress_workspace(n), dtype=torch.uint8, device="cuda")
             rc, csz = s.compress(xd, n, comp, cap, w, w.numel())
             assert rc == 0 and 0 < csz < n
             frame = comp.cpu().numpy()[:csz]
-            assert frame[4] & 0x20 == 0 and frame[4] >> 6 == 2 and frame[5] == 0x38        # windowed, 4-byte content size, 128 KB window
+            # windowed, 4-byte content size, window = block size: 64 KB up to 4 MB, 128 KB above
+            assert frame[4] & 0x20 == 0 and frame[4] >> 6 == 2 and frame[5] == (0x30 if n <= (4 << 20) else 0x38)
+            _, _, info = oracle.decompress(frame, n, want_info=True)
+            assert info.n_blocks == (n + 65535) // 65536 if n <= (4 << 20) else info.n_blocks == (n + 131071) // 131072
             assert libzstd.frame_content_size(frame) == n
             assert np.array_equal(libzstd.decompress(frame, n), x)
             rc2, out = oracle.decompress(frame, n)
