@@ -1138,7 +1138,7 @@ struct cuda_zstd_dict_t { std::vector<unsigned char> bytes; uint32_t id = 0; };
 
 // streams and events of the host-resident batch calls (cuda_zstd_batch_*_host*), created on first use
 struct HostPipe {
-  static constexpr int MAX_WAVES = 4;
+  static constexpr int MAX_WAVES = 8;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_entry = nullptr, ev_in[MAX_WAVES] = {}, ev_run[MAX_WAVES] = {}, ev_done = nullptr;
   bool ready = false;
@@ -1187,9 +1187,19 @@ size_t plan_runs(const void *const *ptrs, const size_t *sizes, size_t lo, size_t
   }
   return align_up(d_off, 256);
 }
-// chunk ranges of the pipeline waves: 1 : 2 : 4 : 9 sixteenths, so that the first results leave early
-int plan_waves(size_t n, size_t edges[HostPipe::MAX_WAVES + 1]) {
+// chunk ranges of the pipeline waves.  Decompress: 1 : 2 : 4 : 9 sixteenths, so that the first results leave early (the
+// device-to-host copy of the output is the long pole).  Compress: the host-to-device copy of the input is, and the encoder
+// runs about as fast as the link, so the call ends one wave's compress time after the last input byte has arrived: equal
+// waves, as many as keep a wave at 2,048 chunks or more (CUDA_ZSTD_HOST_WAVES overrides the count).
+int plan_waves(size_t n, size_t edges[HostPipe::MAX_WAVES + 1], bool compress = false) {
   if (n < 1024) { edges[0] = 0; edges[1] = n; return 1; }
+  if (compress) {
+    static const int env = getenv("CUDA_ZSTD_HOST_WAVES") ? atoi(getenv("CUDA_ZSTD_HOST_WAVES")) : 0;
+    int k = env > 0 ? env : (int)std::min<size_t>(HostPipe::MAX_WAVES, n / 2048);
+    k = std::max(1, std::min(k, HostPipe::MAX_WAVES));
+    for (int w = 0; w <= k; w++) edges[w] = n * (size_t)w / (size_t)k;
+    return k;
+  }
   edges[0] = 0; edges[1] = n / 16; edges[2] = 3 * n / 16; edges[3] = 7 * n / 16; edges[4] = n;
   return 4;
 }
@@ -1429,7 +1439,7 @@ int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *b, const void *const
     if (!b->pipe.init()) return 4;
     HostPipe &P = b->pipe;
     size_t edges[HostPipe::MAX_WAVES + 1];
-    const int nw = plan_waves(n, edges);
+    const int nw = plan_waves(n, edges, true);
     std::vector<HostRun> in_runs[HostPipe::MAX_WAVES];
     std::vector<size_t> in_off(n), caps(n), frame_off(n);
     size_t off = 0;
