@@ -302,6 +302,8 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
   // [128..223] staging.
   const int log_ll = W.tab_log[0], log_of = W.tab_log[1], log_ml = W.tab_log[2];
   uint32_t *const park = W.count, *const codes = W.count + 96, *const stage = W.count + 128;
+  // (the table builds are over: their scratch -- cell, norm, cumul -- stages the transforms: LL, OF in cell, ML in norm / cumul)
+  uint32_t *const est01 = reinterpret_cast<uint32_t *>(W.cell), *const est2 = reinterpret_cast<uint32_t *>(W.norm);
   uint8_t *const sp = dst + op;
   uint32_t *const w32 = reinterpret_cast<uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
   const uint32_t lead = (uint32_t)((uintptr_t)sp & 3);
@@ -329,20 +331,24 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
         if (kn < nseq) { const uint32_t i = nseq - 1 - kn; na = sll[i]; nb_ = sml[i]; nc = sofv[i]; }
       }
       const uint32_t llc = ll_code(a), ofc = (uint32_t)hb32(c), mlc = ml_code(valid ? b : 3u);
+      // the per-symbol transforms of my three codes: the chain lanes read them from shared memory (so a chain step is the
+      // recurrence only: add, shift, shift, add, table load), and I need them again to cut my bits out of the parked states
+      const SymTT e_ll = W.tt[0][llc], e_of = W.tt[1][ofc], e_ml = W.tt[2][mlc];
       codes[lane] = llc | (ofc << 8) | (mlc << 16);
+      est01[lane] = (uint32_t)e_ll.delta_nb; est01[32 + lane] = (uint32_t)e_ll.delta_state;
+      est01[64 + lane] = (uint32_t)e_of.delta_nb; est01[96 + lane] = (uint32_t)e_of.delta_state;
+      est2[lane] = (uint32_t)e_ml.delta_nb; est2[32 + lane] = (uint32_t)e_ml.delta_state;
       stage[lane] = 0; stage[32 + lane] = 0; stage[64 + lane] = 0;
       __syncwarp();
       const uint32_t nv = min(32u, nseq - base);
       if (lane < 3 && log) {
-        for (uint32_t j = 0; j < nv; j++) {
-          const uint32_t code = (codes[j] >> (8 * t)) & 0xFF;
-          if (base + j == 0) state = fse_init_state(st, tt, code);
-          else {
-            const SymTT e = tt[code];
-            const uint32_t nb = (uint32_t)((int32_t)state + e.delta_nb) >> 16;
-            park[t * 32 + j] = (state & ((1u << nb) - 1u)) | (nb << 9);
-            state = st[(int32_t)(state >> nb) + e.delta_state];
-          }
+        const uint32_t *const dn = t < 2 ? est01 + 64 * t : est2, *const ds = dn + 32;
+        uint32_t j = 0;
+        if (base == 0) { state = fse_init_state(st, tt, (codes[0] >> (8 * t)) & 0xFF); j = 1; }
+        for (; j < nv; j++) {
+          const uint32_t nb = (uint32_t)((int32_t)state + (int32_t)dn[j]) >> 16;
+          park[t * 32 + j] = state;                                         // the state BEFORE the step: its low nb bits are the output
+          state = st[(int32_t)(state >> nb) + (int32_t)ds[j]];
         }
       }
       if (lane == 0) stage[0] = carry;
@@ -352,9 +358,9 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
       uint32_t nlo = 0, nhi = 0;
       if (valid) {
         if (kk > 0) {
-          if (log_of) { const uint32_t v = park[32 + lane]; lo |= (uint64_t)(v & 0x1FF) << nlo; nlo += v >> 9; }
-          if (log_ml) { const uint32_t v = park[64 + lane]; lo |= (uint64_t)(v & 0x1FF) << nlo; nlo += v >> 9; }
-          if (log_ll) { const uint32_t v = park[lane]; lo |= (uint64_t)(v & 0x1FF) << nlo; nlo += v >> 9; }
+          if (log_of) { const uint32_t v = park[32 + lane], nb = (uint32_t)((int32_t)v + e_of.delta_nb) >> 16; lo |= (uint64_t)(v & ((1u << nb) - 1u)) << nlo; nlo += nb; }
+          if (log_ml) { const uint32_t v = park[64 + lane], nb = (uint32_t)((int32_t)v + e_ml.delta_nb) >> 16; lo |= (uint64_t)(v & ((1u << nb) - 1u)) << nlo; nlo += nb; }
+          if (log_ll) { const uint32_t v = park[lane], nb = (uint32_t)((int32_t)v + e_ll.delta_nb) >> 16; lo |= (uint64_t)(v & ((1u << nb) - 1u)) << nlo; nlo += nb; }
         }
         lo |= (uint64_t)(a - ll_base(llc)) << nlo; nlo += ll_xbits(llc);
         hi = (uint64_t)(b - ml_base(mlc)); nhi = ml_xbits(mlc);
