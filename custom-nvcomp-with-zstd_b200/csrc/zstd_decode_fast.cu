@@ -932,9 +932,12 @@ __device__ __forceinline__ void warp_copy_match(uint8_t *out, uint32_t d, uint32
 }
 
 // (9 CTAs per SM by registers = 56 per thread: eight resident KC CTAs then leave room for KB's CTA beside them)
-constexpr uint32_t EXEC_OWN = 256;      // pieces of a group whose owning sequence is looked up in shared memory (a group rarely has more)
+#ifndef EXEC_OWN_V
+#define EXEC_OWN_V 256
+#endif
+constexpr uint32_t EXEC_OWN = EXEC_OWN_V;      // pieces of a group whose owning sequence is looked up in shared memory (a group rarely has more)
 __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(FastDecodeArgs F) {
-  __shared__ uint8_t s_own[EXEC_WARPS][EXEC_OWN];
+  __shared__ uint8_t s_own[EXEC_WARPS][EXEC_OWN ? EXEC_OWN : 1];
   const DecodeArgs &A = F.base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t *const own = s_own[warp];
