@@ -1141,6 +1141,7 @@ struct HostPipe {
   static constexpr int MAX_WAVES = 8;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_entry = nullptr, ev_in[MAX_WAVES] = {}, ev_run[MAX_WAVES] = {}, ev_done = nullptr;
+  unsigned long long *h_totals = nullptr;      // pinned: the packed size after every wave (compress_host_packed)
   bool ready = false;
   bool init() {
     if (ready) return true;
@@ -1148,6 +1149,7 @@ struct HostPipe {
     ok = ok && cudaEventCreateWithFlags(&ev_entry, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < MAX_WAVES && ok; i++)
       ok = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev_run[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&h_totals), MAX_WAVES * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) { (void)cudaGetLastError(); return false; }
     return ready = true;
   }
@@ -1156,6 +1158,7 @@ struct HostPipe {
     for (int i = 0; i < MAX_WAVES; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_run[i]); }
     cudaEventDestroy(ev_entry); cudaEventDestroy(ev_done);
     cudaStreamDestroy(s_in); cudaStreamDestroy(s_out);
+    cudaFreeHost(h_totals);
   }
 };
 struct cuda_zstd_batch { cuda_zstd::nvcomp_v5::NvcompV5BatchManager *m; HostPipe pipe; };
@@ -1467,38 +1470,62 @@ int cuda_zstd_batch_compress_host_packed(cuda_zstd_batch_t *b, const void *const
     if ((e = cudaMemcpyAsync(d_tab, tab.data(), 4 * n * 8, cudaMemcpyHostToDevice, P.s_in)) != cudaSuccess) return 4;
     int launches = 0;
     Status overall = Status::SUCCESS;
+    // all input copies are queued at once (every wave has its own staging range): the link never waits for the host
     for (int w = 0; w < nw; w++) {
-      const size_t lo = edges[w], m = edges[w + 1] - edges[w];
-      if (m == 0) continue;
       for (const HostRun &r : in_runs[w])
         if ((e = cudaMemcpyAsync(d + r.d_off, r.h_begin, r.bytes, cudaMemcpyHostToDevice, P.s_in)) != cudaSuccess) return 4;
       cudaEventRecord(P.ev_in[w], P.s_in);
+    }
+    // Per wave: compress, scan of the wave's frame sizes chained to the previous wave's closing offset, pack, and the closing
+    // offset to pinned host memory.  The host follows one wave behind: as soon as wave w - 1 has its closing offset it
+    // queues that wave's packed bytes on the copy-out stream, beside the compress of wave w.
+    unsigned long long done_bytes = 0;
+    int rc_cap = 0;
+    auto copy_home = [&](int w) -> int {
+      if (cudaEventSynchronize(P.ev_run[w]) != cudaSuccess) return 4;
+      const unsigned long long upto = P.h_totals[w];
+      if (upto > packed_cap) { rc_cap = 7; return 0; }
+      if (upto > done_bytes && rc_cap == 0 &&
+          cudaMemcpyAsync(static_cast<unsigned char *>(h_packed) + done_bytes, d + packed_base + done_bytes, (size_t)(upto - done_bytes),
+                          cudaMemcpyDeviceToHost, P.s_out) != cudaSuccess) return 4;
+      done_bytes = upto;
+      return 0;
+    };
+    int prev = -1;
+    for (int w = 0; w < nw; w++) {
+      const size_t lo = edges[w], m = edges[w + 1] - edges[w];
+      if (m == 0) continue;
       cudaStreamWaitEvent(stream, P.ev_in[w], 0);
       Status s = I->run(true, reinterpret_cast<const void *const *>(d_tab) + lo, reinterpret_cast<const size_t *>(d_tab + n * 8) + lo, m,
                         reinterpret_cast<void *const *>(d_tab + 2 * n * 8) + lo, reinterpret_cast<size_t *>(d_tab + 3 * n * 8) + lo, d_status + lo,
                         true, d + ws_base, tmp_bytes - ws_base, stream, false, nullptr, nullptr);
       if (s != Status::SUCCESS) overall = s;
       launches += I->last_launches;
+      const size_t *wsizes = reinterpret_cast<const size_t *>(d_tab + 3 * n * 8) + lo;
+      if ((lo == 0 ? b200zstd::launch_scan_sizes(wsizes, m, 0, d_offsets, stream)
+                   : b200zstd::launch_scan_sizes_from(wsizes, m, d_offsets + lo, d_offsets + lo, stream)) != cudaSuccess) return 4;
+      if (b200zstd::launch_pack(reinterpret_cast<const void *const *>(d_tab + 2 * n * 8) + lo, wsizes, d_offsets + lo, m, d + packed_base, stream) !=
+          cudaSuccess) return 4;
+      launches += 2;
+      if (cudaMemcpyAsync(P.h_totals + w, d_offsets + lo + m, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 4;
+      cudaEventRecord(P.ev_run[w], stream);
+      if (prev >= 0) { const int r2 = copy_home(prev); if (r2) return r2; }
+      prev = w;
     }
-    // device-side exclusive scan of the frame sizes, pack, and two copies home: offsets first (they size the second)
-    if (b200zstd::launch_scan_sizes(reinterpret_cast<const size_t *>(d_tab + 3 * n * 8), n, 0, d_offsets, stream) != cudaSuccess) return 4;
-    if (b200zstd::launch_pack(reinterpret_cast<const void *const *>(d_tab + 2 * n * 8), reinterpret_cast<const size_t *>(d_tab + 3 * n * 8), d_offsets, n,
-                              d + packed_base, stream) != cudaSuccess) return 4;
-    launches += 2;
     std::vector<u32> st(n);
     cudaMemcpyAsync(h_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, stream);
     cudaMemcpyAsync(st.data(), d_status, n * 4, cudaMemcpyDeviceToHost, stream);
+    if (prev >= 0) { const int r2 = copy_home(prev); if (r2) return r2; }
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return 4;
+    if ((e = cudaStreamSynchronize(P.s_out)) != cudaSuccess) return 4;
     I->last_launches = launches;
     if (overall != Status::SUCCESS) return status_to_nvcomp_error(overall);
+    if (rc_cap) return rc_cap;
     int rc = 0;
     for (size_t i = 0; i < n; i++) {
       if (h_status) h_status[i] = st[i];
       if (st[i] != 0 && rc == 0) rc = 1;
     }
-    if (h_offsets[n] > packed_cap) return 7;
-    if ((e = cudaMemcpyAsync(h_packed, d + packed_base, (size_t)h_offsets[n], cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return 4;
-    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return 4;
     return rc;
   } catch (...) { return 1; }
 }

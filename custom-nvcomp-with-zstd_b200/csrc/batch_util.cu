@@ -14,11 +14,11 @@ constexpr int SCAN_THREADS = 1024;
 // scan, one SMEM pass across the 32 warp totals.  N <= a few hundred thousand sizes, so a single CTA
 // (one pass over <= 1 MiB) is launch-latency-, not bandwidth-, bound.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_sizes_kernel(const size_t *__restrict__ sizes, size_t n, uint64_t base,
-                                                                  uint64_t *__restrict__ offsets) {
+                                                                  uint64_t *offsets, const uint64_t *base_ptr) {
   __shared__ uint64_t warp_tot[32];
   __shared__ uint64_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = base;
+  if (tid == 0) carry_s = base_ptr ? *base_ptr : base;        // (base_ptr may be offsets[0]: read before anything is written)
   __syncthreads();
   for (size_t t0 = 0; t0 < n; t0 += SCAN_THREADS) {
     const size_t i = t0 + tid;
@@ -113,7 +113,13 @@ cudaError_t launch_big_result(const uint32_t *d_statuses, size_t n, const uint64
 }
 
 cudaError_t launch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream) {
-  scan_sizes_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_sizes, n, base, d_offsets);
+  scan_sizes_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_sizes, n, base, d_offsets, nullptr);
+  return cudaGetLastError();
+}
+// the same with the base taken from device memory: chains the scans of consecutive ranges (d_base = the previous range's
+// closing offset, which is this range's d_offsets[0])
+cudaError_t launch_scan_sizes_from(const size_t *d_sizes, size_t n, const uint64_t *d_base, uint64_t *d_offsets, cudaStream_t stream) {
+  scan_sizes_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_sizes, n, 0, d_offsets, d_base);
   return cudaGetLastError();
 }
 cudaError_t launch_pack(const void *const *d_ptrs, const size_t *d_sizes, const uint64_t *d_offsets, size_t n, void *d_packed,

@@ -124,6 +124,7 @@ cudaError_t launch_big_result(const uint32_t *d_statuses, size_t n, const uint64
                               cudaStream_t stream);
 // exclusive scan of sizes (+ base) -> offsets[0..n], offsets[n] = base + total; single CTA.
 cudaError_t launch_scan_sizes(const size_t *d_sizes, size_t n, uint64_t base, uint64_t *d_offsets, cudaStream_t stream);
+cudaError_t launch_scan_sizes_from(const size_t *d_sizes, size_t n, const uint64_t *d_base, uint64_t *d_offsets, cudaStream_t stream);
 // gather frames into a packed buffer
 cudaError_t launch_pack(const void *const *d_ptrs, const size_t *d_sizes, const uint64_t *d_offsets, size_t n, void *d_packed,
                         cudaStream_t stream);
