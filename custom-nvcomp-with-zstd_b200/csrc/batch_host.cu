@@ -342,7 +342,7 @@ public:
   }
   // decode workspace: header | staged tables | slow list | general-kernel literal scratch | fast-path slots
   static size_t wave_of(size_t n) { return std::min<size_t>(n, b200zstd::FAST_WAVE); }
-  static size_t slow_list_bytes(size_t n) { return align_up(wave_of(n) * 4, 256); }
+  static size_t slow_list_bytes(size_t n) { return align_up(wave_of(n) * 8, 256); }      // slow list / KA order, then KC's order
   size_t general_scratch_bytes(size_t n) const { return align_up((size_t)dec_grid(n) * b200zstd::LIT_SCRATCH_BYTES, 256); }
   size_t dec_fixed(size_t n) const {
     return b200zstd::WS_HEADER_BYTES + table_bytes(n) + slow_list_bytes(n) + general_scratch_bytes(n) +
@@ -585,7 +585,9 @@ public:
         f.slow_list = reinterpret_cast<u32 *>(slow_list);
         f.slow_count = counter + 16;
         f.group_counters = counter + 48;
-        f.lit_buckets = counter + 60;               // 65 words, inside the 512-byte header
+        f.lit_buckets = counter + 60;               // 65 words
+        f.seq_buckets = counter + 128;              // FAST_ORDER_SUBS x 64 words (the header is 2 KB)
+        f.kc_order = reinterpret_cast<u32 *>(slow_list) + wave_of(n);
         f.sm_count = sm_count;
         f.general_grid = dec_grid(m);
         f.bare_blocks = bare_mode ? 1u : 0u;

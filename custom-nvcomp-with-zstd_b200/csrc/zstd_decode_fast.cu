@@ -34,7 +34,7 @@ namespace b200zstd {
 
 // KA takes the Huffman chunks in descending order of literal count (buckets of 2 KB, counting sort: KP ranks, the order kernel
 // places), so that the streams a group decodes side by side are of one length and the long ones start first.
-constexpr uint32_t KA_BUCKETS = 64, KA_BUCKET_SHIFT = 11;
+constexpr uint32_t KA_BUCKETS = 64, KA_BUCKET_SHIFT = 11, KC_BUCKET_SHIFT = 7;      // (KC: buckets of 128 sequences, the same sort per sub-wave)
 struct __align__(16) FastDesc {
   uint32_t state;        // 0 fast path continues, 1 finished in prep, 2 routed to the general kernel
   uint32_t status;
@@ -59,6 +59,7 @@ struct __align__(16) FastDesc {
   uint32_t lit_status[4];                     // written by the Huffman threads
   uint32_t lit_slot, seq_slot;                // pool offsets in 16-byte units
   uint32_t ka_key;                            // Huffman chunks: literal-count bucket << 16 | rank inside the bucket (KA's work order)
+  uint32_t kc_key;                            // every chunk: sequence-count bucket << 16 | rank inside the bucket of its sub-wave (KC's work order)
 };
 // The tail of the descriptor area holds KC's per-chunk hand-over words: [0] parts of the chunk executed so far, [1] the status
 // the finished parts arrived at (zeroed by KP; see zstd_fast_exec_kernel).
@@ -319,6 +320,11 @@ __device__ __forceinline__ void prep_chunk(const FastDecodeArgs &F, uint32_t chu
         if (A.statuses) A.statuses[chunk] = status;
       } else D.state = 0;
       D.status = status;
+      if (F.kc_order) {
+        // KC takes the chunks of a sub-wave heaviest first (a chunk's parts are a serial chain: the long chains must start early)
+        const uint32_t sb = D.state == 0 ? min(D.nseq >> KC_BUCKET_SHIFT, KA_BUCKETS - 1u) : 0u;
+        D.kc_key = (sb << 16) | atomicAdd(F.seq_buckets + (chunk / F.sub_chunks) * KA_BUCKETS + sb, 1u);
+      }
       *slot.desc() = D;
     }
     __syncwarp();
@@ -391,6 +397,12 @@ __global__ void __launch_bounds__(256) zstd_fast_order_kernel(FastDecodeArgs F) 
   const uint32_t chunk = blockIdx.x * 256 + threadIdx.x;
   if (chunk >= F.base.n) return;
   const FastDesc *const D = slot_of(F, chunk).desc();
+  if (F.kc_order) {
+    const uint32_t key = D->kc_key, b = key >> 16, sub = chunk / F.sub_chunks;
+    uint32_t first = 0;
+    for (uint32_t k = KA_BUCKETS - 1; k > b; k--) first += F.seq_buckets[sub * KA_BUCKETS + k];
+    F.kc_order[sub * F.sub_chunks + first + (key & 0xFFFFu)] = chunk;
+  }
   if (D->state != 0 || D->lit_type != 2) return;
   const uint32_t key = D->ka_key;
   F.slow_list[F.base.n - 1 - (start[key >> 16] + (key & 0xFFFFu))] = chunk;
@@ -959,7 +971,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 9) zstd_fast_exec_kernel(Fast
     if (lane == 0) item = atomicAdd(queue, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= span * (F.part_hi - F.part_lo)) break;
-    const uint32_t part = F.part_lo + item / span, chunk = F.lo + item % span;
+    const uint32_t part = F.part_lo + item / span, chunk = F.kc_order ? F.kc_order[F.lo + item % span] : F.lo + item % span;
     ChunkSlot slot = slot_of(F, chunk);
     const FastDesc *D = slot.desc();
     if (D->state != 0) continue;
@@ -1306,6 +1318,8 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   // one memset zeroes every counter of the pipeline: general work queue, slow count, pool heads, group counters
   if ((e = cudaMemsetAsync(F.base.counter, 0, WS_HEADER_BYTES, stream)) != cudaSuccess) return e;
   const uint32_t sms = (uint32_t)(F.sm_count > 0 ? F.sm_count : 148);
+  F.sub_chunks = ov ? sms * KB_GROUP : n;                                  // (without the side stream the wave is one KB / KC pass)
+  if ((n + F.sub_chunks - 1) / F.sub_chunks > FAST_ORDER_SUBS) F.kc_order = nullptr;
   const uint32_t kp_blocks = (n + KP_WARPS - 1) / KP_WARPS;
   zstd_fast_prep_kernel<<<kp_blocks < 5 * sms ? kp_blocks : 5 * sms, KP_WARPS * 32, 0, stream>>>(F);
   mark("KP", stream);

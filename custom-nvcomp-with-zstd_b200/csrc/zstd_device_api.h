@@ -9,7 +9,7 @@
 namespace b200zstd {
 
 constexpr size_t LIT_SCRATCH_BYTES = 128 * 1024 + 256;   // per in-flight chunk: one block's literals
-constexpr size_t WS_HEADER_BYTES = 512;                   // work counters etc. at the start of the workspace
+constexpr size_t WS_HEADER_BYTES = 2048;                   // work counters etc. at the start of the workspace
 
 // All pointers are DEVICE memory.  out_sizes: in = capacity, out = bytes produced (0 on failure).
 struct DecodeArgs {
@@ -31,6 +31,7 @@ int decode_ctas_per_sm();
 
 // ---- batch fast path: three kernels over the whole batch (zstd_decode_fast.cu) --------------------
 constexpr uint32_t FAST_WAVE = 16384;                         // chunks per fast-path wave (bounds the scratch)
+constexpr uint32_t FAST_ORDER_SUBS = 4;                       // KC's work order is built for up to this many sub-waves per wave
 constexpr uint32_t FAST_SEQ_CAP = 65536;                      // sequences per chunk the fast path accepts
 constexpr size_t FAST_TABLE_BYTES = 64 + 4096 + 3840;         // sequence-stream info, Huffman table, packed LL/ML/OF tables (KP -> KA, KB)
 constexpr size_t FAST_DESC_BYTES = 192;
@@ -48,6 +49,9 @@ struct FastDecodeArgs {
   uint32_t *slow_count;     // 1 entry, zeroed by the launcher
   uint32_t *group_counters; // [0] literal kernel, [1] sequence kernel work queues; zeroed by the launcher
   uint32_t *lit_buckets;    // 64 counters + [64] their sum: Huffman chunks by literal count (KP -> order kernel -> KA); zeroed by the launcher
+  uint32_t *seq_buckets;    // FAST_ORDER_SUBS x 64 counters: chunks of a KB sub-wave by sequence count (KP -> order kernel -> KC's queue)
+  uint32_t *kc_order;       // n entries: the chunks of every sub-wave, most sequences first; null = chunk order
+  uint32_t sub_chunks;      // chunks per KB sub-wave (set by the launcher)
   int general_grid;
   int sm_count;
   uint32_t lo, hi, sub;     // set by the launcher: chunk sub-range and work-queue index of a KB / KC launch
