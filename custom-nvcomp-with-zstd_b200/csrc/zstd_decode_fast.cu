@@ -703,9 +703,9 @@ struct SeqLane {                                      // one lane's decoder stat
 // `lead`: see fast_decode_huffman.  `unknown_history`: a block unit other than the first of its frame starts with repeat
 // offsets nobody knows yet; sentinels far above any legal offset make every use of them fail KC's range check, which
 // sends the whole frame to the serial decoder
-// `seg` of `segs` (FastDecodeArgs::seq_seg / seq_segs): decode only the sequences of KC's parts [seg P / segs, (seg + 1) P / segs),
-// P = EXEC_PARTS; a segment that is not the last leaves the chain's state in the slot (behind SeqInfo) and, at the index it
-// stopped at, a record with the positions reached, which ends KC's last literal run; a later segment picks the state up.
+// [part_lo, part_hi) (FastDecodeArgs): decode only the sequences of those KC parts, P = EXEC_PARTS in all; a launch that does not
+// reach the last part leaves the chain's state in the slot (behind SeqInfo) and, at the index it stopped at, a record with the
+// positions reached, which ends KC's last literal run; a launch that does not start at part 0 picks the state up.
 #ifndef EXEC_PARTS_V
 #define EXEC_PARTS_V 8
 #endif
@@ -713,12 +713,13 @@ constexpr uint32_t EXEC_PARTS = EXEC_PARTS_V;     // KC's work items per chunk (
 struct SeqSave { int t; uint32_t sl, sm, so, rep0, rep1, rep2, out_pos, lit_pos, err; };
 static_assert(sizeof(SeqInfo) + sizeof(SeqSave) <= 64, "the slot reserves 64 bytes for SeqInfo + SeqSave");
 __device__ __forceinline__ void fast_decode_sequences(const uint8_t *src, FastDesc *D, uint4 *out, const SeqTab T, const uint32_t *bases,
-                                                      const SeqInfo &I, uint32_t lead, bool unknown_history, uint32_t seg, uint32_t segs, SeqSave *save) {
+                                                      const SeqInfo &I, uint32_t lead, bool unknown_history, uint32_t part_lo, uint32_t part_hi, SeqSave *save) {
   const uint32_t nseq = D->nseq;
   const uint32_t groups = (nseq + 31) >> 5;
   // first sequence of KC part p (< nseq for p < P: a segment that is not the last never reaches the last sequence)
   auto part_begin = [&](uint32_t p) { return p >= EXEC_PARTS ? nseq : min(nseq, (groups * p / EXEC_PARTS) << 5); };
-  const uint32_t begin = part_begin(seg * EXEC_PARTS / segs), end = seg + 1 == segs ? nseq : part_begin((seg + 1) * EXEC_PARTS / segs);
+  const uint32_t begin = part_begin(part_lo), end = part_begin(part_hi);
+  const uint32_t seg = part_lo;                       // != 0: the chain's state is picked up from the slot
   uint32_t err = ST_OK;
   SeqLane L;
   L.out_pos = 0; L.lit_pos = 0;
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(32 * KB_DEC_WARPS, 1) zstd_fast_seq_kernel(Fas
     if (mine && info.ready) {
       const SeqTab T{tab16 + (size_t)c * 1280, tab8 + (size_t)c * 1280};
       fast_decode_sequences((const uint8_t *)A.in_ptrs[g0 + c], slot.desc(), slot.seqs(), T, bases, info, F.bare_blocks ? 6u : 0u,
-                            F.bare_blocks && (F.unit_base + g0 + c) != 0, F.seq_seg, F.seq_segs,
+                            F.bare_blocks && (F.unit_base + g0 + c) != 0, F.part_lo, F.part_hi,
                             reinterpret_cast<SeqSave *>(slot.seq_info() + sizeof(SeqInfo)));
     }
   }
@@ -1308,7 +1309,7 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
   }
   FastDecodeArgs F = F0;
   F.lo = 0; F.hi = n; F.sub = 0;
-  F.seq_seg = 0; F.seq_segs = 1; F.part_lo = 0; F.part_hi = EXEC_PARTS; F.kb_queue = 1; F.kc_queue = 2;
+  F.part_lo = 0; F.part_hi = EXEC_PARTS; F.kb_queue = 1; F.kc_queue = 2;
   // CUDA_ZSTD_TRACE=1: events after every launch, printed as "kernel@ms since the call began" once the call has drained
   // (a debugging aid: it synchronises the stream; this is how the KB / KC overlap in DESIGN.md 4.1 was timed)
   static const bool trace = getenv("CUDA_ZSTD_TRACE") != nullptr;
@@ -1354,14 +1355,27 @@ cudaError_t launch_decode_fast(const FastDecodeArgs &F0, cudaStream_t stream, co
     static const uint32_t split_env = getenv("CUDA_ZSTD_KB_SPLIT") ? (uint32_t)atoi(getenv("CUDA_ZSTD_KB_SPLIT")) : 0u;
     uint32_t S = split_env ? split_env : nsub == 1 ? KB_SPLIT_ONE_SUBWAVE : KB_SPLIT_DEFAULT;
     if (S > EXEC_PARTS) S = EXEC_PARTS;
-    while (S > 1 && (S * nsub > (uint32_t)FastOverlap::MAX_SUB || EXEC_PARTS % S)) S--;
+    while (S > 1 && S * nsub > (uint32_t)FastOverlap::MAX_SUB) S--;
+    // part boundaries of the segments: equal shares, or CUDA_ZSTD_KB_BOUNDS="0,2,5,8" (S + 1 ascending numbers, 0 .. EXEC_PARTS)
+    uint32_t bounds[EXEC_PARTS + 1];
+    for (uint32_t h = 0; h <= S; h++) bounds[h] = h * EXEC_PARTS / S;
+    // several sub-waves: a short first segment lets KC start early, measured best of {0,4,8}, {0,3,8}, {0,2,5,8}, {0,3,6,8},
+    // {0,2,4,6,8}, {0,1,3,5,8} on the mixed batch (4.41, 4.35, 4.26, 4.44, 4.37, 4.30 ms) and level on the uniform one (3.89 - 3.96)
+    if (!split_env && nsub > 1 && EXEC_PARTS == 8 && 3 * nsub <= (uint32_t)FastOverlap::MAX_SUB) { S = 3; bounds[0] = 0; bounds[1] = 2; bounds[2] = 5; bounds[3] = 8; }
+    static const char *const bounds_env = getenv("CUDA_ZSTD_KB_BOUNDS");
+    if (bounds_env) {
+      uint32_t b[EXEC_PARTS + 1], nb = 0;
+      for (const char *p = bounds_env; *p && nb <= EXEC_PARTS;) { b[nb++] = (uint32_t)strtoul(p, nullptr, 10); while (*p && *p != ',') p++; if (*p) p++; }
+      bool ok = nb >= 2 && b[0] == 0 && b[nb - 1] == EXEC_PARTS && (nb - 1) * nsub <= (uint32_t)FastOverlap::MAX_SUB;
+      for (uint32_t h = 1; h < nb && ok; h++) ok = b[h] > b[h - 1];
+      if (ok) { S = nb - 1; for (uint32_t h = 0; h <= S; h++) bounds[h] = b[h]; }
+    }
     for (uint32_t k = 0; k < nsub; k++) {
       F.lo = k * sub_chunks; F.hi = F.lo + sub_chunks < n ? F.lo + sub_chunks : n; F.sub = k;
       const uint32_t m = F.hi - F.lo, kb_groups = (m + KB_GROUP - 1) / KB_GROUP;
       for (uint32_t h = 0; h < S; h++) {
         const uint32_t q = S * k + h;
-        F.seq_seg = h; F.seq_segs = S;
-        F.part_lo = h * EXEC_PARTS / S; F.part_hi = (h + 1) * EXEC_PARTS / S;
+        F.part_lo = bounds[h]; F.part_hi = bounds[h + 1];
         F.kb_queue = 1 + q; F.kc_queue = S > 1 ? 20 + q : 2 + q;
         launch_kb(kb_warps, kb_groups < sms ? kb_groups : sms, stream, F);
         mark(h ? "KBb" : "KB", stream);

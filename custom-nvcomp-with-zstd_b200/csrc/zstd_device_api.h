@@ -55,10 +55,10 @@ struct FastDecodeArgs {
   int general_grid;
   int sm_count;
   uint32_t lo, hi, sub;     // set by the launcher: chunk sub-range and work-queue index of a KB / KC launch
-  // ... and, when a sub-wave's sequences are decoded in seq_segs > 1 KB launches so that KC can start on the first parts of
-  // every chunk while KB decodes the later ones: this launch decodes segment seq_seg (the chain's state waits in the slot
-  // in between); KC executes parts [part_lo, part_hi); kb_queue / kc_queue = this launch's work counters (header words)
-  uint32_t seq_seg, seq_segs, part_lo, part_hi, kb_queue, kc_queue;
+  // ... and, when a sub-wave's sequences are decoded in several KB launches so that KC can start on the first parts of every
+  // chunk while KB decodes the later ones: this KB launch decodes the sequences of parts [part_lo, part_hi) (the chain's state
+  // waits in the slot in between) and the KC launch behind it executes them; kb_queue / kc_queue = the launches' work counters
+  uint32_t part_lo, part_hi, kb_queue, kc_queue;
   // bare-block mode (a multi-block frame cut into units by launch_split_frame): every item starts at a block header,
   // must regenerate exactly its capacity, and -- except global unit 0 -- starts with an unknown repeat-offset history
   uint32_t bare_blocks, unit_base;
