@@ -774,8 +774,35 @@ struct FinArgs {
 __host__ __device__ constexpr size_t fin_warp_scratch(uint32_t block_max) { return ((size_t)block_max + 64 + (size_t)3 * (block_max / 4 + 64) * 4 + 255) & ~(size_t)255; }
 
 // copies n bytes src -> dst with the whole warp (dst and src are unrelated in alignment)
+// Long runs (a literal-only block is one run of 64 KB) go as 16-byte stores fed by aligned 32-bit loads and funnel shifts,
+// two vectors per lane in flight; the last vector is left to the byte loop so that no word past src + n is read.
 __device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
-  for (uint32_t i = (uint32_t)lane; i < n; i += 32) dst[i] = src[i];
+  uint32_t done = 0;
+  if (n >= 512) {
+    const uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    for (uint32_t i = (uint32_t)lane; i < head; i += 32) dst[i] = src[i];
+    const uint8_t *const s0 = src + head;
+    const uint32_t sh = (uint32_t)((uintptr_t)s0 & 3) * 8;
+    const uint32_t *const w = reinterpret_cast<const uint32_t *>((uintptr_t)s0 & ~(uintptr_t)3);
+    uint4 *const d4 = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t vecs = ((n - head) >> 4) - 1;
+    uint32_t j = (uint32_t)lane;
+    for (; j + 32 < vecs; j += 64) {
+      uint32_t a[5], b[5];
+#pragma unroll
+      for (int q = 0; q < 5; q++) { a[q] = w[4 * j + q]; b[q] = w[4 * (j + 32) + q]; }
+      d4[j] = make_uint4(__funnelshift_r(a[0], a[1], sh), __funnelshift_r(a[1], a[2], sh), __funnelshift_r(a[2], a[3], sh), __funnelshift_r(a[3], a[4], sh));
+      d4[j + 32] = make_uint4(__funnelshift_r(b[0], b[1], sh), __funnelshift_r(b[1], b[2], sh), __funnelshift_r(b[2], b[3], sh), __funnelshift_r(b[3], b[4], sh));
+    }
+    for (; j < vecs; j += 32) {
+      uint32_t a[5];
+#pragma unroll
+      for (int q = 0; q < 5; q++) a[q] = w[4 * j + q];
+      d4[j] = make_uint4(__funnelshift_r(a[0], a[1], sh), __funnelshift_r(a[1], a[2], sh), __funnelshift_r(a[2], a[3], sh), __funnelshift_r(a[3], a[4], sh));
+    }
+    done = head + 16 * vecs;
+  }
+  for (uint32_t i = done + (uint32_t)lane; i < n; i += 32) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(32 * FIN_WARPS, 8) zstd_lz_finish_kernel(FinArgs F) {
