@@ -173,7 +173,16 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
           const uint32_t piece = (cnt + per - 1) / per;
           const uint32_t lo = min(cnt, m * piece), hi = min(cnt, lo + piece);
           uint32_t bits = 0;
-          for (uint32_t i = lo; i < hi; i++) bits += W.hufc[lits[b0 + i]] >> 16;
+          {
+            // (four literals per load: every lane walks its own piece, and byte loads from 128 pieces per CTA thrash the L1)
+            uint32_t i = lo;
+            for (; i < hi && ((uintptr_t)(lits + b0 + i) & 3u); i++) bits += W.hufc[lits[b0 + i]] >> 16;
+            for (; i + 4 <= hi; i += 4) {
+              const uint32_t w = *reinterpret_cast<const uint32_t *>(lits + b0 + i);
+              bits += (W.hufc[w & 0xFF] >> 16) + (W.hufc[(w >> 8) & 0xFF] >> 16) + (W.hufc[(w >> 16) & 0xFF] >> 16) + (W.hufc[w >> 24] >> 16);
+            }
+            for (; i < hi; i++) bits += W.hufc[lits[b0 + i]] >> 16;
+          }
           // suffix sum over the lanes of my stream that hold later symbols (higher m)
           uint32_t after = 0, total = bits;
           for (uint32_t o = 1; o < per; o <<= 1) {
@@ -222,15 +231,22 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
             uint64_t acc = 0;
             bool first = true;
             if (k < nstreams) {
-              for (uint32_t i = hi; i > lo; i--) {
-                const uint32_t c = W.hufc[lits[b0 + i - 1]];
-                acc |= (uint64_t)(c & 0xFFFF) << nacc;
-                nacc += c >> 16;
+              auto emit = [&](uint32_t sym) { const uint32_t c = W.hufc[sym]; acc |= (uint64_t)(c & 0xFFFF) << nacc; nacc += c >> 16; };
+              auto flush = [&]() {
                 if (nacc >= 32) {
                   if (first) { atomicOr(w32 + wi, (uint32_t)acc); first = false; } else w32[wi] = (uint32_t)acc;
                   wi++; acc >>= 32; nacc -= 32;
                 }
+              };
+              // last symbol first; four literals per load, a word check every two symbols (31 + 2 x 11 bits fit the accumulator)
+              uint32_t i = hi;
+              for (; i > lo && ((uintptr_t)(lits + b0 + i) & 3u); i--) { emit(lits[b0 + i - 1]); flush(); }
+              for (; i >= lo + 4; i -= 4) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(lits + b0 + i - 4);
+                emit(w >> 24); emit((w >> 16) & 0xFF); flush();
+                emit((w >> 8) & 0xFF); emit(w & 0xFF); flush();
               }
+              for (; i > lo; i--) { emit(lits[b0 + i - 1]); flush(); }
               if (m == 0) { acc |= 1ull << nacc; nacc++; }           // end mark behind the stream's first symbol
               if (nacc >= 32) {
                 if (first) { atomicOr(w32 + wi, (uint32_t)acc); first = false; } else w32[wi] = (uint32_t)acc;
