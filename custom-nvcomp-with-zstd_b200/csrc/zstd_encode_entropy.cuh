@@ -239,12 +239,20 @@ static __device__ uint32_t entropy_stage_warp(EntropyWs &W, const uint8_t *lits,
                 }
               };
               // last symbol first; four literals per load, a word check every two symbols (31 + 2 x 11 bits fit the accumulator)
+              // (eight literals per load, the next load in flight while these are coded)
               uint32_t i = hi;
-              for (; i > lo && ((uintptr_t)(lits + b0 + i) & 3u); i--) { emit(lits[b0 + i - 1]); flush(); }
-              for (; i >= lo + 4; i -= 4) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(lits + b0 + i - 4);
-                emit(w >> 24); emit((w >> 16) & 0xFF); flush();
-                emit((w >> 8) & 0xFF); emit(w & 0xFF); flush();
+              for (; i > lo && ((uintptr_t)(lits + b0 + i) & 7u); i--) { emit(lits[b0 + i - 1]); flush(); }
+              if (i >= lo + 8) {
+                uint2 cur = *reinterpret_cast<const uint2 *>(lits + b0 + i - 8);
+                for (; i >= lo + 8; i -= 8) {
+                  uint2 nxt = cur;
+                  if (i >= lo + 16) nxt = *reinterpret_cast<const uint2 *>(lits + b0 + i - 16);
+                  emit(cur.y >> 24); emit((cur.y >> 16) & 0xFF); flush();
+                  emit((cur.y >> 8) & 0xFF); emit(cur.y & 0xFF); flush();
+                  emit(cur.x >> 24); emit((cur.x >> 16) & 0xFF); flush();
+                  emit((cur.x >> 8) & 0xFF); emit(cur.x & 0xFF); flush();
+                  cur = nxt;
+                }
               }
               for (; i > lo; i--) { emit(lits[b0 + i - 1]); flush(); }
               if (m == 0) { acc |= 1ull << nacc; nacc++; }           // end mark behind the stream's first symbol

@@ -778,7 +778,7 @@ __host__ __device__ constexpr size_t fin_warp_scratch(uint32_t block_max) { retu
 // two vectors per lane in flight; the last vector is left to the byte loop so that no word past src + n is read.
 __device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
   uint32_t done = 0;
-  if (n >= 512) {
+  if (n >= 128) {
     const uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     for (uint32_t i = (uint32_t)lane; i < head; i += 32) dst[i] = src[i];
     const uint8_t *const s0 = src + head;
